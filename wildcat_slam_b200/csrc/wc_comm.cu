@@ -1,0 +1,172 @@
+// Multi-GPU residual sharding: one process per GPU, correspondences block-partitioned over the ranks,
+// and the packed normal equations [J^T J | J^T r | cost] summed across ranks once per linearisation.
+//
+// The reduction is a one-shot all-reduce over NVLink peer memory inside our own kernel (no host round trip, no library
+// call on the iteration path): every rank's linearisation kernels accumulate into that rank's exchange buffer, which is
+// exported with cudaIpcGetMemHandle and mapped by all peers.  comm_allreduce then
+//   1. publishes "my partial for epoch e is complete" by storing e into flag[my_rank] of every peer (remote st.global),
+//   2. waits until all of its own flags reached e (local spin, bounded by a clock64 timeout so a dead peer can never
+//      hang the GPU),
+//   3. sums the partials of ranks 0..G-1 in rank order with peer ld.volatile.global loads — the same order on every
+//      rank, so all ranks hold bitwise identical normal equations and take bitwise identical LM steps (the replicated
+//      lm_* kernels then need no broadcast).
+// Partials are double-buffered by epoch parity: a rank can start epoch e+2 only after every peer signalled e+1, i.e.
+// after every peer finished reading epoch e, so one flag round per reduction suffices.
+#include "wc_ctx.h"
+
+void wc_solve_exchange_views(wc_ctx* c, int which, double** H, double** g, double** cost, int* N, void** state);
+
+namespace {
+
+struct CommArgs {
+  unsigned long long* my_flags;        // local: flags[rank of writer]
+  unsigned long long* peer_flags[8];   // remote flag arrays
+  const double*       part[8];         // partial buffers of this epoch's parity, by rank (own entry local)
+  double*             H[2];
+  double*             g[2];
+  double*             cost[2];
+  const int*          state;           // LMState: cur @0, done @1, ..., step_valid @4 (see wc_solve.cu)
+  int*                err;
+  unsigned long long  epoch;
+  int                 rank, world, N, at_candidate;
+  long long           timeout_cycles;
+};
+
+__global__ void __launch_bounds__(256) comm_allreduce(CommArgs a) {
+  const int cur = a.state[0], done = a.state[1], step_valid = a.state[4];
+  if (done || (a.at_candidate && !step_valid)) return;  // replicated state: every rank takes the same branch
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    *((volatile unsigned long long*)&a.peer_flags[threadIdx.x][a.rank]) = a.epoch;
+  }
+  if (threadIdx.x < a.world) {
+    const long long t0 = clock64();
+    while (*((volatile unsigned long long*)&a.my_flags[threadIdx.x]) < a.epoch) {
+      if (clock64() - t0 > a.timeout_cycles) {
+        *a.err = WC_ECOMM;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const int    buf   = a.at_candidate ? 1 - cur : cur;
+  const size_t nH    = (size_t)a.N * a.N;
+  const size_t total = nH + a.N + 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; ++r) s += *((const volatile double*)&a.part[r][i]);
+    if (i < nH) a.H[buf][i] = s;
+    else if (i < nH + a.N) a.g[buf][i - nH] = s;
+    else *a.cost[buf] = s;
+  }
+}
+
+}  // namespace
+
+static size_t part_doubles(const wc_ctx* c) {
+  const size_t N = 12 * (size_t)c->prm.max_samples;
+  return N * N + N + 2;
+}
+
+static wc_status comm_alloc(wc_ctx* c) {
+  if (c->d_xchg) return WC_OK;
+  c->xchg_bytes = 256 + 2 * part_doubles(c) * 8;
+  WC_CUDA(c, cudaMalloc(&c->d_xchg, c->xchg_bytes));
+  WC_CUDA(c, cudaMemset(c->d_xchg, 0, c->xchg_bytes));
+  WC_CUDA(c, cudaMalloc(&c->d_comm_err, 4));
+  WC_CUDA(c, cudaMemset(c->d_comm_err, 0, 4));
+  return WC_OK;
+}
+
+void wc_comm_free(wc_ctx* c) {
+  if (c->comm_ready) {
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer_xchg[r]) cudaIpcCloseMemHandle(c->peer_xchg[r]);
+  }
+  if (c->d_xchg) cudaFree(c->d_xchg);
+  if (c->d_comm_err) cudaFree(c->d_comm_err);
+  c->d_xchg = nullptr, c->d_comm_err = nullptr, c->comm_ready = 0, c->world = 1, c->rank = 0;
+}
+
+extern "C" wc_status wc_comm_export(wc_ctx* c, uint8_t handle[WC_IPC_HANDLE_BYTES]) {
+  if (!c || !handle) return WC_EINVAL;
+  wc_status s = comm_alloc(c);
+  if (s) return s;
+  static_assert(sizeof(cudaIpcMemHandle_t) == WC_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  WC_CUDA(c, cudaIpcGetMemHandle(&h, c->d_xchg));
+  memcpy(handle, &h, sizeof(h));
+  return WC_OK;
+}
+
+extern "C" wc_status wc_comm_connect(wc_ctx* c, int rank, int world, const uint8_t* all_handles) {
+  if (!c || !all_handles || world < 1 || world > 8 || rank < 0 || rank >= world) return WC_EINVAL;
+  wc_status s = comm_alloc(c);
+  if (s) return s;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      c->peer_xchg[r] = c->d_xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + (size_t)r * WC_IPC_HANDLE_BYTES, sizeof(h));
+    void*       p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) WC_FAIL(c, WC_ECOMM, "cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+    c->peer_xchg[r] = (double*)p;
+  }
+  c->rank = rank, c->world = world, c->comm_ready = 1, c->comm_epoch = 0;
+  return WC_OK;
+}
+
+extern "C" wc_status wc_comm_disconnect(wc_ctx* c) {
+  if (!c) return WC_EINVAL;
+  cudaStreamSynchronize(c->stream);
+  wc_comm_free(c);
+  return WC_OK;
+}
+
+// where this rank's linearisation kernels must accumulate for the next reduction (world > 1)
+void wc_comm_partial_views(wc_ctx* c, double** H, double** g, double** cost) {
+  const size_t N   = 12 * c->K;
+  const int    par = (int)((c->comm_epoch + 1) & 1);
+  double*      p   = (double*)((char*)c->d_xchg + 256) + (size_t)par * part_doubles(c);
+  *H = p, *g = p + N * N, *cost = p + N * N + N;
+}
+
+wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate) {
+  if (c->world <= 1) return WC_OK;
+  if (!c->comm_ready) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
+  c->comm_epoch += 1;
+  CommArgs a;
+  memset(&a, 0, sizeof(a));
+  const int par = (int)(c->comm_epoch & 1);
+  a.my_flags    = (unsigned long long*)c->d_xchg;
+  for (int r = 0; r < c->world; ++r) {
+    a.peer_flags[r] = (unsigned long long*)c->peer_xchg[r];
+    a.part[r]       = (const double*)((char*)c->peer_xchg[r] + 256) + (size_t)par * part_doubles(c);
+  }
+  void* state = nullptr;
+  wc_solve_exchange_views(c, 0, a.H, a.g, a.cost, &a.N, &state);
+  a.state = (const int*)state, a.err = c->d_comm_err;
+  a.epoch = c->comm_epoch, a.rank = c->rank, a.world = c->world, a.at_candidate = at_candidate;
+  a.timeout_cycles = 4000000000ll;  // ~2 s at 2 GHz
+  const size_t total = (size_t)a.N * a.N + a.N + 1;
+  int          grid  = (int)((total + 255) / 256);
+  if (grid > 64) grid = 64;
+  comm_allreduce<<<grid, 256, 0, c->stream>>>(a);
+  WC_CUDA(c, cudaGetLastError());
+  return WC_OK;
+}
+
+wc_status wc_comm_check(wc_ctx* c) {
+  if (c->world <= 1 || !c->d_comm_err) return WC_OK;
+  int e = 0;
+  WC_CUDA(c, cudaMemcpy(&e, c->d_comm_err, 4, cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemset(c->d_comm_err, 0, 4);
+    WC_FAIL(c, WC_ECOMM, "peer exchange timed out (a rank did not reach the reduction)");
+  }
+  return WC_OK;
+}

@@ -1,0 +1,819 @@
+// Surfel extraction on the device — replaces BuildSurfels / BuildVoxelMap / OctoTree::{InitOctoTree, CutOctoTree,
+// InitPlane, ExtractSurfelInfo} / ClusterSurfels (src/odometry/surfel_extraction.cc:12-65,82-220,304-337).
+//
+//   K0 repack_points        48-byte hilti_ros::Point records -> float4 xyz + double t (resident layout)
+//   K1 voxel_key_moments    per point: VoxelLoc (fp64 floor(p/(double)0.8f)), two octree child codes, time bin;
+//                           open-addressed hash of (voxel, leaf cell, time bin) -> slot; exact int64 moments by
+//                           native RED atomics after warp-level aggregation of equal keys
+//   K2a..c voxel_index / scan / scatter     group the occupied slots by voxel
+//   K2  cluster_eig_emit    per voxel: octree levels from additive moments, planarity flags, exact time clusters
+//                           (gap test on the original fp64 timestamps), 3x3 Jacobi eigen-solve, Surfel records
+//   K2s bitonic sort        final order by (timestamp, resolution desc, center.x)  (surfel_extraction.cc:334)
+//
+// Exactness: the time clusters of a node are maximal runs of its time-ordered points with consecutive gaps
+// <= 0.05 s (surfel_extraction.cc:22-29).  Points sharing a 2^-5 s bin can never be split (spread < gap), and a
+// boundary between consecutive non-empty bins exists iff t_min(next) - t_max(prev) > gap — the same fp64
+// subtraction on the same two operands the reference performs, because those two points are consecutive in the
+// node's time-ordered list.
+#include "wc_ctx.h"
+#include "wc_device_math.cuh"
+
+using namespace wcd;
+
+namespace {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+struct ExtractParams {
+  double voxel;     // (double)(float)voxel_size
+  double q0, q1;    // (double)(float)(voxel/4), (double)(float)(voxel/8)
+  double t_first;
+  int    vox0[3];
+  int    n;
+};
+
+// ---------------------------------------------------------------------------------------------- K0
+__global__ void repack_points(const wc_point48* __restrict__ raw, int n, float4* __restrict__ xyz,
+                              double* __restrict__ t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4* r = reinterpret_cast<const float4*>(raw + i);
+  float4        a = r[0];
+  float4        b = r[1];  // intensity, pad, time (as two floats)
+  xyz[i]          = a;
+  t[i]            = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z));
+}
+
+// ---------------------------------------------------------------------------------------------- K1
+// Insert-or-find in the open-addressed cell table; returns the dense slot index.
+__device__ __forceinline__ int cell_slot(unsigned long long* __restrict__ keys, int* __restrict__ hslot,
+                                         unsigned long long capmask, unsigned long long key, wc_slot* __restrict__ slots,
+                                         int slot_cap, wc_extract_status* st) {
+  unsigned long long h = mix64(key) & capmask;
+  for (unsigned long long probe = 0; probe <= capmask; ++probe, h = (h + 1) & capmask) {
+    unsigned long long k = *((volatile unsigned long long*)&keys[h]);
+    if (k == WC_KEY_EMPTY) {
+      k = atomicCAS(&keys[h], WC_KEY_EMPTY, key);
+      if (k == WC_KEY_EMPTY) {  // we created the cell: allocate its dense slot and publish it
+        int s = atomicAdd(&st->n_slots, 1);
+        if (s >= slot_cap) {
+          st->err_capacity = 1;
+          atomicExch(&hslot[h], -2);
+          return -2;
+        }
+        slots[s].key       = key;
+        slots[s].table_pos = (int)h;
+        __threadfence();
+        atomicExch(&hslot[h], s);
+        return s;
+      }
+    }
+    if (k == key) {
+      int s;
+      while ((s = *((volatile int*)&hslot[h])) == -1) {
+      }
+      return s;
+    }
+  }
+  st->err_capacity = 1;
+  return -2;
+}
+
+__global__ void __launch_bounds__(256)
+voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ time, ExtractParams P,
+                  unsigned long long* __restrict__ keys, int* __restrict__ hslot, unsigned long long capmask,
+                  wc_slot* __restrict__ slots, int slot_cap, wc_extract_status* __restrict__ st,
+                  wc_point_assign* __restrict__ assign) {
+  const int lane   = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  const int n_pad  = (P.n + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    const bool valid = i < P.n;
+    unsigned long long key = 0x8000000000000000ull | (unsigned long long)lane;  // never equal to a real key
+    int                xi = 0, yi = 0, zi = 0, qrel = 0;
+    unsigned long long tob = 0;
+    if (valid) {
+      const float4 p = xyz[i];
+      const double t = time[i];
+      if (i > 0 && t < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
+      const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+      // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
+      const int vx = (int)floor(__ddiv_rn(x, P.voxel));
+      const int vy = (int)floor(__ddiv_rn(y, P.voxel));
+      const int vz = (int)floor(__ddiv_rn(z, P.voxel));
+      // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
+      double cx = __dmul_rn(0.5 + (double)vx, P.voxel), cy = __dmul_rn(0.5 + (double)vy, P.voxel),
+             cz = __dmul_rn(0.5 + (double)vz, P.voxel);
+      int bx = x > cx, by = y > cy, bz = z > cz;
+      const int c1 = 4 * bx + 2 * by + bz;
+      cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
+      bx = x > cx, by = y > cy, bz = z > cz;
+      const int c2 = 4 * bx + 2 * by + bz;
+      cx += bx ? P.q1 : -P.q1, cy += by ? P.q1 : -P.q1, cz += bz ? P.q1 : -P.q1;
+      const int leaf = 8 * c1 + c2;
+      if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
+      // exact fixed-point coordinates relative to the leaf-cell centre, exact fixed-point time
+      xi = (int)__double2ll_rn((x - cx) * WC_COORD_SCALE);
+      yi = (int)__double2ll_rn((y - cy) * WC_COORD_SCALE);
+      zi = (int)__double2ll_rn((z - cz) * WC_COORD_SCALE);
+      const long long Q   = __double2ll_rn((t - P.t_first) * WC_TIME_SCALE);
+      const long long bin = Q >> WC_BIN_SHIFT;
+      qrel                = (int)(Q - (bin << WC_BIN_SHIFT));
+      tob                 = OrderedBits(t);
+      const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
+      if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
+          Q < 0 || bin >= WC_MAX_BINS) {
+        st->err_range = 1;
+      } else {
+        key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) | ((unsigned long long)rz << 18) |
+              ((unsigned long long)leaf << 12) | (unsigned long long)bin;
+      }
+    }
+    // ---- warp aggregation: lanes holding the same cell reduce into the lowest lane of their group
+    const unsigned grp    = __match_any_sync(0xffffffffu, key);
+    const int      leader = __ffs(grp) - 1;
+    const int      gsz    = __popc(grp);
+    const bool     real   = (key >> 63) == 0;
+    const int      maxg   = __reduce_max_sync(0xffffffffu, real ? gsz : 1);
+    long long      a_n = 1, a_t = qrel, a_x = xi, a_y = yi, a_z = zi;
+    long long a_xx = (long long)xi * xi, a_xy = (long long)xi * yi, a_xz = (long long)xi * zi, a_yy = (long long)yi * yi,
+              a_yz = (long long)yi * zi, a_zz = (long long)zi * zi;
+    unsigned long long a_tmin = ~tob, a_tmax = tob;
+    for (int j = 1; j < maxg; ++j) {
+      const unsigned src = __fns(grp, 0, j + 1);  // lane of the (j+1)-th member, 0xffffffff if none
+      const int      sl  = src & 31;
+      const int      ox = __shfl_sync(0xffffffffu, xi, sl), oy = __shfl_sync(0xffffffffu, yi, sl),
+                oz = __shfl_sync(0xffffffffu, zi, sl), oq = __shfl_sync(0xffffffffu, qrel, sl);
+      const unsigned long long ot = __shfl_sync(0xffffffffu, tob, sl);
+      if (lane == leader && j < gsz) {
+        a_n += 1, a_t += oq, a_x += ox, a_y += oy, a_z += oz;
+        a_xx += (long long)ox * ox, a_xy += (long long)ox * oy, a_xz += (long long)ox * oz;
+        a_yy += (long long)oy * oy, a_yz += (long long)oy * oz, a_zz += (long long)oz * oz;
+        a_tmin = max(a_tmin, ~ot), a_tmax = max(a_tmax, ot);
+      }
+    }
+    if (real && lane == leader) {
+      const int s = cell_slot(keys, hslot, capmask, key, slots, slot_cap, st);
+      if (s >= 0) {
+        wc_slot* sl = slots + s;
+        atomicAdd((unsigned long long*)&sl->n, (unsigned long long)a_n);
+        atomicAdd((unsigned long long*)&sl->st, (unsigned long long)a_t);
+        atomicAdd((unsigned long long*)&sl->s[0], (unsigned long long)a_x);
+        atomicAdd((unsigned long long*)&sl->s[1], (unsigned long long)a_y);
+        atomicAdd((unsigned long long*)&sl->s[2], (unsigned long long)a_z);
+        atomicAdd((unsigned long long*)&sl->ss[0], (unsigned long long)a_xx);
+        atomicAdd((unsigned long long*)&sl->ss[1], (unsigned long long)a_xy);
+        atomicAdd((unsigned long long*)&sl->ss[2], (unsigned long long)a_xz);
+        atomicAdd((unsigned long long*)&sl->ss[3], (unsigned long long)a_yy);
+        atomicAdd((unsigned long long*)&sl->ss[4], (unsigned long long)a_yz);
+        atomicAdd((unsigned long long*)&sl->ss[5], (unsigned long long)a_zz);
+        atomicMax(&sl->tmin_inv, a_tmin);
+        atomicMax(&sl->tmax, a_tmax);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K2a-c
+__global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __restrict__ st,
+                            unsigned long long* __restrict__ vkeys, int* __restrict__ vslot, unsigned long long vmask,
+                            int* __restrict__ vox_count, unsigned long long* __restrict__ vox_key,
+                            int* __restrict__ vox_hpos, int vox_cap) {
+  const int ns = min(st->n_slots, INT_MAX);
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+    const unsigned long long key = slots[s].key >> 18;
+    unsigned long long       h   = mix64(key) & vmask;
+    int                      vid = -2;
+    for (unsigned long long probe = 0; probe <= vmask; ++probe, h = (h + 1) & vmask) {
+      unsigned long long k = *((volatile unsigned long long*)&vkeys[h]);
+      if (k == WC_KEY_EMPTY) {
+        k = atomicCAS(&vkeys[h], WC_KEY_EMPTY, key);
+        if (k == WC_KEY_EMPTY) {
+          vid = atomicAdd(&st->n_voxels, 1);
+          if (vid >= vox_cap) {
+            st->err_capacity = 1;
+            vid              = -2;
+          } else {
+            vox_key[vid]  = key;
+            vox_hpos[vid] = (int)h;  // remember the table position for cleanup
+          }
+          __threadfence();
+          atomicExch(&vslot[h], vid);
+          break;
+        }
+      }
+      if (k == key) {
+        while ((vid = *((volatile int*)&vslot[h])) == -1) {
+        }
+        break;
+      }
+    }
+    slots[s].vid = vid;
+    if (vid >= 0) atomicAdd(&vox_count[vid], 1);
+  }
+}
+
+// exclusive scan of vox_count[0..n_voxels) by one CTA
+__global__ void __launch_bounds__(1024) voxel_scan(const int* __restrict__ cnt, int* __restrict__ off,
+                                                   const wc_extract_status* __restrict__ st) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int      nv = st->n_voxels;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nv; base += 1024) {
+    const int i    = base + threadIdx.x;
+    const int v    = i < nv ? cnt[i] : 0;
+    int       incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x], wi = w;
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (threadIdx.x >= d) wi += o;
+      }
+      warp_sums[threadIdx.x] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const int excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < nv) off[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[nv] = carry;
+}
+
+__global__ void voxel_scatter(const wc_slot* __restrict__ slots, const wc_extract_status* __restrict__ st,
+                              const int* __restrict__ off, int* __restrict__ cursor, int* __restrict__ seg) {
+  const int ns = st->n_slots;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+    const int vid = slots[s].vid;
+    if (vid < 0) continue;
+    seg[off[vid] + atomicAdd(&cursor[vid], 1)] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- K2
+struct EmitParams {
+  double voxel, q0, q1;
+  double t_first;
+  double thr;        // (double)planer_threshold (float)
+  double min_like;
+  double gap;
+  double view[3];
+  int    vox0[3];
+  int    lps[3];     // layer_point_size
+  int    cmin;       // cluster_min_points
+  int    max_layer;
+  int    surf_cap;
+};
+
+// moments about the voxel centre, fp64: n, s[3], ss[6]
+struct Mom {
+  double n, s[3], ss[6];
+};
+__device__ __forceinline__ void mom_zero(Mom& m) {
+  m.n = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m.s[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m.ss[k] = 0;
+}
+// add one slot's exact integer moments (about its leaf centre) shifted to the voxel centre
+__device__ __forceinline__ void mom_add_slot(Mom& m, const wc_slot* __restrict__ sl, int leaf, double q0, double q1) {
+  const int    c1 = leaf >> 3, c2 = leaf & 7;
+  const double dx = ((c1 & 4) ? q0 : -q0) + ((c2 & 4) ? q1 : -q1);
+  const double dy = ((c1 & 2) ? q0 : -q0) + ((c2 & 2) ? q1 : -q1);
+  const double dz = ((c1 & 1) ? q0 : -q0) + ((c2 & 1) ? q1 : -q1);
+  const double inv = 1.0 / WC_COORD_SCALE, inv2 = inv * inv;
+  const double n  = (double)sl->n;
+  const double sx = (double)sl->s[0] * inv, sy = (double)sl->s[1] * inv, sz = (double)sl->s[2] * inv;
+  m.n += n;
+  m.s[0] += sx + n * dx, m.s[1] += sy + n * dy, m.s[2] += sz + n * dz;
+  m.ss[0] += (double)sl->ss[0] * inv2 + 2.0 * dx * sx + n * dx * dx;
+  m.ss[1] += (double)sl->ss[1] * inv2 + dx * sy + dy * sx + n * dx * dy;
+  m.ss[2] += (double)sl->ss[2] * inv2 + dx * sz + dz * sx + n * dx * dz;
+  m.ss[3] += (double)sl->ss[3] * inv2 + 2.0 * dy * sy + n * dy * dy;
+  m.ss[4] += (double)sl->ss[4] * inv2 + dy * sz + dz * sy + n * dy * dz;
+  m.ss[5] += (double)sl->ss[5] * inv2 + 2.0 * dz * sz + n * dz * dz;
+}
+__device__ __forceinline__ void mom_add(Mom& a, const Mom& b) {
+  a.n += b.n;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a.s[k] += b.s[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a.ss[k] += b.ss[k];
+}
+// InitPlane / ClusterSurfels statistics: mean, population covariance, ascending eigen-pairs, likeness
+struct PlaneFit {
+  double mu[3], cov[6], ev[3], like;
+  M3     evec;
+};
+__device__ __forceinline__ void plane_fit(const Mom& m, PlaneFit& f) {
+  const double n = m.n;
+  f.mu[0] = m.s[0] / n, f.mu[1] = m.s[1] / n, f.mu[2] = m.s[2] / n;
+  f.cov[0] = m.ss[0] / n - f.mu[0] * f.mu[0];
+  f.cov[1] = m.ss[1] / n - f.mu[0] * f.mu[1];
+  f.cov[2] = m.ss[2] / n - f.mu[0] * f.mu[2];
+  f.cov[3] = m.ss[3] / n - f.mu[1] * f.mu[1];
+  f.cov[4] = m.ss[4] / n - f.mu[1] * f.mu[2];
+  f.cov[5] = m.ss[5] / n - f.mu[2] * f.mu[2];
+  SymEig3(f.cov[0], f.cov[1], f.cov[2], f.cov[3], f.cov[4], f.cov[5], f.ev, f.evec);
+  f.like = 2.0 * (f.ev[1] - f.ev[0]) / (f.ev[0] + f.ev[1] + f.ev[2]);
+}
+
+__device__ __forceinline__ unsigned level_key(unsigned leafbin, int level) {
+  // leafbin = leaf<<12 | bin.  Sort keys: L2 (leaf, bin); L1 (leaf>>3, bin, leaf&7); L0 (bin, leaf)
+  const unsigned leaf = leafbin >> 12, bin = leafbin & 4095u;
+  if (level == 2) return leafbin;
+  if (level == 1) return ((leaf >> 3) << 15) | (bin << 3) | (leaf & 7u);
+  return (bin << 6) | leaf;
+}
+__device__ __forceinline__ unsigned group_of(unsigned lk, int level) { return level == 2 ? lk : (level == 1 ? lk >> 3 : lk >> 6); }
+__device__ __forceinline__ unsigned node_of(unsigned lk, int level) { return level == 2 ? lk >> 12 : (level == 1 ? lk >> 15 : 0u); }
+__device__ __forceinline__ unsigned bin_of(unsigned lk, int level) {
+  return level == 2 ? (lk & 4095u) : (level == 1 ? ((lk >> 3) & 4095u) : (lk >> 6));
+}
+
+template <int NT>
+__device__ void bitonic_sort_smem(unsigned* keys, int npad) {
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += NT) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned a = keys[i], b = keys[ixj];
+          const bool     up = (i & k) == 0;
+          if ((a > b) == up) keys[i] = b, keys[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// One CTA per voxel whose entry count E lies in (E_LO, ECAP].
+template <int ECAP, int NT>
+__global__ void __launch_bounds__(NT)
+cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg, const int* __restrict__ vox_off,
+                 const unsigned long long* __restrict__ vox_key, wc_extract_status* __restrict__ st, EmitParams P, int e_lo,
+                 wc_surfel* __restrict__ out, unsigned long long* __restrict__ sort_hi,
+                 unsigned long long* __restrict__ sort_lo) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned*      skey    = reinterpret_cast<unsigned*>(smem_raw);      // ECAP sort words: levelkey<<14 | entry
+  unsigned*      leafbin = skey + ECAP;                                // ECAP
+  int*           sid     = reinterpret_cast<int*>(leafbin + ECAP);     // ECAP slot ids
+  unsigned char* flag    = reinterpret_cast<unsigned char*>(sid + ECAP);  // ECAP: 1 group head, 2 node head, 4 cluster head
+  __shared__ Mom           tot[73];   // 0 root, 1..8 layer 1, 9..72 layer 2
+  __shared__ unsigned char emit[73];
+  __shared__ unsigned char l1_cut[8];  // layer-1 child analysed and not planar => its children exist
+
+  const int nv = st->n_voxels;
+  for (int v = blockIdx.x; v < nv; v += gridDim.x) {
+    const int off = vox_off[v];
+    const int E   = vox_off[v + 1] - off;
+    if (E <= e_lo || E > ECAP) {
+      if (E > 8192 && threadIdx.x == 0) st->err_capacity = 1;
+      continue;
+    }
+    __syncthreads();
+    int npad = 1;
+    while (npad < E) npad <<= 1;
+    for (int e = threadIdx.x; e < npad; e += NT) {
+      if (e < E) {
+        const int                s   = seg[off + e];
+        const unsigned long long key = slots[s].key;
+        sid[e]                       = s;
+        leafbin[e]                   = (unsigned)(key & 0x3ffffu);
+        skey[e]                      = ((unsigned)(key & 0x3ffffu) << 14) | (unsigned)e;
+      } else {
+        skey[e] = 0xffffffffu;
+      }
+    }
+    for (int k = threadIdx.x; k < 73; k += NT) mom_zero(tot[k]), emit[k] = 0;
+    __syncthreads();
+    // voxel centre (surfel_extraction.cc:209-211)
+    const unsigned long long vk = vox_key[v];
+    const int vx = (int)((vk >> 30) & 32767u) - WC_VOX_BIAS + P.vox0[0], vy = (int)((vk >> 15) & 32767u) - WC_VOX_BIAS + P.vox0[1],
+              vz = (int)(vk & 32767u) - WC_VOX_BIAS + P.vox0[2];
+    const double ccx = (0.5 + (double)vx) * P.voxel, ccy = (0.5 + (double)vy) * P.voxel, ccz = (0.5 + (double)vz) * P.voxel;
+
+    for (int level = 2; level >= 0; --level) {
+      if (level != 2) {
+        for (int e = threadIdx.x; e < npad; e += NT)
+          skey[e] = e < E ? ((level_key(leafbin[e], level) << 14) | (unsigned)e) : 0xffffffffu;
+        __syncthreads();
+      }
+      bitonic_sort_smem<NT>(skey, npad);
+      // head flags
+      for (int i = threadIdx.x; i < E; i += NT) {
+        const unsigned lk = skey[i] >> 14;
+        unsigned char  f  = 0;
+        if (i == 0) f = 3;
+        else {
+          const unsigned pk = skey[i - 1] >> 14;
+          if (group_of(lk, level) != group_of(pk, level)) f |= 1;
+          if (node_of(lk, level) != node_of(pk, level)) f |= 3;
+        }
+        flag[i] = f;
+      }
+      __syncthreads();
+      if (level == 2) {
+        // leaf totals (thread per leaf run), then the tree 64 -> 8 -> 1 and the planarity flags
+        for (int i = threadIdx.x; i < E; i += NT) {
+          if (!(flag[i] & 2)) continue;
+          const int leaf = (int)(skey[i] >> 26);
+          Mom       m;
+          mom_zero(m);
+          for (int j = i; j < E && (j == i || !(flag[j] & 2)); ++j) mom_add_slot(m, slots + sid[skey[j] & 16383u], leaf, P.q0, P.q1);
+          tot[9 + leaf] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+          Mom m;
+          mom_zero(m);
+          for (int c = 0; c < 8; ++c) mom_add(m, tot[9 + 8 * threadIdx.x + c]);
+          tot[1 + threadIdx.x] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          Mom m;
+          mom_zero(m);
+          for (int c = 0; c < 8; ++c) mom_add(m, tot[1 + c]);
+          tot[0] = m;
+        }
+        __syncthreads();
+        // InitOctoTree / CutOctoTree decisions (surfel_extraction.cc:128-184)
+        const bool root_analysed = tot[0].n > (double)P.lps[0];
+        for (int k = threadIdx.x; k < 9; k += NT) {
+          const int layer    = k == 0 ? 0 : 1;
+          bool      analysed = k == 0 ? root_analysed : (root_analysed && P.max_layer >= 1 && tot[k].n > (double)P.lps[1]);
+          bool      plane    = false;
+          if (analysed) {
+            PlaneFit f;
+            plane_fit(tot[k], f);
+            plane = f.ev[0] < P.thr && f.like > P.min_like;
+          }
+          emit[k] = analysed && plane;
+          if (layer == 1) l1_cut[k - 1] = analysed && !plane && P.max_layer >= 2;
+        }
+        __syncthreads();
+        for (int k = 9 + threadIdx.x; k < 73; k += NT) {
+          const bool analysed = l1_cut[(k - 9) >> 3] && tot[k].n > (double)P.lps[2];
+          bool       plane    = false;
+          if (analysed) {
+            PlaneFit f;
+            plane_fit(tot[k], f);
+            plane = f.ev[0] < P.thr && f.like > P.min_like;
+          }
+          emit[k] = analysed && plane;
+        }
+        __syncthreads();
+      }
+      const int node_base = level == 2 ? 9 : (level == 1 ? 1 : 0);
+      // cluster boundaries: at each group head compare with the previous group of the same node
+      for (int i = threadIdx.x; i < E; i += NT) {
+        const unsigned char f = flag[i];
+        if (!(f & 1)) continue;
+        const unsigned lk = skey[i] >> 14;
+        if (!emit[node_base + node_of(lk, level)]) continue;
+        bool start = (f & 2) != 0;
+        if (!start) {
+          unsigned long long gmin_inv = 0, pmax = 0;
+          for (int j = i; j < E && (j == i || !(flag[j] & 1)); ++j) gmin_inv = max(gmin_inv, slots[sid[skey[j] & 16383u]].tmin_inv);
+          for (int j = i - 1; j >= 0; --j) {
+            pmax = max(pmax, slots[sid[skey[j] & 16383u]].tmax);
+            if (flag[j] & 1) break;
+          }
+          // points[i].timestamp - cluster.back().timestamp > 0.05  (surfel_extraction.cc:24)
+          start = __dsub_rn(FromOrderedBits(~gmin_inv), FromOrderedBits(pmax)) > P.gap;
+        }
+        if (start) flag[i] = f | 4;
+      }
+      __syncthreads();
+      // one thread per cluster: accumulate, fit, test, emit
+      for (int i = threadIdx.x; i < E; i += NT) {
+        if (!(flag[i] & 4)) continue;
+        const unsigned lk0 = skey[i] >> 14;
+        Mom            m;
+        mom_zero(m);
+        long long tA = 0, tB = 0;
+        for (int j = i; j < E && (j == i || !(flag[j] & 6)); ++j) {
+          const unsigned w    = skey[j];
+          const int      e    = w & 16383u;
+          const wc_slot* sl   = slots + sid[e];
+          const unsigned lb   = leafbin[e];
+          mom_add_slot(m, sl, (int)(lb >> 12), P.q0, P.q1);
+          tA += sl->n * (long long)(lb & 4095u);
+          tB += sl->st;
+        }
+        if (m.n < (double)P.cmin) continue;  // surfel_extraction.cc:33
+        PlaneFit f;
+        plane_fit(m, f);
+        if (f.ev[0] > P.thr || f.like < P.min_like) continue;  // :54
+        const double cxw = ccx + f.mu[0], cyw = ccy + f.mu[1], czw = ccz + f.mu[2];
+        V3           nrm = col(f.evec, 0);
+        if (nrm.x * (cxw - P.view[0]) + nrm.y * (cyw - P.view[1]) + nrm.z * (czw - P.view[2]) < 0) nrm = -nrm;
+        const int idx = atomicAdd(&st->n_surfels, 1);
+        if (idx >= P.surf_cap) {
+          st->err_capacity = 1;
+          continue;
+        }
+        const double tmean = P.t_first + ((double)tA * 2147483648.0 + (double)tB) / (m.n * WC_TIME_SCALE);
+        wc_surfel    s;
+        s.timestamp           = tmean;
+        s.resolution          = level == 0 ? P.voxel : (level == 1 ? 2.0 * P.q0 : 2.0 * P.q1);  // (float)(quarter*4)
+        s.plane_std_deviation = sqrt(f.ev[0]);
+        s.rot[0] = s.rot[1] = s.rot[2] = 0.0, s.rot[3] = 1.0;
+        s.pos[0] = s.pos[1] = s.pos[2] = 0.0;
+        s.center[0] = cxw, s.center[1] = cyw, s.center[2] = czw;
+        s.covariance[0] = f.cov[0], s.covariance[1] = f.cov[1], s.covariance[2] = f.cov[2];
+        s.covariance[3] = f.cov[1], s.covariance[4] = f.cov[3], s.covariance[5] = f.cov[4];
+        s.covariance[6] = f.cov[2], s.covariance[7] = f.cov[4], s.covariance[8] = f.cov[5];
+        s.norm[0] = nrm.x, s.norm[1] = nrm.y, s.norm[2] = nrm.z;
+        s.is_in_body_frame = 0, s._pad = 0;
+        out[idx]     = s;
+        sort_hi[idx] = OrderedBits(tmean);
+        sort_lo[idx] = ((unsigned long long)level << 62) | (OrderedBits(cxw) >> 2);
+        (void)lk0;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// leave the tables and slots clean for the next call (only the touched entries are reset)
+__global__ void extract_cleanup(wc_slot* __restrict__ slots, const wc_extract_status* __restrict__ st,
+                                unsigned long long* __restrict__ keys, int* __restrict__ hslot,
+                                unsigned long long* __restrict__ vkeys, int* __restrict__ vslot,
+                                const int* __restrict__ vox_hpos, int* __restrict__ vox_count,
+                                int* __restrict__ vox_cursor) {
+  const int ns = st->n_slots, nv = st->n_voxels;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int s = tid; s < ns; s += nth) {
+    const int h = slots[s].table_pos;
+    keys[h]     = WC_KEY_EMPTY;
+    hslot[h]    = -1;
+    uint4* z    = reinterpret_cast<uint4*>(slots + s);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z[k] = make_uint4(0, 0, 0, 0);
+  }
+  for (int v = tid; v < nv; v += nth) {
+    const int h = vox_hpos[v];
+    vkeys[h]    = WC_KEY_EMPTY;
+    vslot[h]                   = -1;
+    vox_count[v]               = 0;
+    vox_cursor[v]              = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- final sort
+struct SortRec {
+  unsigned long long hi, lo;
+  unsigned           idx;
+};
+__device__ __forceinline__ bool rec_less(const SortRec& a, const SortRec& b) {
+  if (a.hi != b.hi) return a.hi < b.hi;
+  if (a.lo != b.lo) return a.lo < b.lo;
+  return a.idx < b.idx;
+}
+
+// sorts tiles of 2048 in shared memory: all (k, j) steps with k <= 2048 when first != 0, otherwise the tail
+// j < 2048 of the merge step k_global
+__global__ void __launch_bounds__(1024)
+sort_tile(unsigned long long* hi, unsigned long long* lo, unsigned* idx, int n_pad, int k_global) {
+  __shared__ unsigned long long shi[2048], slo[2048];
+  __shared__ unsigned           sidx[2048];
+  const int base = blockIdx.x * 2048;
+  for (int i = threadIdx.x; i < 2048; i += 1024) shi[i] = hi[base + i], slo[i] = lo[base + i], sidx[i] = idx[base + i];
+  __syncthreads();
+  const int k_begin = k_global ? k_global : 2, k_end = k_global ? k_global : 2048;
+  for (int k = k_begin; k <= k_end; k <<= 1) {
+    for (int j = min(k >> 1, 1024); j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < 1024; t += 1024) {
+        const int i   = 2 * t - (t & (j - 1));  // index with bit j clear
+        const int ixj = i + j;
+        const bool up = ((base + i) & k) == 0;
+        SortRec a{shi[i], slo[i], sidx[i]}, b{shi[ixj], slo[ixj], sidx[ixj]};
+        if (rec_less(b, a) == up) {
+          shi[i] = b.hi, slo[i] = b.lo, sidx[i] = b.idx;
+          shi[ixj] = a.hi, slo[ixj] = a.lo, sidx[ixj] = a.idx;
+        }
+      }
+      __syncthreads();
+    }
+    if (k_global) break;
+  }
+  for (int i = threadIdx.x; i < 2048; i += 1024) hi[base + i] = shi[i], lo[base + i] = slo[i], idx[base + i] = sidx[i];
+  (void)n_pad;
+}
+// one global compare-exchange step (j >= 2048)
+__global__ void sort_global_step(unsigned long long* hi, unsigned long long* lo, unsigned* idx, int n_pad, int k, int j) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pad / 2) return;
+  const int  i   = 2 * t - (t & (j - 1));
+  const int  ixj = i + j;
+  const bool up  = (i & k) == 0;
+  SortRec    a{hi[i], lo[i], idx[i]}, b{hi[ixj], lo[ixj], idx[ixj]};
+  if (rec_less(b, a) == up) {
+    hi[i] = b.hi, lo[i] = b.lo, idx[i] = b.idx;
+    hi[ixj] = a.hi, lo[ixj] = a.lo, idx[ixj] = a.idx;
+  }
+}
+__global__ void sort_pad(unsigned long long* hi, unsigned long long* lo, unsigned* idx, int n, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  if (i >= n) hi[i] = ~0ull, lo[i] = ~0ull;
+  idx[i] = (unsigned)i;
+}
+__global__ void gather_surfels(const wc_surfel* __restrict__ in, const unsigned* __restrict__ idx, int n,
+                               wc_surfel* __restrict__ out) {
+  // 13 x 16-byte chunks per surfel; consecutive threads move consecutive chunks
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = t / 13, c = t % 13;
+  if (s >= n) return;
+  reinterpret_cast<uint4*>(out + s)[c] = reinterpret_cast<const uint4*>(in + idx[s])[c];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host
+static wc_status extract_alloc(wc_ctx* c) {
+  if (c->d_xyz) return WC_OK;
+  const size_t np = (size_t)c->prm.max_points;
+  c->hcap         = wc_next_pow2(2 * np);
+  c->slot_cap     = np;
+  c->vcap         = wc_next_pow2(2 * np);
+  WC_CUDA(c, cudaMalloc(&c->d_raw, np * sizeof(wc_point48)));
+  WC_CUDA(c, cudaMalloc(&c->d_xyz, np * sizeof(float4)));
+  WC_CUDA(c, cudaMalloc(&c->d_time, np * sizeof(double)));
+  WC_CUDA(c, cudaMalloc(&c->d_hkeys, c->hcap * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_hslot, c->hcap * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_slots, c->slot_cap * sizeof(wc_slot)));
+  WC_CUDA(c, cudaMalloc(&c->d_vkeys, c->vcap * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_vslot, c->vcap * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_vox_count, (np + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_vox_off, (np + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_vox_cursor, (np + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_vox_key, (np + 1) * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_vox_hpos, (np + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_seg, np * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_xstat, sizeof(wc_extract_status)));
+  WC_CUDA(c, cudaMallocHost(&c->h_xstat, sizeof(wc_extract_status)));
+  const size_t sc = wc_next_pow2((size_t)c->prm.max_surfels < 2048 ? 2048 : (size_t)c->prm.max_surfels);
+  WC_CUDA(c, cudaMalloc(&c->d_surf_raw, sc * sizeof(wc_surfel)));
+  WC_CUDA(c, cudaMalloc(&c->d_surf, sc * sizeof(wc_surfel)));
+  WC_CUDA(c, cudaMalloc(&c->d_sort_hi, sc * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_sort_lo, sc * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_sort_idx, sc * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_assign, np * sizeof(wc_point_assign)));
+  WC_CUDA(c, cudaMemsetAsync(c->d_hkeys, 0xff, c->hcap * 8, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_hslot, 0xff, c->hcap * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_vkeys, 0xff, c->vcap * 8, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_vslot, 0xff, c->vcap * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->slot_cap * sizeof(wc_slot), c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_vox_count, 0, (np + 1) * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_vox_cursor, 0, (np + 1) * 4, c->stream));
+  WC_CUDA(c, cudaFuncSetAttribute(cluster_eig_emit<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 13));
+  return WC_OK;
+}
+
+void wc_extract_free(wc_ctx* c) {
+  void* ptrs[] = {c->d_raw,     c->d_xyz,      c->d_time,    c->d_hkeys,   c->d_hslot,   c->d_slots,    c->d_vkeys,
+                  c->d_vslot,   c->d_vox_count, c->d_vox_off, c->d_vox_cursor, c->d_vox_key, c->d_vox_hpos, c->d_seg,   c->d_xstat,
+                  c->d_surf_raw, c->d_surf,    c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, c->d_assign};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (c->h_xstat) cudaFreeHost(c->h_xstat);
+}
+
+extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n) {
+  if (!c || (!pts && n)) return WC_EINVAL;
+  if (n > (size_t)c->prm.max_points) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_points=%lld", n, (long long)c->prm.max_points);
+  wc_status s = extract_alloc(c);
+  if (s) return s;
+  c->n_pts = n;
+  if (n == 0) return WC_OK;
+  WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
+  repack_points<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const wc_point48*)c->d_raw, (int)n, c->d_xyz, c->d_time);
+  WC_CUDA(c, cudaGetLastError());
+  // voxel of the first point / first timestamp anchor the relative keys (host copy of element 0 is at hand)
+  const double vs = (double)c->prm.voxel_size;
+  c->vox0[0] = (int)floor((double)pts[0].x / vs), c->vox0[1] = (int)floor((double)pts[0].y / vs), c->vox0[2] = (int)floor((double)pts[0].z / vs);
+  c->t_first = pts[0].time;
+  WC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return WC_OK;
+}
+
+extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double* gpu_ms_keys, double* gpu_ms_emit,
+                                               double* gpu_ms_total) {
+  if (!c) return WC_EINVAL;
+  wc_status s = extract_alloc(c);
+  if (s) return s;
+  if (c->prm.max_layer < 0 || c->prm.max_layer > 2) WC_FAIL(c, WC_EINVAL, "max_layer must be 0..2");
+  if (!(c->prm.cluster_time_gap > 0.03125)) WC_FAIL(c, WC_EINVAL, "cluster_time_gap must exceed the 2^-5 s time bin");
+  const int n  = (int)c->n_pts;
+  c->n_surfels = 0;
+  if (n_out) *n_out = 0;
+  if (n == 0) return WC_OK;
+  cudaStream_t st = c->stream;
+  const float  vsf = c->prm.voxel_size;
+  ExtractParams P;
+  P.voxel = (double)vsf, P.q0 = (double)(float)(vsf / 4), P.q1 = (double)(float)((float)(vsf / 4) / 2);
+  P.t_first = c->t_first, P.n = n;
+  for (int k = 0; k < 3; ++k) P.vox0[k] = c->vox0[k];
+
+  WC_CUDA(c, cudaEventRecord(c->ev[0], st));
+  WC_CUDA(c, cudaMemsetAsync(c->d_xstat, 0, sizeof(wc_extract_status), st));
+  const int grid1 = c->num_sms * 8;
+  voxel_key_moments<<<grid1, 256, 0, st>>>(c->d_xyz, c->d_time, P, c->d_hkeys, c->d_hslot, c->hcap - 1, c->d_slots,
+                                           (int)c->slot_cap, c->d_xstat, c->want_assign ? c->d_assign : nullptr);
+  WC_CUDA(c, cudaEventRecord(c->ev[1], st));
+  voxel_index<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
+                                              c->d_vox_key, c->d_vox_hpos, (int)c->prm.max_points);
+  voxel_scan<<<1, 1024, 0, st>>>(c->d_vox_count, c->d_vox_off, c->d_xstat);
+  voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vox_off, c->d_vox_cursor, c->d_seg);
+  EmitParams E;
+  E.voxel = P.voxel, E.q0 = P.q0, E.q1 = P.q1, E.t_first = P.t_first;
+  E.thr = (double)c->prm.planer_threshold, E.min_like = c->prm.min_plane_likeness, E.gap = c->prm.cluster_time_gap;
+  for (int k = 0; k < 3; ++k) E.view[k] = c->prm.view_point[k], E.vox0[k] = c->vox0[k], E.lps[k] = c->prm.layer_point_size[k];
+  E.cmin = c->prm.cluster_min_points, E.max_layer = c->prm.max_layer;
+  E.surf_cap = (int)c->prm.max_surfels;
+  cluster_eig_emit<256, 64><<<c->num_sms * 16, 64, 256 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 0,
+                                                                   c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  cluster_eig_emit<2048, 128><<<c->num_sms * 4, 128, 2048 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
+                                                                     256, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  cluster_eig_emit<8192, 256><<<c->num_sms * 2, 256, 8192 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
+                                                                     2048, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
+  extract_cleanup<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_hkeys, c->d_hslot, c->d_vkeys, c->d_vslot,
+                                                  c->d_vox_hpos, c->d_vox_count, c->d_vox_cursor);
+  WC_CUDA(c, cudaEventRecord(c->ev[2], st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  const wc_extract_status hs = *c->h_xstat;
+  if (hs.err_time_order) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "point timestamps are not non-decreasing");
+  if (hs.err_range) WC_FAIL(c, WC_EINVAL, "sweep exceeds the key range (+-16384 voxels around the first point, 128 s)");
+  if (hs.err_capacity) WC_FAIL(c, WC_ECAPACITY, "capacity exceeded (slots=%d voxels=%d surfels=%d)", hs.n_slots, hs.n_voxels, hs.n_surfels);
+  const int S = hs.n_surfels;
+  c->n_surfels = (size_t)S;
+  c->last_slots = hs.n_slots, c->last_voxels = hs.n_voxels;
+  if (S > 0) {
+    int n_pad = 2048;
+    while (n_pad < S) n_pad <<= 1;
+    sort_pad<<<(n_pad + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, S, n_pad);
+    sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, 0);
+    for (int k = 4096; k <= n_pad; k <<= 1) {
+      for (int j = k >> 1; j >= 2048; j >>= 1)
+        sort_global_step<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k, j);
+      sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k);
+    }
+    gather_surfels<<<(S * 13 + 255) / 256, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, S, c->d_surf);
+  }
+  WC_CUDA(c, cudaEventRecord(c->ev[3], st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  float ms;
+  if (gpu_ms_keys) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); *gpu_ms_keys = ms; }
+  if (gpu_ms_emit) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[3]); *gpu_ms_emit = ms; }
+  if (gpu_ms_total) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); *gpu_ms_total = ms; }
+  if (n_out) *n_out = (size_t)S;
+  return WC_OK;
+}
+
+extern "C" wc_status wc_surfels_fetch(wc_ctx* c, wc_surfel* out, size_t cap, size_t* n_out) {
+  if (!c || (!out && c->n_surfels)) return WC_EINVAL;
+  if (n_out) *n_out = c->n_surfels;
+  if (c->n_surfels > cap) WC_FAIL(c, WC_ECAPACITY, "%zu surfels exceed the output capacity %zu", c->n_surfels, cap);
+  if (c->n_surfels)
+    WC_CUDA(c, cudaMemcpyAsync(out, c->d_surf, c->n_surfels * sizeof(wc_surfel), cudaMemcpyDeviceToHost, c->stream));
+  WC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return WC_OK;
+}
+
+extern "C" wc_status wc_build_surfels(wc_ctx* c, const wc_point48* pts, size_t n, wc_surfel* out, size_t cap,
+                                      size_t* n_out, wc_point_assign* assign, double* gpu_ms) {
+  if (!c) return WC_EINVAL;
+  wc_status s = wc_points_upload(c, pts, n);
+  if (s) return s;
+  c->want_assign = assign != nullptr;
+  size_t S = 0;
+  s        = wc_build_surfels_resident(c, &S, nullptr, nullptr, gpu_ms);
+  c->want_assign = 0;
+  if (s) return s;
+  if (assign && n) WC_CUDA(c, cudaMemcpyAsync(assign, c->d_assign, n * sizeof(wc_point_assign), cudaMemcpyDeviceToHost, c->stream));
+  return wc_surfels_fetch(c, out, cap, n_out);
+}

@@ -1,0 +1,306 @@
+// Surfel correspondence search on the device — replaces KnnSurfelMatcher::{BuildIndex, Match, KNearestSearch,
+// ToVector, FLANNBuildIndex, FLANNKNearestSearch} (src/odometry/knn_surfel_matcher.cc:3-98).
+//
+//   surfel_features   world centre / normal of every surfel (surfel.h:67-80) and the 6-D feature
+//                     [c_w / 1.0, n_w / (5 deg)] (knn_surfel_matcher.cc:91-98)
+//   knn6_bruteforce   exact k nearest neighbours in squared L2 (flann::L2_Simple accumulation order, no FMA
+//                     contraction), targets staged through shared memory; ties ordered by target index
+//   gate_candidates   the three gates of Match (:26-34) applied to the k candidates in ascending distance
+//   resolve_pairs     the order-dependent pair de-duplication (:35-39) as a parallel fixed-point iteration:
+//                     query i takes its first gated candidate c unless c < i already took i.  acc[i] depends
+//                     only on acc[c] for c < i, so the fixed point is unique and equals the sequential result.
+//   compact_pairs     output in query order, each pair ordered by time (:41-45)
+#include "wc_ctx.h"
+#include "wc_device_math.cuh"
+
+using namespace wcd;
+
+namespace {
+
+constexpr int KMAX  = 16;
+constexpr int FSTR  = 16;  // doubles per surfel feature record: f[6], c_w[3], n_w[3], t, pad[3]
+constexpr int TILE  = 256;
+
+__global__ void surfel_features(const wc_surfel* __restrict__ s, int n, double inv_center, double ang, double* __restrict__ f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Q4 q = ldq(s[i].rot);
+  const V3 c = q * ld3(s[i].center) + ld3(s[i].pos);
+  const V3 m = q * ld3(s[i].norm);
+  double*  o = f + (size_t)i * FSTR;
+  // Vector3d / double  (Eigen: per-coefficient division)
+  o[0] = __ddiv_rn(c.x, inv_center), o[1] = __ddiv_rn(c.y, inv_center), o[2] = __ddiv_rn(c.z, inv_center);
+  o[3] = __ddiv_rn(m.x, ang), o[4] = __ddiv_rn(m.y, ang), o[5] = __ddiv_rn(m.z, ang);
+  o[6] = c.x, o[7] = c.y, o[8] = c.z, o[9] = m.x, o[10] = m.y, o[11] = m.z;
+  o[12] = s[i].timestamp, o[13] = o[14] = o[15] = 0.0;
+}
+
+// q: nq records of stride qstr (first 6 doubles = feature); t likewise.
+__global__ void __launch_bounds__(TILE)
+knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __restrict__ t, int tstr, int nt, int k,
+                int* __restrict__ out_idx, double* __restrict__ out_d2) {
+  __shared__ double tile[TILE * 6];
+  const int  i      = blockIdx.x * TILE + threadIdx.x;
+  const bool active = i < nq;
+  double     f[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) f[d] = active ? q[(size_t)i * qstr + d] : 0.0;
+  double dk[KMAX];
+  int    ik[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) dk[j] = INFINITY, ik[j] = -1;
+  double worst = INFINITY;  // dk[k-1]
+  for (int base = 0; base < nt; base += TILE) {
+    const int m = min(TILE, nt - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * 6; e += TILE) tile[e] = t[(size_t)(base + e / 6) * tstr + (e % 6)];
+    __syncthreads();
+    if (!active) continue;
+    for (int j = 0; j < m; ++j) {
+      // flann::L2_Simple: result += diff*diff, in dimension order, no contraction
+      double r = 0.0;
+#pragma unroll
+      for (int d = 0; d < 6; ++d) {
+        const double diff = __dsub_rn(f[d], tile[j * 6 + d]);
+        r                 = __dadd_rn(r, __dmul_rn(diff, diff));
+      }
+      if (r < worst) {
+        const int id = base + j;
+#pragma unroll
+        for (int p = KMAX - 1; p > 0; --p) {
+          if (p < k) {
+            const bool shift = r < dk[p - 1];
+            const bool place = !shift && r < dk[p];
+            if (shift) dk[p] = dk[p - 1], ik[p] = ik[p - 1];
+            else if (place) dk[p] = r, ik[p] = id;
+          }
+        }
+        if (r < dk[0]) dk[0] = r, ik[0] = id;
+#pragma unroll
+        for (int p = 0; p < KMAX; ++p)
+          if (p == k - 1) worst = dk[p];
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < k) out_idx[(size_t)i * k + j] = ik[j], out_d2[(size_t)i * k + j] = dk[j];
+}
+
+struct GateParams {
+  double time_diff, ang, dist;
+  int    k;
+};
+
+// gated[i*k + j]: the candidates of query i that pass the gates, ascending distance, -1 terminated
+__global__ void gate_candidates(const double* __restrict__ qf, int nq, const double* __restrict__ tf, const int* __restrict__ knn,
+                                GateParams G, int* __restrict__ gated) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const double* a  = qf + (size_t)i * FSTR;
+  const V3      ca = ld3(a + 6), na = ld3(a + 9);
+  const double  ta = a[12];
+  int           w  = 0;
+  for (int j = 0; j < G.k; ++j) {
+    const int c = knn[(size_t)i * G.k + j];
+    if (c < 0) break;
+    const double* b = tf + (size_t)c * FSTR;
+    if (fabs(__dsub_rn(b[12], ta)) < G.time_diff) continue;                       // knn_surfel_matcher.cc:26
+    const V3 nb = ld3(b + 9), cb = ld3(b + 6);
+    const double dn = __dadd_rn(__dadd_rn(__dmul_rn(na.x, nb.x), __dmul_rn(na.y, nb.y)), __dmul_rn(na.z, nb.z));
+    if (acos(dn) > G.ang) continue;                                               // :29, un-clamped acos (Q9)
+    const V3     d  = ca - cb;
+    const double pd = __dadd_rn(__dadd_rn(__dmul_rn(na.x, d.x), __dmul_rn(na.y, d.y)), __dmul_rn(na.z, d.z));
+    if (fabs(pd) > G.dist) continue;                                              // :32
+    gated[(size_t)i * G.k + w++] = c;
+  }
+  for (; w < G.k; ++w) gated[(size_t)i * G.k + w] = -1;
+}
+
+// one relaxation sweep of the de-duplication recurrence; *changed is set if any entry moved
+__global__ void resolve_pairs(const int* __restrict__ gated, int nq, int k, int self_match, const int* __restrict__ acc_in,
+                              int* __restrict__ acc_out, int* __restrict__ changed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  int take = -1;
+  for (int j = 0; j < k; ++j) {
+    const int c = gated[(size_t)i * k + j];
+    if (c < 0) break;
+    // surfel_pairs already holds {c, i} iff the earlier query c accepted i  (:35-39)
+    if (self_match && c < i && acc_in[c] == i) continue;
+    take = c;
+    break;
+  }
+  if (take != acc_in[i]) *changed = 1;
+  acc_out[i] = take;
+}
+
+// exclusive scan of (acc[i] >= 0) by one CTA, then scatter of the ordered pairs
+__global__ void __launch_bounds__(1024)
+compact_pairs(const int* __restrict__ acc, int nq, const double* __restrict__ qf, const double* __restrict__ tf,
+              wc_corr_idx* __restrict__ out, unsigned char* __restrict__ first_is_target, int* __restrict__ n_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nq; base += 1024) {
+    const int i    = base + threadIdx.x;
+    const int c    = i < nq ? acc[i] : -1;
+    const int v    = c >= 0 ? 1 : 0;
+    int       incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x], wi = w;
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (threadIdx.x >= d) wi += o;
+      }
+      warp_sums[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int pos = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (v) {
+      const bool query_first = qf[(size_t)i * FSTR + 12] < tf[(size_t)c * FSTR + 12];  // :41
+      out[pos].s1            = query_first ? i : c;
+      out[pos].s2            = query_first ? c : i;
+      first_is_target[pos]   = query_first ? 0 : 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_out = carry;
+}
+
+}  // namespace
+
+static wc_status match_alloc(wc_ctx* c) {
+  if (c->d_qfeat) return WC_OK;
+  const size_t ns = (size_t)c->prm.max_surfels;
+  WC_CUDA(c, cudaMalloc(&c->d_msurf_q, ns * sizeof(wc_surfel)));
+  WC_CUDA(c, cudaMalloc(&c->d_msurf_t, ns * sizeof(wc_surfel)));
+  WC_CUDA(c, cudaMalloc(&c->d_qfeat, ns * FSTR * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_tfeat, ns * FSTR * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_knn_idx, ns * KMAX * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_knn_d2, ns * KMAX * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_gated, ns * KMAX * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_acc, ns * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_acc2, ns * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_flag, 16));
+  WC_CUDA(c, cudaMalloc(&c->d_corr_out, ns * sizeof(wc_corr_idx)));
+  WC_CUDA(c, cudaMalloc(&c->d_fit_out, ns));
+  WC_CUDA(c, cudaMallocHost(&c->h_flag, 16));
+  return WC_OK;
+}
+
+void wc_match_free(wc_ctx* c) {
+  void* ptrs[] = {c->d_msurf_q, c->d_msurf_t, c->d_qfeat, c->d_tfeat, c->d_knn_idx, c->d_knn_d2, c->d_gated,
+                  c->d_acc,     c->d_acc2,    c->d_flag,  c->d_corr_out, c->d_fit_out};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+}
+
+// Device-resident matcher core: query/target surfels already at d_q / d_t.  Leaves the pairs in d_corr_out.
+wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_surfel* d_t, size_t nt, int self_match,
+                          size_t* n_out) {
+  *n_out = 0;
+  if (nq == 0 || nt == 0) return WC_OK;  // knn_surfel_matcher.cc:18-20
+  cudaStream_t st = c->stream;
+  const int    k  = c->prm.knn_candidates;
+  if (k < 1 || k > KMAX) WC_FAIL(c, WC_EINVAL, "knn_candidates must be 1..%d", KMAX);
+  const unsigned gq = (unsigned)((nq + 255) / 256), gt = (unsigned)((nt + 255) / 256);
+  surfel_features<<<gq, 256, 0, st>>>(d_q, (int)nq, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_qfeat);
+  const double* tfeat = c->d_qfeat;
+  if (!self_match) {
+    surfel_features<<<gt, 256, 0, st>>>(d_t, (int)nt, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_tfeat);
+    tfeat = c->d_tfeat;
+  }
+  knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
+                                                                       c->d_knn_idx, c->d_knn_d2);
+  GateParams G{c->prm.time_diff_threshold, c->prm.angular_dist_threshold, c->prm.surfel_dist_threshold, k};
+  gate_candidates<<<gq, 256, 0, st>>>(c->d_qfeat, (int)nq, tfeat, c->d_knn_idx, G, c->d_gated);
+  WC_CUDA(c, cudaMemsetAsync(c->d_acc, 0xff, nq * 4, st));
+  int* a = c->d_acc;
+  int* b = c->d_acc2;
+  for (int it = 0;; ++it) {
+    WC_CUDA(c, cudaMemsetAsync(c->d_flag, 0, 4, st));
+    const int sweeps = self_match ? 3 : 1;
+    for (int s = 0; s < sweeps; ++s) {
+      resolve_pairs<<<gq, 256, 0, st>>>(c->d_gated, (int)nq, k, self_match, a, b, c->d_flag);
+      int* tmp = a; a = b; b = tmp;
+    }
+    if (!self_match) break;
+    // the last sweep of the batch wrote `changed` relative to its input; converged iff the whole batch was quiet
+    WC_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, st));
+    WC_CUDA(c, cudaStreamSynchronize(st));
+    if (*c->h_flag == 0) break;
+    if (it > (int)nq) WC_FAIL(c, WC_ENUMERIC, "pair de-duplication did not converge");
+  }
+  compact_pairs<<<1, 1024, 0, st>>>(a, (int)nq, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1);
+  WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 4, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  *n_out = (size_t)c->h_flag[1];
+  return WC_OK;
+}
+
+extern "C" wc_status wc_match(wc_ctx* c, const wc_surfel* query, size_t nq, const wc_surfel* target, size_t nt,
+                              int self_match, wc_corr_idx* out, size_t cap, size_t* n_out, uint8_t* first_is_target,
+                              double* gpu_ms) {
+  if (!c || !n_out || (nq && !query) || (nt && !target)) return WC_EINVAL;
+  *n_out = 0;
+  if (nq > (size_t)c->prm.max_surfels || nt > (size_t)c->prm.max_surfels)
+    WC_FAIL(c, WC_ECAPACITY, "surfel count exceeds max_surfels=%lld", (long long)c->prm.max_surfels);
+  if (self_match && (nq != nt)) WC_FAIL(c, WC_EINVAL, "self_match requires target == query");
+  wc_status s = match_alloc(c);
+  if (s) return s;
+  cudaStream_t st = c->stream;
+  if (nq) WC_CUDA(c, cudaMemcpyAsync(c->d_msurf_q, query, nq * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
+  if (!self_match && nt) WC_CUDA(c, cudaMemcpyAsync(c->d_msurf_t, target, nt * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
+  WC_CUDA(c, cudaEventRecord(c->ev[0], st));
+  size_t np = 0;
+  s         = wc_match_device(c, c->d_msurf_q, nq, self_match ? c->d_msurf_q : c->d_msurf_t, nt, self_match, &np);
+  if (s) return s;
+  WC_CUDA(c, cudaEventRecord(c->ev[1], st));
+  if (np > cap) WC_FAIL(c, WC_ECAPACITY, "%zu pairs exceed the output capacity %zu", np, cap);
+  if (np) {
+    WC_CUDA(c, cudaMemcpyAsync(out, c->d_corr_out, np * sizeof(wc_corr_idx), cudaMemcpyDeviceToHost, st));
+    if (first_is_target) WC_CUDA(c, cudaMemcpyAsync(first_is_target, c->d_fit_out, np, cudaMemcpyDeviceToHost, st));
+  }
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  if (gpu_ms) {
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    *gpu_ms = ms;
+  }
+  *n_out = np;
+  return WC_OK;
+}
+
+extern "C" wc_status wc_knn6(wc_ctx* c, const double* query6, size_t nq, const double* target6, size_t nt, int k,
+                             int32_t* out_idx, double* out_dist2) {
+  if (!c || !query6 || !target6 || !out_idx || !out_dist2) return WC_EINVAL;
+  if (k < 1 || k > KMAX) WC_FAIL(c, WC_EINVAL, "k must be 1..%d", KMAX);
+  if (nq > (size_t)c->prm.max_surfels || nt > (size_t)c->prm.max_surfels) WC_FAIL(c, WC_ECAPACITY, "too many vectors");
+  wc_status s = match_alloc(c);
+  if (s) return s;
+  cudaStream_t st = c->stream;
+  // the feature buffers have room for FSTR doubles per record: pack the 6-vectors at the front
+  WC_CUDA(c, cudaMemcpyAsync(c->d_qfeat, query6, nq * 48, cudaMemcpyHostToDevice, st));
+  WC_CUDA(c, cudaMemcpyAsync(c->d_tfeat, target6, nt * 48, cudaMemcpyHostToDevice, st));
+  if (nq && nt)
+    knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, 6, (int)nq, c->d_tfeat, 6, (int)nt, k,
+                                                                         c->d_knn_idx, c->d_knn_d2);
+  WC_CUDA(c, cudaGetLastError());
+  WC_CUDA(c, cudaMemcpyAsync(out_idx, c->d_knn_idx, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaMemcpyAsync(out_dist2, c->d_knn_d2, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  return WC_OK;
+}

@@ -1,0 +1,1089 @@
+// Window solve on the device — replaces LidarOdometry::Build{SldWin,FixWin}LidarResiduals + BuildImuResiduals +
+// ceres::Solve (src/odometry/lidar_odometry.cc:254-363,541-561) with the cost functors of src/odometry/cost_functor.h.
+//
+//   K4 corr_pack        factor construction (cost_functor.h:17-26,102-114): eigen of Sigma1w+Sigma2w -> weight*normal,
+//                       v_i = R_i c_i, bracketing sample intervals (upper_bound, lidar_odometry.cc:258-268,303-307),
+//                       interpolation factors; records bucketed by interval pair, stored as 16 SoA columns
+//   K5 lidar_linearize  residual + Cauchy corrector + analytic 1x24 Jacobian row (cost_functor.h:28-59,116-179, Q1
+//                       switch) per correspondence; J^T J / J^T r of a 256-record tile by a register-tiled SYRK out of
+//                       shared memory; per-bucket 24x24 blocks flushed to the dense normal equations with fp64 RED
+//      imu_linearize    ImuFactor residuals/Jacobians (cost_functor.h:264-472), one warp per IMU triplet
+//   K6 (fused into K5)  the candidate-cost pass of Ceres' step evaluation is the same launch that linearises at the
+//                       candidate: an accepted step re-uses that J^T J, a rejected one discards it
+//   K7 lm_*             Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy: Jacobi scaling,
+//                       damping, dense Cholesky in shared memory, step, accept/reject, radius update, termination —
+//                       one CTA, state resident on the device
+#include <float.h>
+
+#include "wc_ctx.h"
+#include "wc_device_math.cuh"
+
+using namespace wcd;
+
+wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate);  // wc_comm.cu; no-op when world == 1
+wc_status wc_comm_check(wc_ctx* c);
+void      wc_comm_partial_views(wc_ctx* c, double** H, double** g, double** cost);
+
+namespace {
+
+constexpr int REC_COLS = 16;
+constexpr int LT       = 256;       // linearize tile = threads per CTA
+constexpr int JR       = 28;        // augmented row count: 24 Jacobian columns, residual, 3 pad
+constexpr int JS       = LT + 1;    // padded row stride (doubles)
+constexpr int NGRP     = LT / 32;
+
+struct LMState {
+  // control
+  int    cur;            // which of the two normal-equation buffers belongs to the current point x
+  int    done;
+  int    termination;
+  int    iteration;
+  int    step_valid;
+  int    last_successful;
+  int    reuse_diagonal;
+  int    num_consecutive_invalid;
+  int    num_successful, num_unsuccessful, num_linearizations;
+  int    D;              // reduced dimension
+  int    err;            // assembly / evaluation errors (wc_status)
+  int    pad;
+  double radius, decrease_factor;
+  double x_cost, x_norm, grad_max, model_cost_change, step_norm, initial_cost;
+  double iter_cost[WC_MAX_ITER_LOG];
+  double iter_radius[WC_MAX_ITER_LOG];
+  signed char iter_accepted[WC_MAX_ITER_LOG];
+};
+
+struct SolveBufs {
+  double* H[2];
+  double* g[2];
+  double* cost[2];  // each one double
+  double* x;        // current point (N)
+  double* xc;       // candidate
+  double* scale;    // D
+  double* diag;     // D
+  double* step;     // D
+  double* A;        // D*D workspace when it does not fit shared memory
+  LMState* st;
+  int     N;        // 12 K
+  int     fix_first;
+};
+
+__device__ __forceinline__ int upper_bound_ts(const double* __restrict__ ts, int K, double t) {
+  int lo = 0, hi = K;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t < ts[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+struct PackArgs {
+  const wc_surfel*   sld;
+  const wc_surfel*   fix;
+  const wc_corr_idx* sld_corr;
+  const wc_corr_idx* fix_corr;
+  int                n_sld, n_fix, n_sld_corr, n_fix_corr;
+  int                c0, c1;  // this rank's slice of the concatenated correspondence list
+  const double*      ts;
+  int                K;
+  double             weight_floor;
+  double*            tmp;     // REC_COLS x stride, unsorted
+  int                stride;
+  int*               bucket;  // per record
+  int*               hist;
+  LMState*           st;
+};
+
+__global__ void corr_pack(PackArgs a) {
+  const int i = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.c1) return;
+  const bool       unary = i >= a.n_sld_corr;
+  const wc_corr_idx ci   = unary ? a.fix_corr[i - a.n_sld_corr] : a.sld_corr[i];
+  const int        n1    = unary ? a.n_fix : a.n_sld;
+  if (ci.s1 < 0 || ci.s1 >= n1 || ci.s2 < 0 || ci.s2 >= a.n_sld) {
+    a.st->err = WC_EINVAL;
+    return;
+  }
+  const wc_surfel& s1 = unary ? a.fix[ci.s1] : a.sld[ci.s1];
+  const wc_surfel& s2 = a.sld[ci.s2];
+  if (!(s1.timestamp < s2.timestamp)) a.st->err = WC_EINVAL_TIME_ORDER;  // CHECK_LT lidar_odometry.cc:256,301
+  const Q4 q1 = ldq(s1.rot), q2 = ldq(s2.rot);
+  const M3 R1 = ToMatrix(q1), R2 = ToMatrix(q2);
+  // GetCovarianceInWorld (surfel.h:89-91) of both, summed; weight and direction (cost_functor.h:22-25,110-113)
+  const M3 cw = (R1 * ld33(s1.covariance)) * transpose(R1) + (R2 * ld33(s2.covariance)) * transpose(R2);
+  double   ev[3];
+  M3       V;
+  SymEig3(cw.m[0][0], cw.m[1][0], cw.m[2][0], cw.m[1][1], cw.m[2][1], cw.m[2][2], ev, V);  // lower triangle like Eigen
+  const double w  = 1.0 / sqrt(a.weight_floor + ev[0]);
+  const V3     wn = w * col(V, 0);
+  const V3     v1 = q1 * ld3(s1.center), v2 = q2 * ld3(s2.center);
+  const V3     p1 = ld3(s1.pos), p2 = ld3(s2.pos);
+  const int    sp2r = upper_bound_ts(a.ts, a.K, s2.timestamp);
+  int          b1l = -1, b2l = sp2r - 1, mode = 0;
+  double       f1 = 0.0, f2 = 0.0;
+  bool         ok = sp2r > 0 && sp2r < a.K;  // CHECKs lidar_odometry.cc:265-266,304-305
+  if (ok) f2 = (s2.timestamp - a.ts[b2l]) / (a.ts[b2l + 1] - a.ts[b2l]);
+  if (!unary) {
+    const int sp1r = upper_bound_ts(a.ts, a.K, s1.timestamp);
+    ok             = ok && sp1r > 0 && sp1r < a.K;  // :259-260
+    b1l            = sp1r - 1;
+    if (ok) {
+      f1   = (s1.timestamp - a.ts[b1l]) / (a.ts[b1l + 1] - a.ts[b1l]);
+      mode = (a.ts[b1l + 1] < a.ts[b2l]) ? 0 : ((b1l + 1 == b2l) ? 1 : 2);  // :271,280
+    }
+  }
+  if (!ok) {
+    a.st->err = WC_EOUT_OF_SPAN;
+    return;
+  }
+  const int    r  = i - a.c0;
+  double*      o  = a.tmp + r;
+  const size_t S  = (size_t)a.stride;
+  const V3     d0 = unary ? (v1 + p1) - p2 : p1 - p2;
+  const V3     w1 = unary ? mk(0, 0, 0) : v1;
+  o[0 * S] = w1.x, o[1 * S] = w1.y, o[2 * S] = w1.z;
+  o[3 * S] = v2.x, o[4 * S] = v2.y, o[5 * S] = v2.z;
+  o[6 * S] = d0.x, o[7 * S] = d0.y, o[8 * S] = d0.z;
+  o[9 * S] = wn.x, o[10 * S] = wn.y, o[11 * S] = wn.z;
+  o[12 * S] = f1, o[13 * S] = f2;
+  const int bk = (b1l + 1) * a.K + b2l;
+  o[14 * S]    = __longlong_as_double(((long long)(unsigned)b1l << 32) | (unsigned)b2l);
+  o[15 * S]    = __longlong_as_double(((long long)(unsigned)mode << 32) | (unsigned)bk);
+  a.bucket[r]  = bk;
+  atomicAdd(&a.hist[bk], 1);
+}
+
+__global__ void __launch_bounds__(1024) bucket_scan(const int* __restrict__ hist, int nb, int* __restrict__ off) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? hist[i] : 0;
+    int       incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x], wi = w;
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (threadIdx.x >= d) wi += o;
+      }
+      warp_sums[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < nb) off[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void bucket_scatter(const double* __restrict__ tmp, const int* __restrict__ bucket, int n, int stride,
+                               const int* __restrict__ off, int* __restrict__ cursor, double* __restrict__ rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int bk  = bucket[i];
+  const int pos = off[bk] + atomicAdd(&cursor[bk], 1);
+#pragma unroll
+  for (int c = 0; c < REC_COLS; ++c) rec[(size_t)c * stride + pos] = tmp[(size_t)c * stride + i];
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+struct LinArgs {
+  const double* rec;
+  int           stride, n_rec;
+  SolveBufs     B;
+  int           at_candidate;  // 0: linearise at x into buffer cur; 1: at xc into buffer 1-cur
+  int           jac_mode;
+  double        cauchy_b, cauchy_c;
+};
+
+__device__ __forceinline__ void lidar_eval(const double* __restrict__ rec, size_t S, int i, const double* __restrict__ x,
+                                           int jac_mode, double cb, double cc, double J[24], double& r_out, double& cost_out,
+                                           int& b1l, int& b2l, int& bk) {
+  const double* o  = rec + i;
+  const V3      v1 = mk(o[0 * S], o[1 * S], o[2 * S]), v2 = mk(o[3 * S], o[4 * S], o[5 * S]);
+  const V3      d0 = mk(o[6 * S], o[7 * S], o[8 * S]), wn = mk(o[9 * S], o[10 * S], o[11 * S]);
+  const double  f1 = o[12 * S], f2 = o[13 * S];
+  const long long w14 = __double_as_longlong(o[14 * S]), w15 = __double_as_longlong(o[15 * S]);
+  b1l = (int)(w14 >> 32), b2l = (int)(w14 & 0xffffffffll);
+  const int mode = (int)(w15 >> 32);
+  bk             = (int)(w15 & 0xffffffffll);
+  const double* x2l = x + 12 * b2l;
+  const V3 r2 = (1 - f2) * ld3(x2l) + f2 * ld3(x2l + 12);
+  const V3 t2 = (1 - f2) * ld3(x2l + 3) + f2 * ld3(x2l + 15);
+  const Q4 E2 = Exp(r2);
+  V3       r1 = mk(0, 0, 0), t1 = mk(0, 0, 0);
+  Q4       E1 = Q4{1, 0, 0, 0};
+  const bool unary = b1l < 0;
+  if (!unary) {
+    const double* x1l = x + 12 * b1l;
+    r1 = (1 - f1) * ld3(x1l) + f1 * ld3(x1l + 12);
+    t1 = (1 - f1) * ld3(x1l + 3) + f1 * ld3(x1l + 15);
+    E1 = Exp(r1);
+  }
+  // residual (cost_functor.h:39,140); wn carries the weight
+  const V3     e   = (E1 * v1 + t1 + d0) - (E2 * v2 + t2);
+  const double r   = dot(wn, e);
+  const double s   = r * r;
+  const double sum = 1.0 + s * cc, inv = 1.0 / sum;  // ceres::CauchyLoss
+  cost_out         = 0.5 * cb * log(sum);
+  const double sr  = sqrt(fmax(DBL_MIN, inv));       // Corrector: rho'' < 0 => scale by sqrt(rho')
+  r_out            = r * sr;
+  // jacobian_s2 (:42-45,162-165), jacobian_s1 (:147-150)
+  const V3 a2 = vTm(vTm(vTm(wn, ToMatrix(E2)), Hat(v2)), Jr(r2));
+  double   g1l = 1 - f1, g1r = f1;
+  const double g2l = 1 - f2, g2r = f2;
+  // Q1: in the aliased modes the later '=' overwrites the s1 part (cost_functor.h:152-175 + 215-229)
+  if (jac_mode == WC_JAC_REFERENCE_OVERWRITE) {
+    if (mode == 1) g1r = 0.0;
+    if (mode == 2) g1l = 0.0, g1r = 0.0;
+  }
+  if (unary) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) J[k] = 0.0;
+  } else {
+    const V3 a1 = vTm(vTm(vTm(-wn, ToMatrix(E1)), Hat(v1)), Jr(r1));
+    J[0] = sr * g1l * a1.x, J[1] = sr * g1l * a1.y, J[2] = sr * g1l * a1.z;
+    J[3] = sr * g1l * wn.x, J[4] = sr * g1l * wn.y, J[5] = sr * g1l * wn.z;
+    J[6] = sr * g1r * a1.x, J[7] = sr * g1r * a1.y, J[8] = sr * g1r * a1.z;
+    J[9] = sr * g1r * wn.x, J[10] = sr * g1r * wn.y, J[11] = sr * g1r * wn.z;
+  }
+  J[12] = sr * g2l * a2.x, J[13] = sr * g2l * a2.y, J[14] = sr * g2l * a2.z;
+  J[15] = -sr * g2l * wn.x, J[16] = -sr * g2l * wn.y, J[17] = -sr * g2l * wn.z;
+  J[18] = sr * g2r * a2.x, J[19] = sr * g2r * a2.y, J[20] = sr * g2r * a2.z;
+  J[21] = -sr * g2r * wn.x, J[22] = -sr * g2r * wn.y, J[23] = -sr * g2r * wn.z;
+}
+
+// block (bi, bj), bi <= bj, of the 7x7 grid of 4x4 blocks, enumerated by lane 0..27
+__device__ __forceinline__ void lane_block(int lane, int& bi, int& bj) {
+  int l = lane;
+  bi    = 0;
+  while (l >= 7 - bi) l -= 7 - bi, ++bi;
+  bj = bi + l;
+}
+
+__global__ void __launch_bounds__(LT) lidar_linearize(LinArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  double* Jt = sm;  // JR x JS
+  __shared__ int sbk[LT];
+  __shared__ int sb1[LT], sb2[LT];
+  __shared__ int heads[LT];
+  __shared__ int nheads;
+  __shared__ double wcost[NGRP];
+
+  LMState* st = a.B.st;
+  if (st->done || (a.at_candidate && !st->step_valid)) return;
+  const int     buf = a.at_candidate ? 1 - st->cur : st->cur;
+  const double* x   = a.at_candidate ? a.B.xc : a.B.x;
+  double*       H   = a.B.H[buf];
+  double*       g   = a.B.g[buf];
+  const int     N   = a.B.N;
+  const size_t  S   = (size_t)a.stride;
+
+  const int t = threadIdx.x, lane = t & 31, grp = t >> 5;
+  int       bi, bj;
+  lane_block(lane < 28 ? lane : 0, bi, bj);
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  double cost_local = 0.0;
+  int    cur_b1 = -2, cur_b2 = -2, cur_bk = -1;
+
+  const int ntiles = (a.n_rec + LT - 1) / LT;
+  const int per    = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int tile0 = blockIdx.x * per, tile1 = min(ntiles, tile0 + per);
+
+  // flush the per-thread 4x4 partial blocks of the current bucket into the dense normal equations
+  auto flush = [&]() {
+    __syncthreads();
+    double* stage = Jt;  // NGRP x 28 x 16
+    if (lane < 28)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) stage[(grp * 28 + lane) * 16 + k] = acc[k], acc[k] = 0.0;
+    __syncthreads();
+    if (cur_bk >= 0) {
+      for (int o = t; o < 28 * 16; o += LT) {
+        const int blk = o >> 4, k = o & 15;
+        int       pbi, pbj;
+        lane_block(blk, pbi, pbj);
+        const int p = 4 * pbi + (k >> 2), q = 4 * pbj + (k & 3);
+        if (p > q || p >= 24 || q > 24) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int gi = 0; gi < NGRP; ++gi) v += stage[(gi * 28 + blk) * 16 + k];
+        if (v == 0.0) continue;
+        const int sa = p / 6, gpb = (sa < 2 ? cur_b1 + sa : cur_b2 + sa - 2);
+        const int gp = 12 * gpb + p % 6;
+        if (q == 24) {
+          atomicAdd(&g[gp], v);
+        } else {
+          const int sb = q / 6, gqb = (sb < 2 ? cur_b1 + sb : cur_b2 + sb - 2);
+          const int gq = 12 * gqb + q % 6;
+          atomicAdd(&H[(size_t)gp * N + gq], v);
+          if (p != q) atomicAdd(&H[(size_t)gq * N + gp], v);
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  for (int tile = tile0; tile < tile1; ++tile) {
+    const int  i     = tile * LT + t;
+    const bool valid = i < a.n_rec;
+    double     J[24], r = 0.0, cst = 0.0;
+    int        b1l = -2, b2l = -2, bk = -1;
+    if (valid) lidar_eval(a.rec, S, i, x, a.jac_mode, a.cauchy_b, a.cauchy_c, J, r, cst, b1l, b2l, bk);
+    else
+#pragma unroll
+      for (int k = 0; k < 24; ++k) J[k] = 0.0;
+    cost_local += cst;
+    __syncthreads();  // previous tile's SYRK reads are done
+#pragma unroll
+    for (int k = 0; k < 24; ++k) Jt[k * JS + t] = J[k];
+    Jt[24 * JS + t] = r;
+    Jt[25 * JS + t] = 0.0, Jt[26 * JS + t] = 0.0, Jt[27 * JS + t] = 0.0;
+    sbk[t] = bk, sb1[t] = b1l, sb2[t] = b2l;
+    if (t == 0) nheads = 0;
+    __syncthreads();
+    if (valid && (t == 0 || sbk[t - 1] != bk)) heads[atomicAdd(&nheads, 1)] = t;
+    __syncthreads();
+    const int nh = nheads;
+    for (int h = 0; h < nh; ++h) {
+      const int hd = heads[h];
+      const int b  = sbk[hd];
+      if (b != cur_bk) {
+        if (cur_bk >= 0) flush();
+        cur_bk = b, cur_b1 = sb1[hd], cur_b2 = sb2[hd];
+      }
+      if (lane < 28) {
+        const int c0 = grp * 32;
+        for (int c = c0; c < c0 + 32; ++c) {
+          if (sbk[c] != b) continue;
+          double ra[4], rb[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ra[k] = Jt[(4 * bi + k) * JS + c], rb[k] = Jt[(4 * bj + k) * JS + c];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[4 * u + v] = fma(ra[u], rb[v], acc[4 * u + v]);
+        }
+      }
+    }
+  }
+  if (cur_bk >= 0) flush();
+  // cost: warp reduce, then one RED per CTA
+  for (int d = 16; d > 0; d >>= 1) cost_local += __shfl_down_sync(0xffffffffu, cost_local, d);
+  if (lane == 0) wcost[grp] = cost_local;
+  __syncthreads();
+  if (t == 0) {
+    double c = 0.0;
+    for (int k = 0; k < NGRP; ++k) c += wcost[k];
+    atomicAdd(a.B.cost[buf], c);
+  }
+}
+
+// ---- IMU factors -----------------------------------------------------------------------------------------------
+struct ImuArgs {
+  const wc_imu_state* imu;
+  int                 n_imu;
+  const double*       ts;
+  int                 K;
+  SolveBufs           B;
+  int                 at_candidate;
+  double              wg, wa, wbg, wba, dt;
+  double              grav[3];
+};
+
+struct StateCorr {
+  V3 r, t, bg, ba;
+};
+__device__ __forceinline__ void state_corr(const double* xl, const double* xr, double f, StateCorr& c) {
+  c.r  = (1 - f) * ld3(xl) + f * ld3(xr);
+  c.t  = (1 - f) * ld3(xl + 3) + f * ld3(xr + 3);
+  c.bg = (1 - f) * ld3(xl + 6) + f * ld3(xr + 6);
+  c.ba = (1 - f) * ld3(xl + 9) + f * ld3(xr + 9);
+}
+// F (cost_functor.h:446-448)
+__device__ __forceinline__ M3 imu_F(const Q4& L, const Q4& R, const V3& r) {
+  return (Jr_inv(Log((L * Exp(r)) * R)) * ToMatrix(conj(R))) * Jr(r);
+}
+__device__ __forceinline__ void add_block(double* jac, int ld, int r0, int c0, const M3& m, double s) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) jac[(r0 + i) * ld + c0 + j] += s * m.m[i][j];
+}
+
+constexpr int IMU_WARPS = 4;
+constexpr int IMU_LD    = 37;  // 36 Jacobian columns + residual
+
+// One warp per IMU triplet (BuildImuResiduals, lidar_odometry.cc:319-363).
+__global__ void __launch_bounds__(IMU_WARPS * 32) imu_linearize(ImuArgs a) {
+  __shared__ double sj[IMU_WARPS][12 * IMU_LD];
+  __shared__ int    sblk[IMU_WARPS][4];
+  LMState* st = a.B.st;
+  if (st->done || (a.at_candidate && !st->step_valid)) return;
+  const int     buf  = a.at_candidate ? 1 - st->cur : st->cur;
+  const double* x    = a.at_candidate ? a.B.xc : a.B.x;
+  double*       H    = a.B.H[buf];
+  double*       g    = a.B.g[buf];
+  const int     N    = a.B.N;
+  const int     lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int     i    = blockIdx.x * IMU_WARPS + wid;
+  if (i + 2 >= a.n_imu) return;
+  const wc_imu_state &i1 = a.imu[i], &i2 = a.imu[i + 1], &i3 = a.imu[i + 2];
+  if (i1.timestamp < a.ts[0] || i3.timestamp > a.ts[a.K - 1]) return;  // :324-329 (timestamps increase)
+  double* jac = sj[wid];
+  for (int k = lane; k < 12 * IMU_LD; k += 32) jac[k] = 0.0;
+  __syncwarp();
+  if (lane == 0) {
+    const int sp2  = upper_bound_ts(a.ts, a.K, i1.timestamp);
+    const int mode = (sp2 == a.K - 1) ? 1 : 0;
+    const int nblk = mode == 0 ? 3 : 2;
+    const double tsv[3] = {a.ts[sp2 - 1], a.ts[sp2], mode == 0 ? a.ts[sp2 + 1] : DBL_MAX};
+    const double* xs[3] = {x + 12 * (sp2 - 1), x + 12 * sp2, x + 12 * (mode == 0 ? sp2 + 1 : sp2)};
+    // ComputeStateCorr for the three IMU states (cost_functor.h:358-400)
+    StateCorr c[3];
+    int       l[3];
+    double    f[3];
+    const double tt[3] = {i1.timestamp, i2.timestamp, i3.timestamp};
+    bool         ok    = true;
+    for (int s = 0; s < 3; ++s) {
+      const double t = tt[s];
+      if (mode == 0) {
+        const bool in12 = t >= tsv[0] && t < tsv[1], in23 = t >= tsv[1] && t <= tsv[2];
+        ok   = ok && (in12 || in23);
+        l[s] = in12 ? 0 : 1;
+      } else {
+        ok   = ok && t >= tsv[0] && t <= tsv[1];
+        l[s] = 0;
+      }
+      f[s] = (t - tsv[l[s]]) / (tsv[l[s] + 1] - tsv[l[s]]);
+      state_corr(xs[l[s]], xs[l[s] + 1], f[s], c[s]);
+    }
+    if (!ok) st->err = WC_EOUT_OF_SPAN;
+    const Q4 R1 = ldq(i1.rot), R2 = ldq(i2.rot);
+    const Q4 E1R1 = Exp(c[0].r) * R1;
+    const V3 gyr_est = Log((conj(E1R1) * Exp(c[1].r)) * R2) / a.dt;
+    const V3 acc_est = ((c[2].t + ld3(i3.pos)) + (c[0].t + ld3(i1.pos)) - 2.0 * (c[1].t + ld3(i2.pos))) / (a.dt * a.dt);
+    const V3 rg  = a.wg * ((ld3(i1.gyr) + ld3(i2.gyr)) / 2.0 - gyr_est - c[0].bg);
+    const V3 ra  = a.wa * (E1R1 * (ld3(i1.acc) - c[0].ba) - acc_est + ld3(a.grav));
+    const V3 rbg = a.wbg * (c[0].bg - c[1].bg);
+    const V3 rba = a.wba * (c[0].ba - c[1].ba);
+    const double res[12] = {rg.x, rg.y, rg.z, ra.x, ra.y, ra.z, rbg.x, rbg.y, rbg.z, rba.x, rba.y, rba.z};
+    for (int k = 0; k < 12; ++k) jac[k * IMU_LD + 36] = res[k];
+    // jacobian_tau, tau1, tau2 (:301-321) dispatched to the bracketing blocks (:402-444)
+    const M3     I   = eye3();
+    const double idt = 1 / a.dt, idt2 = 1 / a.dt / a.dt;
+    {
+      const int    cl = 12 * l[0], cr = cl + 12;
+      const double wl = 1 - f[0], wr = f[0];
+      const M3     F0  = imu_F(conj(R1), Exp(c[1].r) * R2, c[0].r);
+      const M3     A30 = (ToMatrix(Exp(c[0].r)) * Hat(R1 * (ld3(i1.acc) - c[0].ba))) * Jr(c[0].r);
+      const M3     A39 = ToMatrix(E1R1);
+      for (int side = 0; side < 2; ++side) {
+        const int    c0 = side ? cr : cl;
+        const double w  = side ? wr : wl;
+        add_block(jac, IMU_LD, 0, c0 + 0, F0, w * a.wg * idt);
+        add_block(jac, IMU_LD, 0, c0 + 6, I, -w * a.wg);
+        add_block(jac, IMU_LD, 3, c0 + 0, A30, -w * a.wa);
+        add_block(jac, IMU_LD, 3, c0 + 3, I, -w * a.wa * idt2);
+        add_block(jac, IMU_LD, 3, c0 + 9, A39, -w * a.wa);
+        add_block(jac, IMU_LD, 6, c0 + 6, I, w * a.wbg);
+        add_block(jac, IMU_LD, 9, c0 + 9, I, w * a.wba);
+      }
+    }
+    {
+      const int    cl = 12 * l[1], cr = cl + 12;
+      const double wl = 1 - f[1], wr = f[1];
+      const M3     F1 = imu_F(conj(E1R1), R2, c[1].r);
+      for (int side = 0; side < 2; ++side) {
+        const int    c0 = side ? cr : cl;
+        const double w  = side ? wr : wl;
+        add_block(jac, IMU_LD, 0, c0 + 0, F1, -w * a.wg * idt);
+        add_block(jac, IMU_LD, 0, c0 + 6, I, -w * a.wg);
+        add_block(jac, IMU_LD, 3, c0 + 3, I, w * a.wa * (2 / a.dt / a.dt));
+        add_block(jac, IMU_LD, 6, c0 + 6, I, -w * a.wbg);
+        add_block(jac, IMU_LD, 9, c0 + 9, I, -w * a.wba);
+      }
+    }
+    {
+      const int    cl = 12 * l[2], cr = cl + 12;
+      const double wl = 1 - f[2], wr = f[2];
+      add_block(jac, IMU_LD, 3, cl + 3, I, -wl * a.wa * idt2);
+      add_block(jac, IMU_LD, 3, cr + 3, I, -wr * a.wa * idt2);
+    }
+    sblk[wid][0] = sp2 - 1, sblk[wid][1] = sp2, sblk[wid][2] = mode == 0 ? sp2 + 1 : -1, sblk[wid][3] = nblk;
+    double cst = 0.0;
+    for (int k = 0; k < 12; ++k) cst += 0.5 * res[k] * res[k];  // TrivialLoss
+    atomicAdd(a.B.cost[buf], cst);
+  }
+  __syncwarp();
+  const int nc = 12 * sblk[wid][3];
+  // J^T J (both triangles) and J^T r of this factor, lanes over outputs
+  for (int o = lane; o < nc * (nc + 1); o += 32) {
+    const int p = o / (nc + 1), q = o % (nc + 1);
+    const int qc = q == nc ? 36 : q;
+    double    v  = 0.0;
+#pragma unroll
+    for (int r = 0; r < 12; ++r) v = fma(jac[r * IMU_LD + p], jac[r * IMU_LD + qc], v);
+    if (v == 0.0) continue;
+    const int gp = 12 * sblk[wid][p / 12] + p % 12;
+    if (q == nc) atomicAdd(&g[gp], v);
+    else atomicAdd(&H[(size_t)gp * N + 12 * sblk[wid][q / 12] + q % 12], v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+constexpr int LMT = 512;
+
+__device__ __forceinline__ int col_of(int i, int fix_first) { return fix_first ? (i < 3 ? i : (i < 6 ? -1 : i - 3)) : i; }
+__device__ __forceinline__ int amb_of(int c, int fix_first) { return fix_first ? (c < 3 ? c : c + 3) : c; }
+
+__device__ double block_sum(double v, double* red) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int k = 0; k < LMT / 32; ++k) s += red[k];  // fixed order: identical on every thread and every rank
+  return s;
+}
+__device__ double block_max(double v, double* red) {
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, d));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int k = 0; k < LMT / 32; ++k) s = fmax(s, red[k]);
+  return s;
+}
+
+__global__ void zero_buffers(SolveBufs B, int which /*0 cur, 1 other*/) {
+  const LMState* st  = B.st;
+  const int      buf = which ? 1 - st->cur : st->cur;
+  const size_t   n   = (size_t)B.N * B.N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) B.H[buf][i] = 0.0;
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < B.N; i += blockDim.x) B.g[buf][i] = 0.0;
+    if (threadIdx.x == 0) *B.cost[buf] = 0.0;
+  }
+}
+
+// after the first linearisation: Jacobi scaling, gradient norm, initial state (TrustRegionMinimizer::Init)
+__global__ void __launch_bounds__(LMT) lm_init(SolveBufs B, wc_solve_opts o) {
+  __shared__ double red[LMT / 32];
+  LMState*      st = B.st;
+  const int     N = B.N, ff = B.fix_first;
+  const double* H = B.H[st->cur];
+  const double* g = B.g[st->cur];
+  const int     D = ff ? N - 3 : N;
+  double        gm = 0.0, xn = 0.0;
+  for (int i = threadIdx.x; i < N; i += LMT) {
+    const int c = col_of(i, ff);
+    if (c >= 0) {
+      B.scale[c] = 1.0 / (1.0 + sqrt(H[(size_t)i * N + i]));  // jacobian_scaling_, computed once
+      gm         = fmax(gm, fabs(g[i]));
+    }
+    xn += B.x[i] * B.x[i];
+  }
+  gm = block_max(gm, red);
+  xn = block_sum(xn, red);
+  if (threadIdx.x == 0) {
+    st->D = D;
+    st->x_cost = st->initial_cost = *B.cost[st->cur];
+    st->grad_max = gm, st->x_norm = sqrt(xn);
+    st->radius = o.initial_trust_region_radius, st->decrease_factor = 2.0;
+    st->reuse_diagonal = 0, st->num_consecutive_invalid = 0, st->iteration = 0, st->last_successful = 1;
+    st->num_successful = st->num_unsuccessful = 0, st->num_linearizations = 1;
+    st->termination = WC_TERM_NO_CONVERGENCE, st->done = 0, st->step_valid = 0;
+    if (!isfinite(st->x_cost)) st->done = 1, st->termination = WC_TERM_FAILURE;
+  }
+}
+
+// FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep: candidate point xc, or an invalid step
+__global__ void __launch_bounds__(LMT) lm_solve_step(SolveBufs B, wc_solve_opts o, int a_in_smem) {
+  extern __shared__ __align__(16) double sA[];
+  __shared__ double red[LMT / 32];
+  __shared__ int    fail;
+  LMState* st = B.st;
+  if (st->done) return;
+  const int t = threadIdx.x;
+  const int N = B.N, ff = B.fix_first, D = st->D;
+  if (t == 0) {
+    int term = -1;
+    if (st->iteration >= o.max_num_iterations) term = WC_TERM_NO_CONVERGENCE;
+    else if (st->last_successful && st->grad_max <= o.gradient_tolerance) term = WC_TERM_GRADIENT_TOL;
+    else if (st->radius < o.min_trust_region_radius) term = WC_TERM_MIN_RADIUS;
+    if (term >= 0) st->done = 1, st->termination = term;
+    fail = 0;
+  }
+  __syncthreads();
+  if (st->done) return;
+  const double* H = B.H[st->cur];
+  const double* g = B.g[st->cur];
+  double*       A = a_in_smem ? sA : B.A;
+  const double  radius = st->radius;
+  // LevenbergMarquardtStrategy::ComputeStep: diagonal of the scaled J^T J, clamped, refreshed only after an
+  // accepted step; A = S H S + diag / radius
+  if (!st->reuse_diagonal)
+    for (int c = t; c < D; c += LMT) {
+      const int    i = amb_of(c, ff);
+      const double d = H[(size_t)i * N + i] * B.scale[c] * B.scale[c];
+      B.diag[c]      = fmin(fmax(d, o.min_lm_diagonal), o.max_lm_diagonal);
+    }
+  __syncthreads();
+  for (int e = t; e < D * D; e += LMT) {
+    const int    r = e / D, c = e % D;
+    const double v = H[(size_t)amb_of(r, ff) * N + amb_of(c, ff)] * B.scale[r] * B.scale[c];
+    double       lm = 0.0;
+    if (r == c) {
+      const double s = sqrt(B.diag[r] / radius);
+      lm             = s * s;
+    }
+    A[e] = v + lm;
+  }
+  __syncthreads();
+  // right-looking Cholesky, lower triangle, in place
+  for (int j = 0; j < D; ++j) {
+    const double djj = A[j * D + j];
+    if (!(djj > 0.0) || !isfinite(djj)) {
+      if (t == 0) fail = 1;
+      break;  // uniform: every thread reads the same value
+    }
+    const double d = sqrt(djj);
+    __syncthreads();
+    for (int i = j + t; i < D; i += LMT) A[i * D + j] = (i == j) ? d : A[i * D + j] / d;
+    __syncthreads();
+    const int m = D - j - 1;
+    for (int e = t; e < m * m; e += LMT) {
+      const int r = j + 1 + e / m, c = j + 1 + e % m;
+      if (c <= r) A[r * D + c] -= A[r * D + j] * A[c * D + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  bool valid = !fail;
+  // solve A y = gs, step = -y (column-oriented substitutions)
+  double* y = B.step;
+  if (valid) {
+    for (int c = t; c < D; c += LMT) y[c] = g[amb_of(c, ff)] * B.scale[c];
+    __syncthreads();
+    for (int j = 0; j < D; ++j) {
+      const double yj = y[j] / A[j * D + j];
+      __syncthreads();
+      if (t == 0) y[j] = yj;
+      for (int i = j + 1 + t; i < D; i += LMT) y[i] -= A[i * D + j] * yj;
+      __syncthreads();
+    }
+    for (int j = D - 1; j >= 0; --j) {
+      const double yj = y[j] / A[j * D + j];
+      __syncthreads();
+      if (t == 0) y[j] = yj;
+      for (int i = t; i < j; i += LMT) y[i] -= A[j * D + i] * yj;
+      __syncthreads();
+    }
+    for (int c = t; c < D; c += LMT) y[c] = -y[c];
+    __syncthreads();
+  }
+  // model_cost_change = -step^T (gs + Hs step / 2), Hs = S H S without damping
+  double part = 0.0, bad = 0.0;
+  if (valid)
+    for (int r = t; r < D; r += LMT) {
+      const int i  = amb_of(r, ff);
+      double    hd = 0.0;
+      for (int c = 0; c < D; ++c) hd = fma(H[(size_t)i * N + amb_of(c, ff)] * B.scale[c], y[c], hd);
+      hd *= B.scale[r];
+      part -= y[r] * (g[i] * B.scale[r] + 0.5 * hd);
+      if (!isfinite(y[r])) bad = 1.0;
+    }
+  const double mcc  = block_sum(part, red);
+  const double nbad = block_sum(bad, red);
+  valid             = valid && nbad == 0.0 && mcc > 0.0;
+  // delta = step .* scale, candidate, step norm
+  double sn = 0.0;
+  for (int i = t; i < N; i += LMT) {
+    const int    c = col_of(i, ff);
+    const double d = (valid && c >= 0) ? y[c] * B.scale[c] : 0.0;
+    B.xc[i]        = B.x[i] + d;
+    sn += d * d;
+  }
+  sn = block_sum(sn, red);
+  if (t == 0) {
+    st->iteration += 1;
+    st->last_successful   = 0;
+    st->reuse_diagonal    = 1;
+    st->step_valid        = valid ? 1 : 0;
+    st->model_cost_change = mcc;
+    st->step_norm         = sqrt(sn);
+    const int it          = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
+    st->iter_radius[it]   = radius;
+  }
+}
+
+// after the candidate evaluation: tolerances, accept / reject, trust-region update
+__global__ void __launch_bounds__(LMT) lm_decide(SolveBufs B, wc_solve_opts o) {
+  __shared__ double red[LMT / 32];
+  __shared__ int    accept;
+  LMState* st = B.st;
+  if (st->done) return;
+  const int t = threadIdx.x, N = B.N, ff = B.fix_first;
+  const int it = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
+  if (t == 0) {
+    accept = 0;
+    if (!st->step_valid) {  // HandleInvalidStep
+      st->num_unsuccessful += 1;
+      st->iter_cost[it] = nan(""), st->iter_accepted[it] = 0;
+      if (++st->num_consecutive_invalid >= 5) st->done = 1, st->termination = WC_TERM_FAILURE;
+      else st->radius = st->radius / st->decrease_factor, st->decrease_factor *= 2.0, st->reuse_diagonal = 1;
+    } else {
+      st->num_consecutive_invalid = 0;
+      st->num_linearizations += 1;
+      double cand = *B.cost[1 - st->cur];
+      if (!isfinite(cand)) cand = DBL_MAX;
+      st->iter_cost[it] = cand;
+      st->iter_accepted[it] = 0;
+      if (st->step_norm <= o.parameter_tolerance * (st->x_norm + o.parameter_tolerance)) {
+        st->done = 1, st->termination = WC_TERM_PARAMETER_TOL;
+      } else if (fabs(st->x_cost - cand) <= o.function_tolerance * st->x_cost) {
+        st->done = 1, st->termination = WC_TERM_FUNCTION_TOL;
+      } else {
+        const double rd = (st->x_cost - cand) / st->model_cost_change;
+        if (rd > o.min_relative_decrease) {
+          accept = 1;
+          st->x_cost = cand;
+          st->cur    = 1 - st->cur;
+          st->iter_accepted[it] = 1;
+          st->num_successful += 1;
+          st->last_successful = 1;
+          const double d  = 1.0 - pow(2.0 * rd - 1.0, 3);
+          st->radius      = fmin(o.max_trust_region_radius, st->radius / fmax(1.0 / 3.0, d));
+          st->decrease_factor = 2.0, st->reuse_diagonal = 0;
+        } else {
+          st->num_unsuccessful += 1;
+          st->radius = st->radius / st->decrease_factor, st->decrease_factor *= 2.0, st->reuse_diagonal = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!accept) return;
+  const double* g = B.g[st->cur];
+  double gm = 0.0, xn = 0.0;
+  for (int i = t; i < N; i += LMT) {
+    const double v = B.xc[i];
+    B.x[i]         = v;
+    xn += v * v;
+    if (col_of(i, ff) >= 0) gm = fmax(gm, fabs(g[i]));
+  }
+  gm = block_max(gm, red);
+  xn = block_sum(xn, red);
+  if (t == 0) st->grad_max = gm, st->x_norm = sqrt(xn);
+}
+
+__global__ void extract_ts(const wc_sample_state* __restrict__ s, int K, double* __restrict__ ts, double* __restrict__ x) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  ts[k] = s[k].timestamp;
+  for (int j = 0; j < 12; ++j) x[12 * k + j] = s[k].data_cor[j];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host
+struct wc_solve_mem {
+  double*  ts;
+  double*  tmp;
+  double*  rec;
+  int*     bucket;
+  int*     hist;
+  int*     off;
+  int*     cursor;
+  int      stride;
+  int      nb_cap;
+  double*  Hbuf[2];
+  double*  gbuf[2];
+  double*  cost;  // 2 doubles
+  double*  scale;
+  double*  diag;
+  double*  step;
+  double*  A;
+  int      Ncap;
+  LMState* st;
+  LMState* h_st;
+  double*  h_x;
+  double   grav[3];
+};
+
+static wc_status solve_alloc(wc_ctx* c) {
+  if (c->d_lm) return WC_OK;
+  wc_solve_mem* m = (wc_solve_mem*)calloc(1, sizeof(wc_solve_mem));
+  c->d_lm         = m;
+  const size_t ns = (size_t)c->prm.max_surfels, nc = (size_t)c->prm.max_corrs, K = (size_t)c->prm.max_samples;
+  const size_t N  = 12 * K;
+  m->stride       = (int)((nc + 255) & ~(size_t)255);
+  m->nb_cap       = (int)(K * K);
+  m->Ncap         = (int)N;
+  WC_CUDA(c, cudaMalloc(&c->d_sld, ns * sizeof(wc_surfel)));
+  WC_CUDA(c, cudaMalloc(&c->d_fix, ns * sizeof(wc_surfel)));
+  WC_CUDA(c, cudaMalloc(&c->d_sld_corr, nc * sizeof(wc_corr_idx)));
+  WC_CUDA(c, cudaMalloc(&c->d_fix_corr, nc * sizeof(wc_corr_idx)));
+  WC_CUDA(c, cudaMalloc(&c->d_imu, (size_t)c->prm.max_imu_states * sizeof(wc_imu_state)));
+  WC_CUDA(c, cudaMalloc(&c->d_samples, K * sizeof(wc_sample_state)));
+  WC_CUDA(c, cudaMalloc(&m->ts, K * 8));
+  WC_CUDA(c, cudaMalloc(&m->tmp, (size_t)REC_COLS * m->stride * 8));
+  WC_CUDA(c, cudaMalloc(&m->rec, (size_t)REC_COLS * m->stride * 8));
+  WC_CUDA(c, cudaMalloc(&m->bucket, (size_t)m->stride * 4));
+  WC_CUDA(c, cudaMalloc(&m->hist, (size_t)m->nb_cap * 4));
+  WC_CUDA(c, cudaMalloc(&m->off, (size_t)m->nb_cap * 4));
+  WC_CUDA(c, cudaMalloc(&m->cursor, (size_t)m->nb_cap * 4));
+  for (int b = 0; b < 2; ++b) {
+    WC_CUDA(c, cudaMalloc(&m->Hbuf[b], N * N * 8));
+    WC_CUDA(c, cudaMalloc(&m->gbuf[b], N * 8));
+  }
+  WC_CUDA(c, cudaMalloc(&m->cost, 16));
+  WC_CUDA(c, cudaMalloc(&m->scale, N * 8));
+  WC_CUDA(c, cudaMalloc(&m->diag, N * 8));
+  WC_CUDA(c, cudaMalloc(&m->step, N * 8));
+  WC_CUDA(c, cudaMalloc(&m->A, N * N * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_x, N * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_xc, N * 8));
+  WC_CUDA(c, cudaMalloc(&c->d_x0, N * 8));
+  WC_CUDA(c, cudaMalloc(&m->st, sizeof(LMState)));
+  WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
+  WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
+  WC_CUDA(c, cudaFuncSetAttribute(lidar_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, JR * JS * 8));
+  WC_CUDA(c, cudaFuncSetAttribute(lm_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return WC_OK;
+}
+
+void wc_solve_free(wc_ctx* c) {
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  void* ptrs[] = {c->d_sld, c->d_fix, c->d_sld_corr, c->d_fix_corr, c->d_imu, c->d_samples, c->d_x, c->d_xc, c->d_x0};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (!m) return;
+  void* mp[] = {m->ts, m->tmp, m->rec, m->bucket, m->hist, m->off, m->cursor, m->Hbuf[0], m->Hbuf[1], m->gbuf[0], m->gbuf[1],
+                m->cost, m->scale, m->diag, m->step, m->A, m->st};
+  for (void* p : mp)
+    if (p) cudaFree(p);
+  if (m->h_st) cudaFreeHost(m->h_st);
+  if (m->h_x) cudaFreeHost(m->h_x);
+  free(m);
+  c->d_lm = nullptr;
+}
+
+static SolveBufs make_bufs(wc_ctx* c, int fix_first) {
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  SolveBufs     B;
+  for (int b = 0; b < 2; ++b) B.H[b] = m->Hbuf[b], B.g[b] = m->gbuf[b], B.cost[b] = m->cost + b;
+  B.x = c->d_x, B.xc = c->d_xc, B.scale = m->scale, B.diag = m->diag, B.step = m->step, B.A = m->A, B.st = m->st;
+  B.N = (int)(12 * c->K), B.fix_first = fix_first;
+  return B;
+}
+
+extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_sld, const wc_surfel* fix, size_t n_fix,
+                                      const wc_corr_idx* sld_corr, size_t n_sld_corr, const wc_corr_idx* fix_corr,
+                                      size_t n_fix_corr, const wc_imu_state* imu, size_t n_imu,
+                                      const wc_sample_state* samples, size_t K) {
+  if (!c || !samples || K < 2 || (n_sld && !sld) || (n_fix && !fix) || (n_sld_corr && !sld_corr) || (n_fix_corr && !fix_corr) ||
+      (n_imu && !imu))
+    return WC_EINVAL;
+  wc_status s = solve_alloc(c);
+  if (s) return s;
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  if (n_sld > (size_t)c->prm.max_surfels || n_fix > (size_t)c->prm.max_surfels) WC_FAIL(c, WC_ECAPACITY, "too many surfels");
+  if (n_sld_corr + n_fix_corr > (size_t)c->prm.max_corrs) WC_FAIL(c, WC_ECAPACITY, "too many correspondences");
+  if (K > (size_t)c->prm.max_samples) WC_FAIL(c, WC_ECAPACITY, "too many sample states");
+  if (n_imu > (size_t)c->prm.max_imu_states) WC_FAIL(c, WC_ECAPACITY, "too many IMU states");
+  cudaStream_t st = c->stream;
+  c->n_sld = n_sld, c->n_fix = n_fix, c->n_sld_corr = n_sld_corr, c->n_fix_corr = n_fix_corr, c->n_imu = n_imu, c->K = K;
+  if (n_sld) WC_CUDA(c, cudaMemcpyAsync(c->d_sld, sld, n_sld * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
+  if (n_fix) WC_CUDA(c, cudaMemcpyAsync(c->d_fix, fix, n_fix * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
+  if (n_sld_corr) WC_CUDA(c, cudaMemcpyAsync(c->d_sld_corr, sld_corr, n_sld_corr * sizeof(wc_corr_idx), cudaMemcpyHostToDevice, st));
+  if (n_fix_corr) WC_CUDA(c, cudaMemcpyAsync(c->d_fix_corr, fix_corr, n_fix_corr * sizeof(wc_corr_idx), cudaMemcpyHostToDevice, st));
+  if (n_imu) WC_CUDA(c, cudaMemcpyAsync(c->d_imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
+  WC_CUDA(c, cudaMemcpyAsync(c->d_samples, samples, K * sizeof(wc_sample_state), cudaMemcpyHostToDevice, st));
+  for (int k = 0; k < 3; ++k) m->grav[k] = samples[K - 1].grav[k];  // lidar_odometry.cc:341,355
+  c->n_imu_blocks = 0;  // BuildImuResiduals' block count (:320-329), for the summary only
+  for (size_t i = 0; i + 2 < n_imu; ++i)
+    if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) ++c->n_imu_blocks;
+  extract_ts<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(c->d_samples, (int)K, m->ts, c->d_x0);
+  // factor construction for this rank's slice of the correspondence list, bucketed by interval pair
+  const int C  = (int)(n_sld_corr + n_fix_corr);
+  const int c0 = (int)((long long)C * c->rank / c->world), c1 = (int)((long long)C * (c->rank + 1) / c->world);
+  c->n_rec     = (size_t)(c1 - c0);
+  const int nb = (int)(K * K);
+  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
+  WC_CUDA(c, cudaMemsetAsync(m->hist, 0, (size_t)nb * 4, st));
+  WC_CUDA(c, cudaMemsetAsync(m->cursor, 0, (size_t)nb * 4, st));
+  if (c->n_rec) {
+    PackArgs a;
+    a.sld = c->d_sld, a.fix = c->d_fix, a.sld_corr = c->d_sld_corr, a.fix_corr = c->d_fix_corr;
+    a.n_sld = (int)n_sld, a.n_fix = (int)n_fix, a.n_sld_corr = (int)n_sld_corr, a.n_fix_corr = (int)n_fix_corr;
+    a.c0 = c0, a.c1 = c1, a.ts = m->ts, a.K = (int)K, a.weight_floor = c->prm.weight_floor;
+    a.tmp = m->tmp, a.stride = m->stride, a.bucket = m->bucket, a.hist = m->hist, a.st = m->st;
+    const unsigned grid = (unsigned)((c->n_rec + 255) / 256);
+    corr_pack<<<grid, 256, 0, st>>>(a);
+    bucket_scan<<<1, 1024, 0, st>>>(m->hist, nb, m->off);
+    bucket_scatter<<<grid, 256, 0, st>>>(m->tmp, m->bucket, (int)c->n_rec, m->stride, m->off, m->cursor, m->rec);
+  }
+  WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (m->h_st->err == WC_EINVAL) WC_FAIL(c, WC_EINVAL, "correspondence index out of range");
+  if (m->h_st->err == WC_EINVAL_TIME_ORDER) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "correspondence with timestamp(s1) >= timestamp(s2)");
+  if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the sample-state span");
+  return WC_OK;
+}
+
+// enqueue one linearisation (lidar + IMU [+ exchange]) on the ctx stream
+static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_solve_opts* o, int at_candidate) {
+  wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
+  cudaStream_t  st = c->stream;
+  SolveBufs     B  = B_in;
+  if (c->world > 1) {
+    // sharded: accumulate into this rank's exchange partial; comm_allreduce sums the ranks into the real buffers
+    double *pH, *pg, *pc;
+    wc_comm_partial_views(c, &pH, &pg, &pc);
+    B.H[0] = B.H[1] = pH, B.g[0] = B.g[1] = pg, B.cost[0] = B.cost[1] = pc;
+  }
+  zero_buffers<<<64, 256, 0, st>>>(B, at_candidate);
+  if (c->n_rec) {
+    LinArgs a;
+    a.rec = m->rec, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
+    a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
+    const int ntiles = (int)((c->n_rec + LT - 1) / LT);
+    const int grid   = ntiles < c->num_sms ? ntiles : c->num_sms;
+    lidar_linearize<<<grid, LT, JR * JS * 8, st>>>(a);
+  }
+  if (o->use_imu_factors && c->n_imu >= 3 && c->rank == 0) {
+    ImuArgs a;
+    a.imu = c->d_imu, a.n_imu = (int)c->n_imu, a.ts = m->ts, a.K = (int)c->K, a.B = B, a.at_candidate = at_candidate;
+    a.wg = c->prm.weight_gyr, a.wa = c->prm.weight_acc, a.wbg = c->prm.weight_bg, a.wba = c->prm.weight_ba;
+    a.dt = 1.0 / c->prm.imu_rate;
+    for (int k = 0; k < 3; ++k) a.grav[k] = m->grav[k];
+    imu_linearize<<<(unsigned)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS), IMU_WARPS * 32, 0, st>>>(a);
+  }
+  WC_CUDA(c, cudaGetLastError());
+  return WC_OK;
+}
+
+static void fill_summary(const wc_ctx* c, const LMState* s, wc_solve_summary* sum) {
+  memset(sum, 0, sizeof(*sum));
+  sum->initial_cost = s->initial_cost, sum->final_cost = s->x_cost;
+  sum->num_iterations = s->iteration, sum->num_successful_steps = s->num_successful;
+  sum->num_unsuccessful_steps = s->num_unsuccessful, sum->termination = s->termination;
+  sum->num_residual_blocks_sld = (int)c->n_sld_corr, sum->num_residual_blocks_fix = (int)c->n_fix_corr;
+  sum->num_linearizations = s->num_linearizations;
+  sum->num_residual_blocks_imu = c->n_imu_blocks;
+  for (int i = 0; i < WC_MAX_ITER_LOG; ++i)
+    sum->iter_cost[i] = s->iter_cost[i], sum->iter_radius[i] = s->iter_radius[i], sum->iter_accepted[i] = s->iter_accepted[i];
+}
+
+extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* opts, wc_solve_summary* summary,
+                                              double* data_cor_out) {
+  if (!c || !c->d_lm || c->K < 2) return WC_EINVAL;
+  wc_solve_opts o;
+  if (opts) o = *opts; else wc_default_solve_opts(&o);
+  wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
+  cudaStream_t  st = c->stream;
+  const int     N  = (int)(12 * c->K);
+  SolveBufs     B  = make_bufs(c, o.fix_first_position ? 1 : 0);
+  const int     D  = o.fix_first_position ? N - 3 : N;
+  const int     a_in_smem   = (size_t)D * D * 8 <= 200 * 1024;
+  const size_t  smem        = a_in_smem ? (size_t)D * D * 8 : 0;
+  WC_CUDA(c, cudaEventRecord(c->ev[4], st));
+  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
+  WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+  wc_status s = enqueue_linearize(c, B, &o, 0);
+  if (s) return s;
+  if ((s = wc_comm_allreduce(c, 0))) return s;
+  lm_init<<<1, LMT, 0, st>>>(B, o);
+  const int batch = 4;
+  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 8; it += batch) {
+    for (int b = 0; b < batch; ++b) {
+      lm_solve_step<<<1, LMT, smem, st>>>(B, o, a_in_smem);
+      if ((s = enqueue_linearize(c, B, &o, 1))) return s;
+      if ((s = wc_comm_allreduce(c, 1))) return s;
+      lm_decide<<<1, LMT, 0, st>>>(B, o);
+    }
+    WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+    WC_CUDA(c, cudaStreamSynchronize(st));
+    done = m->h_st->done;
+  }
+  WC_CUDA(c, cudaMemcpyAsync(m->h_x, c->d_x, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaEventRecord(c->ev[5], st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "IMU state outside its sample interval (cost_functor.h:367,390)");
+  if ((s = wc_comm_check(c))) return s;
+  if (summary) {
+    fill_summary(c, m->h_st, summary);
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+    summary->gpu_ms_total = ms;
+  }
+  if (data_cor_out) memcpy(data_cor_out, m->h_x, (size_t)N * 8);
+  if (m->h_st->termination == WC_TERM_FAILURE) WC_FAIL(c, WC_ENUMERIC, "solve failed: non-finite cost or 5 consecutive invalid steps");
+  return WC_OK;
+}
+
+extern "C" wc_status wc_window_solve(wc_ctx* c, const wc_surfel* sld, size_t n_sld, const wc_surfel* fix, size_t n_fix,
+                                     const wc_corr_idx* sld_corr, size_t n_sld_corr, const wc_corr_idx* fix_corr,
+                                     size_t n_fix_corr, const wc_imu_state* imu, size_t n_imu, wc_sample_state* samples,
+                                     size_t K, const wc_solve_opts* opts, wc_solve_summary* summary) {
+  wc_status s = wc_window_upload(c, sld, n_sld, fix, n_fix, sld_corr, n_sld_corr, fix_corr, n_fix_corr, imu, n_imu, samples, K);
+  if (s) return s;
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  s               = wc_window_solve_resident(c, opts, summary, nullptr);
+  if (s && s != WC_ENUMERIC) return s;
+  for (size_t k = 0; k < K; ++k)
+    for (int j = 0; j < 12; ++j) samples[k].data_cor[j] = m->h_x[12 * k + j];  // in place, like SampleState::data_cor
+  return s;
+}
+
+extern "C" wc_status wc_window_evaluate(wc_ctx* c, const wc_surfel* sld, size_t n_sld, const wc_surfel* fix, size_t n_fix,
+                                        const wc_corr_idx* sld_corr, size_t n_sld_corr, const wc_corr_idx* fix_corr,
+                                        size_t n_fix_corr, const wc_imu_state* imu, size_t n_imu,
+                                        const wc_sample_state* samples, size_t K, const wc_solve_opts* opts, double* cost,
+                                        double* grad, double* jtj) {
+  wc_status s = wc_window_upload(c, sld, n_sld, fix, n_fix, sld_corr, n_sld_corr, fix_corr, n_fix_corr, imu, n_imu, samples, K);
+  if (s) return s;
+  wc_solve_opts o;
+  if (opts) o = *opts; else wc_default_solve_opts(&o);
+  wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
+  cudaStream_t  st = c->stream;
+  const size_t  N  = 12 * K;
+  SolveBufs     B  = make_bufs(c, 0);
+  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
+  WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, N * 8, cudaMemcpyDeviceToDevice, st));
+  if ((s = enqueue_linearize(c, B, &o, 0))) return s;
+  if ((s = wc_comm_allreduce(c, 0))) return s;
+  if (cost) WC_CUDA(c, cudaMemcpyAsync(cost, m->cost, 8, cudaMemcpyDeviceToHost, st));
+  if (grad) WC_CUDA(c, cudaMemcpyAsync(grad, m->gbuf[0], N * 8, cudaMemcpyDeviceToHost, st));
+  if (jtj) WC_CUDA(c, cudaMemcpyAsync(jtj, m->Hbuf[0], N * N * 8, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "IMU state outside its sample interval");
+  return WC_OK;
+}
+
+// accessors used by the exchange layer (wc_comm.cu): the packed [H | g | cost] of a buffer
+void wc_solve_exchange_views(wc_ctx* c, int which, double** H, double** g, double** cost, int* N, void** state) {
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  (void)which;
+  H[0] = m->Hbuf[0], H[1] = m->Hbuf[1], g[0] = m->gbuf[0], g[1] = m->gbuf[1], cost[0] = m->cost, cost[1] = m->cost + 1;
+  *N     = (int)(12 * c->K);
+  *state = m->st;
+}

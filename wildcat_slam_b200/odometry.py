@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's src/odometry interface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference's C++ symbols (with CHECK aborts turned into
+WildcatError carrying a wc_status):
+
+  BuildSurfels(cloud)                        <- surfel_extraction.h:145-147
+  UpdateSurfelPoses(imu_states, surfels)     <- lidar_odometry.cc:160-170
+  KnnSurfelMatcher().BuildIndex / .Match     <- knn_surfel_matcher.h:17-19
+  SolveWindow(...)                           <- Build*Residuals + ceres::Solve, lidar_odometry.cc:254-363,541-561
+  CubicBSplineInterpolator(ts, pts).Interp   <- spline_interpolation.h:42-113
+  ApplyCorrections(samples, imu)             <- UpdateImuPoses + UpdateSamplePoses, lidar_odometry.cc:172-215
+
+Arrays are numpy structured arrays of the dtypes in wildcat_slam_b200.types (layout-identical to the reference's
+structs).  Every call runs on the CUDA device owned by the Context; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from . import types as T
+
+
+class Context:
+    """wc_ctx: device memory, stream and (multi-GPU) peer mappings.  One per thread / per GPU."""
+
+    def __init__(self, device=0, params=None):
+        self.lib = abi.load()
+        self.params = params or T.default_params()
+        self._h = C.c_void_p()
+        st = self.lib.wc_create(C.byref(self.params), int(device), C.byref(self._h))
+        if st != T.WC_OK:
+            raise abi.WildcatError(st, "wc_create", "(no CUDA device? the library has no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self.lib.wc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st, where):
+        if st != T.WC_OK:
+            raise abi.WildcatError(st, where, self.lib.wc_last_error(self._h).decode(errors="replace"))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stream(self):
+        return self.lib.wc_stream(self._h)
+
+    # ---- multi-GPU residual sharding -------------------------------------------------------------------------
+    def comm_export(self):
+        h = np.zeros(64, dtype=np.uint8)
+        self.check(self.lib.wc_comm_export(self._h, T.ptr(h)), "wc_comm_export")
+        return h
+
+    def comm_connect(self, rank, world, all_handles):
+        all_handles = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world * 64)
+        self.check(self.lib.wc_comm_connect(self._h, rank, world, T.ptr(all_handles)), "wc_comm_connect")
+
+    def comm_disconnect(self):
+        self.check(self.lib.wc_comm_disconnect(self._h), "wc_comm_disconnect")
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def BuildSurfels(cloud, ctx=None, want_assign=False, timing=None):
+    """void BuildSurfels(const std::vector<hilti_ros::Point>&, std::deque<Surfel::Ptr>&, GlobalMap&).
+
+    cloud: POINT48 array with non-decreasing time.  Returns the surfels sorted by timestamp (world frame), and the
+    per-point (voxel, leaf) assignment when want_assign."""
+    ctx = ctx or default_context()
+    cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
+    cap = int(ctx.params.max_surfels)
+    out = np.zeros(cap, dtype=T.SURFEL)
+    assign = np.zeros(len(cloud), dtype=T.ASSIGN) if want_assign else None
+    n_out = C.c_size_t(0)
+    ms = C.c_double(0)
+    st = ctx.lib.wc_build_surfels(ctx.handle, T.ptr(cloud), len(cloud), T.ptr(out), cap, C.byref(n_out), T.ptr(assign),
+                                  C.byref(ms))
+    ctx.check(st, "wc_build_surfels")
+    if timing is not None:
+        timing["gpu_ms"] = ms.value
+    surfels = out[: n_out.value].copy()
+    return (surfels, assign) if want_assign else surfels
+
+
+def UpdateSurfelPoses(imu_states, surfels, ctx=None):
+    """UpdateSurfelPoses(const std::deque<ImuState>&, std::deque<Surfel::Ptr>&): returns the updated copy."""
+    ctx = ctx or default_context()
+    imu = np.ascontiguousarray(imu_states, dtype=T.IMU)
+    s = np.ascontiguousarray(surfels, dtype=T.SURFEL).copy()
+    ctx.check(ctx.lib.wc_update_surfel_poses(ctx.handle, T.ptr(imu), len(imu), T.ptr(s), len(s)), "wc_update_surfel_poses")
+    return s
+
+
+class KnnSurfelMatcher:
+    """class KnnSurfelMatcher (knn_surfel_matcher.h:10-42)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self.target_surfels_ = None
+
+    def BuildIndex(self, surfels):
+        if len(surfels) == 0:  # knn_surfel_matcher.cc:4-6
+            return
+        self.target_surfels_ = np.ascontiguousarray(surfels, dtype=T.SURFEL)
+
+    def Match(self, surfels, timing=None):
+        """Returns (correspondences CORR[], first_is_target uint8[]).  When the query array is the array the index
+        was built from, both indices address it (sliding-window matcher); otherwise s1/s2 are time ordered and
+        first_is_target tells which array s1 indexes (fixed-window matcher: always the target)."""
+        q = np.ascontiguousarray(surfels, dtype=T.SURFEL)
+        if self.target_surfels_ is None or len(q) == 0:
+            return np.zeros(0, T.CORR), np.zeros(0, np.uint8)
+        t = self.target_surfels_
+        self_match = int(t.ctypes.data == q.ctypes.data or (len(t) == len(q) and t.tobytes() == q.tobytes()))
+        out = np.zeros(len(q), dtype=T.CORR)
+        fit = np.zeros(len(q), dtype=np.uint8)
+        n = C.c_size_t(0)
+        ms = C.c_double(0)
+        st = self.ctx.lib.wc_match(self.ctx.handle, T.ptr(q), len(q), T.ptr(t), len(t), self_match, T.ptr(out), len(out),
+                                   C.byref(n), T.ptr(fit), C.byref(ms))
+        self.ctx.check(st, "wc_match")
+        if timing is not None:
+            timing["gpu_ms"] = ms.value
+        return out[: n.value].copy(), fit[: n.value].copy()
+
+    def KNearestSearchVectors(self, query6, target6, k=10):
+        """FLANNBuildIndex + FLANNKNearestSearch on raw 6-vectors (knn_surfel_matcher_test.cc:19-43)."""
+        q = np.ascontiguousarray(query6, dtype=np.float64)
+        t = np.ascontiguousarray(target6, dtype=np.float64)
+        idx = np.zeros((len(q), k), dtype=np.int32)
+        d2 = np.zeros((len(q), k), dtype=np.float64)
+        st = self.ctx.lib.wc_knn6(self.ctx.handle, T.ptr(q), len(q), T.ptr(t), len(t), k, T.ptr(idx), T.ptr(d2))
+        self.ctx.check(st, "wc_knn6")
+        return idx, d2
+
+
+def _window_arrays(sld, fix, sld_corr, fix_corr, imu, samples):
+    sld = np.ascontiguousarray(sld, dtype=T.SURFEL)
+    fix = np.ascontiguousarray(fix if fix is not None else np.zeros(0, T.SURFEL), dtype=T.SURFEL)
+    sc = np.ascontiguousarray(sld_corr if sld_corr is not None else np.zeros(0, T.CORR), dtype=T.CORR)
+    fc = np.ascontiguousarray(fix_corr if fix_corr is not None else np.zeros(0, T.CORR), dtype=T.CORR)
+    imu = np.ascontiguousarray(imu if imu is not None else np.zeros(0, T.IMU), dtype=T.IMU)
+    smp = np.ascontiguousarray(samples, dtype=T.SAMPLE).copy()
+    args = [T.ptr(sld), len(sld), T.ptr(fix), len(fix), T.ptr(sc), len(sc), T.ptr(fc), len(fc), T.ptr(imu), len(imu),
+            T.ptr(smp), len(smp)]
+    return (sld, fix, sc, fc, imu, smp), args
+
+
+def SolveWindow(sld, fix, sld_corr, fix_corr, imu, samples, opts=None, ctx=None):
+    """BuildSldWinLidarResiduals + BuildFixWinLidarResiduals + BuildImuResiduals + ceres::Solve.
+
+    Returns (samples with data_cor overwritten by the solution, SolveSummary)."""
+    ctx = ctx or default_context()
+    o = opts or T.default_solve_opts()
+    keep, args = _window_arrays(sld, fix, sld_corr, fix_corr, imu, samples)
+    summ = T.SolveSummary()
+    st = ctx.lib.wc_window_solve(ctx.handle, *args, C.byref(o), C.byref(summ))
+    ctx.check(st, "wc_window_solve")
+    return keep[5], summ
+
+
+def EvaluateWindow(sld, fix, sld_corr, fix_corr, imu, samples, opts=None, ctx=None, want_jtj=True):
+    """ceres::Problem::Evaluate-like hook: cost, gradient and J^T J of the robustified problem at samples.data_cor."""
+    ctx = ctx or default_context()
+    o = opts or T.default_solve_opts()
+    keep, args = _window_arrays(sld, fix, sld_corr, fix_corr, imu, samples)
+    n = 12 * len(keep[5])
+    cost = C.c_double(0)
+    grad = np.zeros(n)
+    jtj = np.zeros((n, n)) if want_jtj else None
+    st = ctx.lib.wc_window_evaluate(ctx.handle, *args, C.byref(o), C.byref(cost), T.ptr(grad), T.ptr(jtj))
+    ctx.check(st, "wc_window_evaluate")
+    return cost.value, grad, jtj
+
+
+class ResidentWindow:
+    """Upload a window once, then solve repeatedly from the uploaded starting point (benchmark / multi-GPU path)."""
+
+    def __init__(self, sld, fix, sld_corr, fix_corr, imu, samples, ctx=None):
+        self.ctx = ctx or default_context()
+        self._keep, args = _window_arrays(sld, fix, sld_corr, fix_corr, imu, samples)
+        self.K = len(self._keep[5])
+        self.ctx.check(self.ctx.lib.wc_window_upload(self.ctx.handle, *args), "wc_window_upload")
+
+    def solve(self, opts=None):
+        o = opts or T.default_solve_opts()
+        summ = T.SolveSummary()
+        x = np.zeros((self.K, 12))
+        st = self.ctx.lib.wc_window_solve_resident(self.ctx.handle, C.byref(o), C.byref(summ), T.ptr(x))
+        self.ctx.check(st, "wc_window_solve_resident")
+        return x, summ
+
+
+class CubicBSplineInterpolator:
+    """class CubicBSplineInterpolator (spline_interpolation.h:42-113); Interp returns None where the reference
+    returns nullptr."""
+
+    def __init__(self, timestamps, points, ctx=None):
+        self.ctx = ctx or default_context()
+        self.timestamps_ = np.ascontiguousarray(timestamps, dtype=np.float64)
+        self.points_ = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        if len(self.timestamps_) != len(self.points_):  # CHECK_EQ :47
+            raise abi.WildcatError(T.WC_EINVAL, "CubicBSplineInterpolator", "timestamps.size() != points.size()")
+
+    def InterpMany(self, ts):
+        q = np.ascontiguousarray(np.atleast_1d(ts), dtype=np.float64)
+        out = np.zeros((len(q), 3))
+        valid = np.zeros(len(q), dtype=np.uint8)
+        st = self.ctx.lib.wc_spline_fit_eval(self.ctx.handle, T.ptr(self.timestamps_), T.ptr(self.points_), len(self.timestamps_),
+                                             T.ptr(q), len(q), T.ptr(out), T.ptr(valid))
+        self.ctx.check(st, "wc_spline_fit_eval")
+        return out, valid.astype(bool)
+
+    def Interp(self, timestamp):
+        out, valid = self.InterpMany([timestamp])
+        return out[0] if valid[0] else None
+
+
+def ApplyCorrections(samples, imu_states, ctx=None):
+    """UpdateImuPoses(sample_states, imu_states) then UpdateSamplePoses(sample_states): returns updated copies."""
+    ctx = ctx or default_context()
+    s = np.ascontiguousarray(samples, dtype=T.SAMPLE).copy()
+    imu = np.ascontiguousarray(imu_states, dtype=T.IMU).copy()
+    ctx.check(ctx.lib.wc_apply_corrections(ctx.handle, T.ptr(s), len(s), T.ptr(imu), len(imu)), "wc_apply_corrections")
+    return s, imu
+
+
+class ResidentSweep:
+    """Upload a sweep once, extract repeatedly (the "inputs resident in HBM" leg of the benchmark)."""
+
+    def __init__(self, cloud, ctx=None):
+        self.ctx = ctx or default_context()
+        self.cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
+        self.ctx.check(self.ctx.lib.wc_points_upload(self.ctx.handle, T.ptr(self.cloud), len(self.cloud)), "wc_points_upload")
+
+    def extract(self):
+        n = C.c_size_t(0)
+        k, e, t = C.c_double(0), C.c_double(0), C.c_double(0)
+        st = self.ctx.lib.wc_build_surfels_resident(self.ctx.handle, C.byref(n), C.byref(k), C.byref(e), C.byref(t))
+        self.ctx.check(st, "wc_build_surfels_resident")
+        return n.value, dict(keys_ms=k.value, emit_ms=e.value, total_ms=t.value)
+
+    def fetch(self):
+        cap = int(self.ctx.params.max_surfels)
+        out = np.zeros(cap, dtype=T.SURFEL)
+        n = C.c_size_t(0)
+        self.ctx.check(self.ctx.lib.wc_surfels_fetch(self.ctx.handle, T.ptr(out), cap, C.byref(n)), "wc_surfels_fetch")
+        return out[: n.value].copy()
