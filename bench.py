@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the window-odometry hot path (BASELINE.json metric: GN iters/sec on the 2 M-point / 12-pose window;
+surfel-extract HBM GB/s).
+
+A "step" is one pass of the whole hot path over one synthetic C3 window (steps 7-13 of LidarOdometry::AddLidarScan):
+surfel extraction from the 2 M-point sweep -> surfel pose update -> sliding- and fixed-window matching -> problem
+assembly -> the Levenberg-Marquardt solve to Ceres' own termination.  `value` = LM iterations executed per second of
+whole-pass time with the sweep / IMU / sample states / fixed window resident in HBM (wc_window_pass_resident);
+`e2e` = the same metric through the host-buffer C-ABI calls a drop-in user makes (wc_build_surfels, wc_update_surfel_poses,
+wc_match x2, wc_window_solve), host<->device copies inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C3]
+
+N > 1 (torchrun, one rank per GPU): every rank extracts and matches (replicas), the residual blocks are sharded over
+the ranks and the normal equations are summed over NVLink peer memory once per linearisation (strong scaling of one
+window).  --impl reference times the CPU restatement of the reference (oracle/, single thread like the reference) on
+the same window.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+
+
+def oracle_pass(O, w, fix_body, timings=None):
+    """one full window pass on the CPU restatement; returns LM iterations."""
+    t0 = time.perf_counter()
+    s = O.build_surfels(w.points)["surfels"]
+    t1 = time.perf_counter()
+    _, sld = O.update_surfel_poses(w.imu, s)
+    cs, _ = O.match(sld, sld, True)
+    cf, _ = O.match(sld, fix_body, False)
+    t2 = time.perf_counter()
+    _, _, summ = O.window_solve(sld, fix_body, cs, cf, w.imu, w.samples)
+    t3 = time.perf_counter()
+    if timings is not None:
+        timings.append(dict(extract_ms=1e3 * (t1 - t0), match_ms=1e3 * (t2 - t1), solve_ms=1e3 * (t3 - t2), total_ms=1e3 * (t3 - t0),
+                            iters=summ.num_iterations, ms_per_iter=1e3 * (t3 - t2) / max(1, summ.num_iterations)))
+    return summ.num_iterations
+
+
+def run_reference(args, w, workload):
+    """--impl reference: the reference's own algorithm on the host cores.  The reference cannot be built in this image
+    (Eigen/Ceres/FLANN/PCL absent) so this is the oracle port, single-threaded like the reference (Ceres num_threads=1)."""
+    from oracle import wc_oracle as O
+
+    O.build()
+    fix_body = O.update_surfel_poses(w.fix_imu, O.build_surfels(w.fix_points)["surfels"])[1]
+    for _ in range(args.warmup):
+        oracle_pass(O, w, fix_body)
+    tm = []
+    t0 = time.perf_counter()
+    iters = sum(oracle_pass(O, w, fix_body, tm) for _ in range(args.steps))
+    dt = time.perf_counter() - t0
+    val = iters / dt
+    line = {
+        "impl": "reference", "metric": "gn_iters_per_sec", "value": val, "unit": "LM iterations/s (whole window pass)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload},
+        "cpu_baseline": {"value": val, "unit": "LM iterations/s (whole window pass)", "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} full {w.cfg.name} window passes (extract+match+solve), oracle/ C++ -O3, 1 thread",
+                         "stages_ms": {k: float(np.mean([t[k] for t in tm])) for k in ("extract_ms", "match_ms", "solve_ms", "ms_per_iter")}},
+        "e2e": {"value": val, "unit": "LM iterations/s (whole window pass)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from wildcat_slam_b200 import synthetic as S
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = S.make_window(args.config)
+        run_reference(args, w, _workload(w))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from wildcat_slam_b200 import odometry as od
+    from wildcat_slam_b200 import types as T
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = S.make_window(args.config)
+    workload = _workload(w)
+    N, K = len(w.points), len(w.samples)
+
+    ctx = od.Context(local_rank)
+    if world > 1:  # exchange the IPC handles of the per-rank exchange buffers (plumbing only: torch.distributed / NCCL)
+        mine = torch.from_numpy(ctx.comm_export()).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.comm_connect(rank, world, torch.stack(allh).cpu().numpy())
+    # fixed window = surfels of the preceding (already optimised) sweep, body frame; built once by the GPU path
+    fix = od.UpdateSurfelPoses(w.fix_imu, od.BuildSurfels(w.fix_points, ctx=ctx), ctx=ctx) if len(w.fix_points) else None
+    rp = od.ResidentPass(w.points, w.imu, w.samples, fix, ctx=ctx)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        return rp.run()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.lib.wc_launch_count(ctx.handle)
+    dev_ms, iters, stats, summ = 0.0, 0, [], None
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        x, summ, st = step()
+        dev_ms += st.ms_total
+        iters += summ.num_iterations
+        stats.append(st)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = ctx.lib.wc_launch_count(ctx.handle) - l0
+    tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms = float(tm.item())
+    value = iters / (dev_ms / 1e3)
+
+    mean = lambda f: float(np.mean([getattr(s, f) for s in stats]))  # noqa: E731
+    S_n, C_n = int(stats[-1].n_surfels), int(stats[-1].n_sld_corr + stats[-1].n_fix_corr)
+    peak, peak_src = _peaks()
+    keys_ms = mean("ms_extract_keys")
+    alg_bytes = 24.0 * N  # 12 B xyz + 8 B t + 4 B assignment per point, K1 only (the S*160 B belong to K2)
+    achieved = alg_bytes / (keys_ms * 1e-3) / 1e9
+    roofline = {"kernel": "voxel_key_moments (K1, surfel extraction)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic("voxel_key_moments"),
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": keys_ms,
+                "share_of_step": keys_ms / mean("ms_total"),
+                "extract_total": {"bytes": 24.0 * N + 160.0 * S_n, "ms": mean("ms_extract"),
+                                  "gbps": (24.0 * N + 160.0 * S_n) / (mean("ms_extract") * 1e-3) / 1e9,
+                                  "frac": (24.0 * N + 160.0 * S_n) / (mean("ms_extract") * 1e-3) / 1e9 / peak},
+                "solve_pass": {"bytes_per_iteration": 128.0 * C_n, "ms_per_iteration": mean("ms_solve") / max(1, summ.num_iterations),
+                               "gbps": 128.0 * C_n / (mean("ms_solve") / max(1, summ.num_iterations) * 1e-3) / 1e9}}
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs, H2D + D2H inside the timed region) ----------------
+    e2e = None
+    if rank == 0 and world == 1:
+        pin = torch.empty(N * 48, dtype=torch.uint8).pin_memory()
+        pts = pin.numpy().view(T.POINT48)
+        pts[:] = w.points
+        ctx2 = ctx
+
+        def e2e_step():
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s = od.BuildSurfels(pts, ctx=ctx2)
+            sld = od.UpdateSurfelPoses(w.imu, s, ctx=ctx2)
+            m = od.KnnSurfelMatcher(ctx2)
+            m.BuildIndex(sld)
+            cs, _ = m.Match(sld)
+            m2 = od.KnnSurfelMatcher(ctx2)
+            m2.BuildIndex(fix)
+            cf, _ = m2.Match(sld)
+            smp, sg = od.SolveWindow(sld, fix, cs, cf, w.imu, w.samples, ctx=ctx2)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ns, nf = len(sld), len(fix)
+            h2d = N * 48 + len(w.imu) * 112 * 2 + ns * 208 * 4 + nf * 208 * 2 + (len(cs) + len(cf)) * 8 + K * 184
+            d2h = ns * 208 * 2 + (len(cs) + len(cf)) * 9 + K * 96 + 2400
+            return dt, sg.num_iterations, h2d, d2h
+
+        for _ in range(2):
+            e2e_step()
+        tot, its, h2d, d2h = 0.0, 0, 0, 0
+        for _ in range(args.steps):
+            dt, it, h2d, d2h = e2e_step()
+            tot += dt
+            its += it
+        e2e = {"value": its / tot, "unit": "LM iterations/s (whole window pass)", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * tot / args.steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import wc_oracle as O
+
+        O.build()
+        fix_o = O.update_surfel_poses(w.fix_imu, O.build_surfels(w.fix_points)["surfels"])[1]
+        tm_o, reps = [], 5
+        t0 = time.perf_counter()
+        it_o = sum(oracle_pass(O, w, fix_o, tm_o) for _ in range(reps))
+        dt_o = time.perf_counter() - t0
+        cpu = {"value": it_o / dt_o, "unit": "LM iterations/s (whole window pass)", "cores": 1, "kind": "port",
+               "sample": f"{reps} full {w.cfg.name} window passes (extract+match+solve) by oracle/ (C++ -O3 -march=native, 1 thread; "
+                         f"host has {os.cpu_count()} cores)",
+               "stages_ms": {k: float(np.mean([t[k] for t in tm_o])) for k in ("extract_ms", "match_ms", "solve_ms", "ms_per_iter")}}
+
+    if rank == 0:
+        line = {
+            "metric": "gn_iters_per_sec", "value": value, "unit": "LM iterations/s (whole window pass)", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "l2_flush": "256 MiB write between steps", "parallelism": f"residual-shard x{world}",
+                       "surfels": S_n, "correspondences": C_n, "lm_iterations_per_step": iters / args.steps},
+            "stages_ms": {"extract": mean("ms_extract"), "extract_keys_K1": keys_ms, "extract_emit_K2": mean("ms_extract_emit"),
+                          "match": mean("ms_match"), "pack": mean("ms_pack"), "solve": mean("ms_solve"),
+                          "solve_ms_per_iteration": mean("ms_solve") / max(1, summ.num_iterations),
+                          "solve_only_iters_per_sec": summ.num_iterations / (mean("ms_solve") * 1e-3)},
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        ctx.comm_disconnect()
+        dist.destroy_process_group()
+
+
+def _workload(w):
+    c = w.cfg
+    return (f"{c.name}: {len(w.points)}-point sweep ({c.rings} rings x {c.az_steps} az/rev, {c.rev_hz:g} rev/s), {len(w.samples)} control poses, "
+            f"{len(w.imu)} IMU states @200 Hz, fixed window from a {len(w.fix_points)}-point preceding sweep, seed {w.seed}")
+
+
+def _traffic(kernel):
+    """dram bytes per launch from the committed ncu --set full summary (profiles/traffic.json), else null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+if __name__ == "__main__":
+    main()

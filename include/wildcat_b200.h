@@ -266,6 +266,25 @@ wc_status wc_window_evaluate(wc_ctx* ctx, const wc_surfel* sld, size_t n_sld, co
                              const wc_sample_state* samples, size_t K, const wc_solve_opts* opts, double* cost,
                              double* grad, double* jtj);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident window pass: steps 7-13 of LidarOdometry::AddLidarScan (lidar_odometry.cc:523-561) in one
+ * call on data already in HBM.  wc_points_upload provides the sweep, wc_pass_upload the IMU states, the
+ * sample states and the body-frame fixed-window surfels; the pass extracts the surfels, moves them to the body
+ * frame, runs both matchers, assembles and solves.  Nothing but the summary crosses the host boundary.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wc_pass_stats {
+  double  ms_total, ms_extract, ms_extract_keys, ms_extract_emit, ms_match, ms_pack, ms_solve;
+  int64_t n_surfels, n_sld_corr, n_fix_corr;
+  int64_t n_launches; /* kernels launched by this ctx so far (cumulative) */
+} wc_pass_stats;
+wc_status wc_pass_upload(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu, const wc_sample_state* samples,
+                         size_t K, const wc_surfel* fix, size_t n_fix);
+wc_status wc_window_pass_resident(wc_ctx* ctx, const wc_solve_opts* opts, wc_solve_summary* summary,
+                                  double* data_cor_out /* K*12, may be NULL */, wc_pass_stats* stats);
+/* number of CUDA kernels this ctx has launched since creation */
+int64_t   wc_launch_count(const wc_ctx* ctx);
+
 /* ------------------------------------------------------------------------------------------------
  * Spline — replaces CubicBSplineInterpolator(timestamps, points) + Interp(t)
  *   src/odometry/spline_interpolation.h:42-113.  valid[i] == 0 <=> Interp returned nullptr.

@@ -61,13 +61,17 @@ def load():
     lib.wc_window_evaluate.argtypes = [vp, *win, P(T.SolveOpts), P(dbl), vp, vp]
     lib.wc_spline_fit_eval.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp]
     lib.wc_apply_corrections.argtypes = [vp, vp, sz, vp, sz]
+    lib.wc_pass_upload.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+    lib.wc_window_pass_resident.argtypes = [vp, P(T.SolveOpts), P(T.SolveSummary), vp, P(T.PassStats)]
+    lib.wc_launch_count.argtypes = [vp]
+    lib.wc_launch_count.restype = C.c_int64
     lib.wc_comm_export.argtypes = [vp, vp]
     lib.wc_comm_connect.argtypes = [vp, i32, i32, vp]
     lib.wc_comm_disconnect.argtypes = [vp]
     for name in declared_symbols():
         f = getattr(lib, name)  # raises AttributeError if the library lacks a declared entry point
         if name not in ("wc_abi_version", "wc_default_params", "wc_default_solve_opts", "wc_destroy", "wc_last_error",
-                        "wc_status_str", "wc_stream"):
+                        "wc_status_str", "wc_stream", "wc_launch_count"):
             f.restype = i32
     _lib = lib
     return lib

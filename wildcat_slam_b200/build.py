@@ -13,7 +13,7 @@ OUT = os.path.join(HERE, "libwildcat_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 SOURCES = {"wc_api.cu": [], "wc_extract.cu": [], "wc_match.cu": ["-fmad=false"], "wc_solve.cu": [], "wc_spline.cu": [],
-           "wc_comm.cu": []}
+           "wc_comm.cu": [], "wc_pass.cu": []}
 
 
 def _newer(src, dst):

@@ -155,7 +155,7 @@ wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate) {
   const size_t total = (size_t)a.N * a.N + a.N + 1;
   int          grid  = (int)((total + 255) / 256);
   if (grid > 64) grid = 64;
-  comm_allreduce<<<grid, 256, 0, c->stream>>>(a);
+  { ++c->n_launches; comm_allreduce<<<grid, 256, 0, c->stream>>>(a); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }

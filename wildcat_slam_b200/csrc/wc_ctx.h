@@ -70,6 +70,7 @@ struct wc_ctx {
   cudaStream_t stream;
   cudaEvent_t  ev[8];
   char         err[512];
+  long long    n_launches;  // kernels launched so far (bench.py's gpu_launches)
 
   // ---- extraction
   void*               d_raw;      // wc_point48 staging (raw upload)

@@ -709,7 +709,7 @@ extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n
   c->n_pts = n;
   if (n == 0) return WC_OK;
   WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
-  repack_points<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const wc_point48*)c->d_raw, (int)n, c->d_xyz, c->d_time);
+  { ++c->n_launches; repack_points<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const wc_point48*)c->d_raw, (int)n, c->d_xyz, c->d_time); }
   WC_CUDA(c, cudaGetLastError());
   // voxel of the first point / first timestamp anchor the relative keys (host copy of element 0 is at hand)
   const double vs = (double)c->prm.voxel_size;
@@ -740,28 +740,28 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
   WC_CUDA(c, cudaMemsetAsync(c->d_xstat, 0, sizeof(wc_extract_status), st));
   const int grid1 = c->num_sms * 8;
-  voxel_key_moments<<<grid1, 256, 0, st>>>(c->d_xyz, c->d_time, P, c->d_hkeys, c->d_hslot, c->hcap - 1, c->d_slots,
-                                           (int)c->slot_cap, c->d_xstat, c->want_assign ? c->d_assign : nullptr);
+  { ++c->n_launches; voxel_key_moments<<<grid1, 256, 0, st>>>(c->d_xyz, c->d_time, P, c->d_hkeys, c->d_hslot, c->hcap - 1, c->d_slots,
+                                           (int)c->slot_cap, c->d_xstat, c->want_assign ? c->d_assign : nullptr); }
   WC_CUDA(c, cudaEventRecord(c->ev[1], st));
-  voxel_index<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
-                                              c->d_vox_key, c->d_vox_hpos, (int)c->prm.max_points);
-  voxel_scan<<<1, 1024, 0, st>>>(c->d_vox_count, c->d_vox_off, c->d_xstat);
-  voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vox_off, c->d_vox_cursor, c->d_seg);
+  { ++c->n_launches; voxel_index<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
+                                              c->d_vox_key, c->d_vox_hpos, (int)c->prm.max_points); }
+  { ++c->n_launches; voxel_scan<<<1, 1024, 0, st>>>(c->d_vox_count, c->d_vox_off, c->d_xstat); }
+  { ++c->n_launches; voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vox_off, c->d_vox_cursor, c->d_seg); }
   EmitParams E;
   E.voxel = P.voxel, E.q0 = P.q0, E.q1 = P.q1, E.t_first = P.t_first;
   E.thr = (double)c->prm.planer_threshold, E.min_like = c->prm.min_plane_likeness, E.gap = c->prm.cluster_time_gap;
   for (int k = 0; k < 3; ++k) E.view[k] = c->prm.view_point[k], E.vox0[k] = c->vox0[k], E.lps[k] = c->prm.layer_point_size[k];
   E.cmin = c->prm.cluster_min_points, E.max_layer = c->prm.max_layer;
   E.surf_cap = (int)c->prm.max_surfels;
-  cluster_eig_emit<256, 64><<<c->num_sms * 16, 64, 256 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 0,
-                                                                   c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
-  cluster_eig_emit<2048, 128><<<c->num_sms * 4, 128, 2048 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
-                                                                     256, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
-  cluster_eig_emit<8192, 256><<<c->num_sms * 2, 256, 8192 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
-                                                                     2048, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  { ++c->n_launches; cluster_eig_emit<256, 64><<<c->num_sms * 16, 64, 256 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 0,
+                                                                   c->d_surf_raw, c->d_sort_hi, c->d_sort_lo); }
+  { ++c->n_launches; cluster_eig_emit<2048, 128><<<c->num_sms * 4, 128, 2048 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
+                                                                     256, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo); }
+  { ++c->n_launches; cluster_eig_emit<8192, 256><<<c->num_sms * 2, 256, 8192 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
+                                                                     2048, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo); }
   WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
-  extract_cleanup<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_hkeys, c->d_hslot, c->d_vkeys, c->d_vslot,
-                                                  c->d_vox_hpos, c->d_vox_count, c->d_vox_cursor);
+  { ++c->n_launches; extract_cleanup<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_hkeys, c->d_hslot, c->d_vkeys, c->d_vslot,
+                                                  c->d_vox_hpos, c->d_vox_count, c->d_vox_cursor); }
   WC_CUDA(c, cudaEventRecord(c->ev[2], st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   const wc_extract_status hs = *c->h_xstat;
@@ -774,14 +774,14 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   if (S > 0) {
     int n_pad = 2048;
     while (n_pad < S) n_pad <<= 1;
-    sort_pad<<<(n_pad + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, S, n_pad);
-    sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, 0);
+    { ++c->n_launches; sort_pad<<<(n_pad + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, S, n_pad); }
+    { ++c->n_launches; sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, 0); }
     for (int k = 4096; k <= n_pad; k <<= 1) {
       for (int j = k >> 1; j >= 2048; j >>= 1)
-        sort_global_step<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k, j);
-      sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k);
+        { ++c->n_launches; sort_global_step<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k, j); }
+      { ++c->n_launches; sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k); }
     }
-    gather_surfels<<<(S * 13 + 255) / 256, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, S, c->d_surf);
+    { ++c->n_launches; gather_surfels<<<(S * 13 + 255) / 256, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, S, c->d_surf); }
   }
   WC_CUDA(c, cudaEventRecord(c->ev[3], st));
   WC_CUDA(c, cudaStreamSynchronize(st));

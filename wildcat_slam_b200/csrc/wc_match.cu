@@ -212,20 +212,22 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
                           size_t* n_out) {
   *n_out = 0;
   if (nq == 0 || nt == 0) return WC_OK;  // knn_surfel_matcher.cc:18-20
+  wc_status as = match_alloc(c);
+  if (as) return as;
   cudaStream_t st = c->stream;
   const int    k  = c->prm.knn_candidates;
   if (k < 1 || k > KMAX) WC_FAIL(c, WC_EINVAL, "knn_candidates must be 1..%d", KMAX);
   const unsigned gq = (unsigned)((nq + 255) / 256), gt = (unsigned)((nt + 255) / 256);
-  surfel_features<<<gq, 256, 0, st>>>(d_q, (int)nq, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_qfeat);
+  { ++c->n_launches; surfel_features<<<gq, 256, 0, st>>>(d_q, (int)nq, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_qfeat); }
   const double* tfeat = c->d_qfeat;
   if (!self_match) {
-    surfel_features<<<gt, 256, 0, st>>>(d_t, (int)nt, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_tfeat);
+    { ++c->n_launches; surfel_features<<<gt, 256, 0, st>>>(d_t, (int)nt, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_tfeat); }
     tfeat = c->d_tfeat;
   }
-  knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
-                                                                       c->d_knn_idx, c->d_knn_d2);
+  { ++c->n_launches; knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
+                                                                       c->d_knn_idx, c->d_knn_d2); }
   GateParams G{c->prm.time_diff_threshold, c->prm.angular_dist_threshold, c->prm.surfel_dist_threshold, k};
-  gate_candidates<<<gq, 256, 0, st>>>(c->d_qfeat, (int)nq, tfeat, c->d_knn_idx, G, c->d_gated);
+  { ++c->n_launches; gate_candidates<<<gq, 256, 0, st>>>(c->d_qfeat, (int)nq, tfeat, c->d_knn_idx, G, c->d_gated); }
   WC_CUDA(c, cudaMemsetAsync(c->d_acc, 0xff, nq * 4, st));
   int* a = c->d_acc;
   int* b = c->d_acc2;
@@ -233,7 +235,7 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     WC_CUDA(c, cudaMemsetAsync(c->d_flag, 0, 4, st));
     const int sweeps = self_match ? 3 : 1;
     for (int s = 0; s < sweeps; ++s) {
-      resolve_pairs<<<gq, 256, 0, st>>>(c->d_gated, (int)nq, k, self_match, a, b, c->d_flag);
+      { ++c->n_launches; resolve_pairs<<<gq, 256, 0, st>>>(c->d_gated, (int)nq, k, self_match, a, b, c->d_flag); }
       int* tmp = a; a = b; b = tmp;
     }
     if (!self_match) break;
@@ -243,7 +245,7 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     if (*c->h_flag == 0) break;
     if (it > (int)nq) WC_FAIL(c, WC_ENUMERIC, "pair de-duplication did not converge");
   }
-  compact_pairs<<<1, 1024, 0, st>>>(a, (int)nq, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1);
+  { ++c->n_launches; compact_pairs<<<1, 1024, 0, st>>>(a, (int)nq, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
   WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 4, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
@@ -296,8 +298,8 @@ extern "C" wc_status wc_knn6(wc_ctx* c, const double* query6, size_t nq, const d
   WC_CUDA(c, cudaMemcpyAsync(c->d_qfeat, query6, nq * 48, cudaMemcpyHostToDevice, st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_tfeat, target6, nt * 48, cudaMemcpyHostToDevice, st));
   if (nq && nt)
-    knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, 6, (int)nq, c->d_tfeat, 6, (int)nt, k,
-                                                                         c->d_knn_idx, c->d_knn_d2);
+    { ++c->n_launches; knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, 6, (int)nq, c->d_tfeat, 6, (int)nt, k,
+                                                                         c->d_knn_idx, c->d_knn_d2); }
   WC_CUDA(c, cudaGetLastError());
   WC_CUDA(c, cudaMemcpyAsync(out_idx, c->d_knn_idx, nq * k * 4, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaMemcpyAsync(out_dist2, c->d_knn_d2, nq * k * 8, cudaMemcpyDeviceToHost, st));

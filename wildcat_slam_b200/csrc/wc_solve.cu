@@ -31,6 +31,7 @@ constexpr int LT       = 256;       // linearize tile = threads per CTA
 constexpr int JR       = 28;        // augmented row count: 24 Jacobian columns, residual, 3 pad
 constexpr int JS       = LT + 1;    // padded row stride (doubles)
 constexpr int NGRP     = LT / 32;
+constexpr int LIN_SMEM = (JR * JS + NGRP * 28 * 16) * 8;
 
 struct LMState {
   // control
@@ -273,7 +274,8 @@ __device__ __forceinline__ void lane_block(int lane, int& bi, int& bj) {
 
 __global__ void __launch_bounds__(LT) lidar_linearize(LinArgs a) {
   extern __shared__ __align__(16) double sm[];
-  double* Jt = sm;  // JR x JS
+  double* Jt    = sm;            // JR x JS
+  double* stage = sm + JR * JS;  // NGRP x 28 x 16 (flush staging; separate from Jt: a flush can happen mid-tile)
   __shared__ int sbk[LT];
   __shared__ int sb1[LT], sb2[LT];
   __shared__ int heads[LT];
@@ -305,7 +307,6 @@ __global__ void __launch_bounds__(LT) lidar_linearize(LinArgs a) {
   // flush the per-thread 4x4 partial blocks of the current bucket into the dense normal equations
   auto flush = [&]() {
     __syncthreads();
-    double* stage = Jt;  // NGRP x 28 x 16
     if (lane < 28)
 #pragma unroll
       for (int k = 0; k < 16; ++k) stage[(grp * 28 + lane) * 16 + k] = acc[k], acc[k] = 0.0;
@@ -322,11 +323,13 @@ __global__ void __launch_bounds__(LT) lidar_linearize(LinArgs a) {
         for (int gi = 0; gi < NGRP; ++gi) v += stage[(gi * 28 + blk) * 16 + k];
         if (v == 0.0) continue;
         const int sa = p / 6, gpb = (sa < 2 ? cur_b1 + sa : cur_b2 + sa - 2);
+        if (sa < 2 && cur_b1 < 0) continue;  // unary factor: no s1 blocks
         const int gp = 12 * gpb + p % 6;
         if (q == 24) {
           atomicAdd(&g[gp], v);
         } else {
           const int sb = q / 6, gqb = (sb < 2 ? cur_b1 + sb : cur_b2 + sb - 2);
+          if (sb < 2 && cur_b1 < 0) continue;
           const int gq = 12 * gqb + q % 6;
           atomicAdd(&H[(size_t)gp * N + gq], v);
           if (p != q) atomicAdd(&H[(size_t)gq * N + gp], v);
@@ -861,7 +864,7 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
-  WC_CUDA(c, cudaFuncSetAttribute(lidar_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, JR * JS * 8));
+  WC_CUDA(c, cudaFuncSetAttribute(lidar_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
   WC_CUDA(c, cudaFuncSetAttribute(lm_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return WC_OK;
 }
@@ -891,6 +894,43 @@ static SolveBufs make_bufs(wc_ctx* c, int fix_first) {
   return B;
 }
 
+// Device-side window preparation: sample timestamps / start point, factor construction for this rank's slice of the
+// correspondence list, bucketing by interval pair.  Expects d_sld/d_fix/d_sld_corr/d_fix_corr/d_imu/d_samples and the
+// counts in the ctx.
+wc_status wc_window_prepare_device(wc_ctx* c) {
+  wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
+  cudaStream_t  st = c->stream;
+  const size_t  K = c->K, n_sld = c->n_sld, n_fix = c->n_fix, n_sld_corr = c->n_sld_corr, n_fix_corr = c->n_fix_corr;
+  if (n_sld_corr + n_fix_corr > (size_t)c->prm.max_corrs) WC_FAIL(c, WC_ECAPACITY, "too many correspondences");
+  { ++c->n_launches; extract_ts<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(c->d_samples, (int)K, m->ts, c->d_x0); }
+  // factor construction for this rank's slice of the correspondence list, bucketed by interval pair
+  const int C  = (int)(n_sld_corr + n_fix_corr);
+  const int c0 = (int)((long long)C * c->rank / c->world), c1 = (int)((long long)C * (c->rank + 1) / c->world);
+  c->n_rec     = (size_t)(c1 - c0);
+  const int nb = (int)(K * K);
+  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
+  WC_CUDA(c, cudaMemsetAsync(m->hist, 0, (size_t)nb * 4, st));
+  WC_CUDA(c, cudaMemsetAsync(m->cursor, 0, (size_t)nb * 4, st));
+  if (c->n_rec) {
+    PackArgs a;
+    a.sld = c->d_sld, a.fix = c->d_fix, a.sld_corr = c->d_sld_corr, a.fix_corr = c->d_fix_corr;
+    a.n_sld = (int)n_sld, a.n_fix = (int)n_fix, a.n_sld_corr = (int)n_sld_corr, a.n_fix_corr = (int)n_fix_corr;
+    a.c0 = c0, a.c1 = c1, a.ts = m->ts, a.K = (int)K, a.weight_floor = c->prm.weight_floor;
+    a.tmp = m->tmp, a.stride = m->stride, a.bucket = m->bucket, a.hist = m->hist, a.st = m->st;
+    const unsigned grid = (unsigned)((c->n_rec + 255) / 256);
+    { ++c->n_launches; corr_pack<<<grid, 256, 0, st>>>(a); }
+    { ++c->n_launches; bucket_scan<<<1, 1024, 0, st>>>(m->hist, nb, m->off); }
+    { ++c->n_launches; bucket_scatter<<<grid, 256, 0, st>>>(m->tmp, m->bucket, (int)c->n_rec, m->stride, m->off, m->cursor, m->rec); }
+  }
+  WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (m->h_st->err == WC_EINVAL) WC_FAIL(c, WC_EINVAL, "correspondence index out of range");
+  if (m->h_st->err == WC_EINVAL_TIME_ORDER) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "correspondence with timestamp(s1) >= timestamp(s2)");
+  if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the sample-state span");
+  return WC_OK;
+}
+
 extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_sld, const wc_surfel* fix, size_t n_fix,
                                       const wc_corr_idx* sld_corr, size_t n_sld_corr, const wc_corr_idx* fix_corr,
                                       size_t n_fix_corr, const wc_imu_state* imu, size_t n_imu,
@@ -917,32 +957,31 @@ extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_
   c->n_imu_blocks = 0;  // BuildImuResiduals' block count (:320-329), for the summary only
   for (size_t i = 0; i + 2 < n_imu; ++i)
     if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) ++c->n_imu_blocks;
-  extract_ts<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(c->d_samples, (int)K, m->ts, c->d_x0);
-  // factor construction for this rank's slice of the correspondence list, bucketed by interval pair
-  const int C  = (int)(n_sld_corr + n_fix_corr);
-  const int c0 = (int)((long long)C * c->rank / c->world), c1 = (int)((long long)C * (c->rank + 1) / c->world);
-  c->n_rec     = (size_t)(c1 - c0);
-  const int nb = (int)(K * K);
-  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
-  WC_CUDA(c, cudaMemsetAsync(m->hist, 0, (size_t)nb * 4, st));
-  WC_CUDA(c, cudaMemsetAsync(m->cursor, 0, (size_t)nb * 4, st));
-  if (c->n_rec) {
-    PackArgs a;
-    a.sld = c->d_sld, a.fix = c->d_fix, a.sld_corr = c->d_sld_corr, a.fix_corr = c->d_fix_corr;
-    a.n_sld = (int)n_sld, a.n_fix = (int)n_fix, a.n_sld_corr = (int)n_sld_corr, a.n_fix_corr = (int)n_fix_corr;
-    a.c0 = c0, a.c1 = c1, a.ts = m->ts, a.K = (int)K, a.weight_floor = c->prm.weight_floor;
-    a.tmp = m->tmp, a.stride = m->stride, a.bucket = m->bucket, a.hist = m->hist, a.st = m->st;
-    const unsigned grid = (unsigned)((c->n_rec + 255) / 256);
-    corr_pack<<<grid, 256, 0, st>>>(a);
-    bucket_scan<<<1, 1024, 0, st>>>(m->hist, nb, m->off);
-    bucket_scatter<<<grid, 256, 0, st>>>(m->tmp, m->bucket, (int)c->n_rec, m->stride, m->off, m->cursor, m->rec);
-  }
-  WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+  return wc_window_prepare_device(c);
+}
+
+// Upload of everything a device-resident window pass needs besides the sweep itself: IMU states, sample states and
+// the (body-frame) fixed-window surfels.  The sliding-window surfels and both correspondence lists are produced on
+// the device by the pass.
+wc_status wc_window_upload_aux(wc_ctx* c, const wc_imu_state* imu, size_t n_imu, const wc_sample_state* samples, size_t K,
+                               const wc_surfel* fix, size_t n_fix) {
+  if (!c || !samples || K < 2 || (n_imu && !imu) || (n_fix && !fix)) return WC_EINVAL;
+  wc_status s = solve_alloc(c);
+  if (s) return s;
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  if (n_fix > (size_t)c->prm.max_surfels) WC_FAIL(c, WC_ECAPACITY, "too many surfels");
+  if (K > (size_t)c->prm.max_samples) WC_FAIL(c, WC_ECAPACITY, "too many sample states");
+  if (n_imu > (size_t)c->prm.max_imu_states) WC_FAIL(c, WC_ECAPACITY, "too many IMU states");
+  cudaStream_t st = c->stream;
+  c->n_fix = n_fix, c->n_imu = n_imu, c->K = K;
+  if (n_fix) WC_CUDA(c, cudaMemcpyAsync(c->d_fix, fix, n_fix * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
+  if (n_imu) WC_CUDA(c, cudaMemcpyAsync(c->d_imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
+  WC_CUDA(c, cudaMemcpyAsync(c->d_samples, samples, K * sizeof(wc_sample_state), cudaMemcpyHostToDevice, st));
+  for (int k = 0; k < 3; ++k) m->grav[k] = samples[K - 1].grav[k];  // lidar_odometry.cc:341,355
+  c->n_imu_blocks = 0;
+  for (size_t i = 0; i + 2 < n_imu; ++i)
+    if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) ++c->n_imu_blocks;
   WC_CUDA(c, cudaStreamSynchronize(st));
-  WC_CUDA(c, cudaGetLastError());
-  if (m->h_st->err == WC_EINVAL) WC_FAIL(c, WC_EINVAL, "correspondence index out of range");
-  if (m->h_st->err == WC_EINVAL_TIME_ORDER) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "correspondence with timestamp(s1) >= timestamp(s2)");
-  if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the sample-state span");
   return WC_OK;
 }
 
@@ -957,14 +996,14 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     wc_comm_partial_views(c, &pH, &pg, &pc);
     B.H[0] = B.H[1] = pH, B.g[0] = B.g[1] = pg, B.cost[0] = B.cost[1] = pc;
   }
-  zero_buffers<<<64, 256, 0, st>>>(B, at_candidate);
+  { ++c->n_launches; zero_buffers<<<64, 256, 0, st>>>(B, at_candidate); }
   if (c->n_rec) {
     LinArgs a;
     a.rec = m->rec, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
     a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
     const int ntiles = (int)((c->n_rec + LT - 1) / LT);
     const int grid   = ntiles < c->num_sms ? ntiles : c->num_sms;
-    lidar_linearize<<<grid, LT, JR * JS * 8, st>>>(a);
+    { ++c->n_launches; lidar_linearize<<<grid, LT, LIN_SMEM, st>>>(a); }
   }
   if (o->use_imu_factors && c->n_imu >= 3 && c->rank == 0) {
     ImuArgs a;
@@ -972,7 +1011,7 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     a.wg = c->prm.weight_gyr, a.wa = c->prm.weight_acc, a.wbg = c->prm.weight_bg, a.wba = c->prm.weight_ba;
     a.dt = 1.0 / c->prm.imu_rate;
     for (int k = 0; k < 3; ++k) a.grav[k] = m->grav[k];
-    imu_linearize<<<(unsigned)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS), IMU_WARPS * 32, 0, st>>>(a);
+    { ++c->n_launches; imu_linearize<<<(unsigned)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS), IMU_WARPS * 32, 0, st>>>(a); }
   }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
@@ -1008,14 +1047,14 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   wc_status s = enqueue_linearize(c, B, &o, 0);
   if (s) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;
-  lm_init<<<1, LMT, 0, st>>>(B, o);
+  { ++c->n_launches; lm_init<<<1, LMT, 0, st>>>(B, o); }
   const int batch = 4;
   for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 8; it += batch) {
     for (int b = 0; b < batch; ++b) {
-      lm_solve_step<<<1, LMT, smem, st>>>(B, o, a_in_smem);
+      { ++c->n_launches; lm_solve_step<<<1, LMT, smem, st>>>(B, o, a_in_smem); }
       if ((s = enqueue_linearize(c, B, &o, 1))) return s;
       if ((s = wc_comm_allreduce(c, 1))) return s;
-      lm_decide<<<1, LMT, 0, st>>>(B, o);
+      { ++c->n_launches; lm_decide<<<1, LMT, 0, st>>>(B, o); }
     }
     WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));

@@ -259,9 +259,9 @@ extern "C" wc_status wc_spline_fit_eval(wc_ctx* c, const double* ts, const doubl
   cudaStream_t   st = c->stream;
   WC_CUDA(c, cudaMemcpyAsync(m->pts, pts3, K * 3 * 8, cudaMemcpyHostToDevice, st));
   if (nq) WC_CUDA(c, cudaMemcpyAsync(m->tq, query_t, nq * 8, cudaMemcpyHostToDevice, st));
-  bspline_fit<<<1, 256, K * (K + 3) * 8, st>>>(m->pts, (int)K, 3, m->Q);
+  { ++c->n_launches; bspline_fit<<<1, 256, K * (K + 3) * 8, st>>>(m->pts, (int)K, 3, m->Q); }
   if (nq) {
-    bspline_eval<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(m->Q, (int)K, 3, ts[0], ts[K - 1], m->tq, (int)nq, m->out, m->valid);
+    { ++c->n_launches; bspline_eval<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(m->Q, (int)K, 3, ts[0], ts[K - 1], m->tq, (int)nq, m->out, m->valid); }
     WC_CUDA(c, cudaMemcpyAsync(out3, m->out, nq * 3 * 8, cudaMemcpyDeviceToHost, st));
     if (valid) WC_CUDA(c, cudaMemcpyAsync(valid, m->valid, nq, cudaMemcpyDeviceToHost, st));
   }
@@ -281,7 +281,7 @@ extern "C" wc_status wc_update_surfel_poses(wc_ctx* c, const wc_imu_state* imu, 
   WC_CUDA(c, cudaMemcpyAsync(m->imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
   WC_CUDA(c, cudaMemcpyAsync(m->surf, surfels, n * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
   WC_CUDA(c, cudaMemsetAsync(m->flags, 0, 16, st));
-  update_surfel_poses<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->imu, (int)n_imu, m->surf, (int)n, m->flags + 2);
+  { ++c->n_launches; update_surfel_poses<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->imu, (int)n_imu, m->surf, (int)n, m->flags + 2); }
   WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaMemcpyAsync(surfels, m->surf, n * sizeof(wc_surfel), cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
@@ -297,7 +297,7 @@ wc_status wc_update_surfel_poses_device(wc_ctx* c, const wc_imu_state* d_imu, si
   wc_spline_mem* m = (wc_spline_mem*)c->d_spline;
   if (n == 0) return WC_OK;
   WC_CUDA(c, cudaMemsetAsync(m->flags, 0, 16, c->stream));
-  update_surfel_poses<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_imu, (int)n_imu, d_surf, (int)n, m->flags + 2);
+  { ++c->n_launches; update_surfel_poses<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_imu, (int)n_imu, d_surf, (int)n, m->flags + 2); }
   WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, c->stream));
   WC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (m->h_flags[2]) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the IMU state span (lidar_odometry.cc:164)");
@@ -316,13 +316,13 @@ extern "C" wc_status wc_apply_corrections(wc_ctx* c, wc_sample_state* samples, s
   if (n_imu) WC_CUDA(c, cudaMemcpyAsync(m->imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
   const int init[4] = {0x7fffffff, -1, 0, 0};
   WC_CUDA(c, cudaMemcpyAsync(m->flags, init, 16, cudaMemcpyHostToDevice, st));
-  gather_corrections<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(m->samples, (int)K, m->pts, m->ts);
-  bspline_fit<<<1, 256, K * (K + 6) * 8, st>>>(m->pts, (int)K, 6, m->Q);
+  { ++c->n_launches; gather_corrections<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(m->samples, (int)K, m->pts, m->ts); }
+  { ++c->n_launches; bspline_fit<<<1, 256, K * (K + 6) * 8, st>>>(m->pts, (int)K, 6, m->Q); }
   if (n_imu)
-    apply_imu_corrections<<<(unsigned)((n_imu + 127) / 128), 128, 0, st>>>(m->Q, (int)K, samples[0].timestamp,
-                                                                           samples[K - 1].timestamp, m->imu, (int)n_imu, m->flags);
-  repredict_and_update_samples<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(m->imu, (int)n_imu, m->samples, (int)K, m->flags,
-                                                                            m->flags + 2);
+    { ++c->n_launches; apply_imu_corrections<<<(unsigned)((n_imu + 127) / 128), 128, 0, st>>>(m->Q, (int)K, samples[0].timestamp,
+                                                                           samples[K - 1].timestamp, m->imu, (int)n_imu, m->flags); }
+  { ++c->n_launches; repredict_and_update_samples<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(m->imu, (int)n_imu, m->samples, (int)K, m->flags,
+                                                                            m->flags + 2); }
   WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaMemcpyAsync(samples, m->samples, K * sizeof(wc_sample_state), cudaMemcpyDeviceToHost, st));
   if (n_imu) WC_CUDA(c, cudaMemcpyAsync(imu, m->imu, n_imu * sizeof(wc_imu_state), cudaMemcpyDeviceToHost, st));

@@ -264,3 +264,27 @@ class ResidentSweep:
         n = C.c_size_t(0)
         self.ctx.check(self.ctx.lib.wc_surfels_fetch(self.ctx.handle, T.ptr(out), cap, C.byref(n)), "wc_surfels_fetch")
         return out[: n.value].copy()
+
+
+class ResidentPass:
+    """Device-resident window pass (steps 7-13 of AddLidarScan in one call): upload sweep + IMU/sample states + fixed
+    window once, then run extract -> poses -> match x2 -> assemble -> solve repeatedly without host round trips."""
+
+    def __init__(self, cloud, imu, samples, fix_body, ctx=None):
+        self.ctx = ctx or default_context()
+        self.cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
+        self.imu = np.ascontiguousarray(imu, dtype=T.IMU)
+        self.samples = np.ascontiguousarray(samples, dtype=T.SAMPLE)
+        self.fix = np.ascontiguousarray(fix_body if fix_body is not None else np.zeros(0, T.SURFEL), dtype=T.SURFEL)
+        lib, h = self.ctx.lib, self.ctx.handle
+        self.ctx.check(lib.wc_points_upload(h, T.ptr(self.cloud), len(self.cloud)), "wc_points_upload")
+        self.ctx.check(lib.wc_pass_upload(h, T.ptr(self.imu), len(self.imu), T.ptr(self.samples), len(self.samples),
+                                          T.ptr(self.fix), len(self.fix)), "wc_pass_upload")
+
+    def run(self, opts=None):
+        o = opts or T.default_solve_opts()
+        summ, stats = T.SolveSummary(), T.PassStats()
+        x = np.zeros((len(self.samples), 12))
+        st = self.ctx.lib.wc_window_pass_resident(self.ctx.handle, C.byref(o), C.byref(summ), T.ptr(x), C.byref(stats))
+        self.ctx.check(st, "wc_window_pass_resident")
+        return x, summ, stats

@@ -131,6 +131,11 @@ class SolveSummary(C.Structure):
     ]
 
 
+class PassStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ms_total", "ms_extract", "ms_extract_keys", "ms_extract_emit", "ms_match", "ms_pack",
+                                          "ms_solve")] + [(n, C.c_int64) for n in ("n_surfels", "n_sld_corr", "n_fix_corr", "n_launches")]
+
+
 def default_params() -> Params:
     """Python-side copy of wc_default_params (the library's own is checked against this in tests).
 
