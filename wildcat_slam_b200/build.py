@@ -39,7 +39,13 @@ def build(force=False, verbose=False):
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:  # a runaway cicc/ptxas must not hang the caller
+            p.kill()
+            out, _ = p.communicate()
+            out += f"\n{src}: nvcc timed out after 600 s\n".encode()
+            p.returncode = 1
         if p.returncode != 0 or verbose:
             sys.stderr.write(out.decode())
         failed |= p.returncode != 0

@@ -96,6 +96,8 @@ extern "C" wc_status wc_create(const wc_params* p, int device, wc_ctx** out) {
   for (int i = 0; i < 8; ++i)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { free(c); return WC_ECUDA; }
   c->rank = 0, c->world = 1;
+  c->knn_grid_min = 512;
+  if (const char* e = getenv("WC_KNN_GRID_MIN")) c->knn_grid_min = atoll(e);  // test hook: force either exact search
   *out = c;
   return WC_OK;
 }

@@ -120,6 +120,8 @@ struct wc_ctx {
   wc_corr_idx* d_corr_out;
   unsigned char* d_fit_out;
   int*    d_scan_tmp;
+  void*   d_grid;      // GridBufs (host copy of the device pointers)
+  long long knn_grid_min;  // target count from which the uniform-grid kNN replaces the brute-force scan
 
   // ---- window solve
   wc_surfel*       d_sld;

@@ -88,6 +88,288 @@ knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __
     if (j < k) out_idx[(size_t)i * k + j] = ik[j], out_d2[(size_t)i * k + j] = dk[j];
 }
 
+
+// ---- exact kNN through a uniform grid over the centre part of the feature (cell = 1 feature unit) ------------------
+// Targets are bucketed by cell (open-addressed cell table -> dense cell id -> counting-sort scatter).  A query scans
+// Chebyshev rings of cells around its own cell; after ring r every unvisited target differs from the query by at least
+// b = (distance from the query to the faces of the visited cube) in one centre coordinate, so its squared 6-D distance
+// is >= b^2: the search stops as soon as the k-th best distance is strictly below b^2 — the result is the exact k-NN,
+// identical to brute force, ordered by (distance, target index).
+constexpr int RMAX = 3;
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+__device__ __forceinline__ unsigned long long cell_key(long long ix, long long iy, long long iz) {
+  return ((unsigned long long)(ix + (1 << 20)) << 42) | ((unsigned long long)(iy + (1 << 20)) << 21) | (unsigned long long)(iz + (1 << 20));
+}
+#define WC_CELL_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct GridBufs {
+  unsigned long long* keys;  // cell table
+  int*                cid;   // published dense cell id
+  unsigned long long  mask;
+  int*                cnt;   // per cell
+  int*                off;
+  int*                cur;
+  int*                hpos;  // table position per cell (cleanup)
+  int*                tcell; // per target
+  int*                ncells;
+  double*             sfeat; // sorted: 8 doubles per target (f[6], index bits, pad)
+  int*                err;
+};
+
+__global__ void grid_count(const double* __restrict__ tf, int tstr, int nt, GridBufs G, int cell_cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  const double* f  = tf + (size_t)i * tstr;
+  const double  fx = floor(f[0]), fy = floor(f[1]), fz = floor(f[2]);
+  if (!(fabs(fx) < 1e6 && fabs(fy) < 1e6 && fabs(fz) < 1e6)) {
+    *G.err = 1;  // outside the 2^20-cell key range (or non-finite)
+    G.tcell[i] = -1;
+    return;
+  }
+  const unsigned long long key = cell_key((long long)fx, (long long)fy, (long long)fz);
+  unsigned long long       h   = mix64(key) & G.mask;
+  int                      id  = -2;
+  for (;; h = (h + 1) & G.mask) {
+    unsigned long long k = *((volatile unsigned long long*)&G.keys[h]);
+    if (k == WC_CELL_EMPTY) {
+      k = atomicCAS(&G.keys[h], WC_CELL_EMPTY, key);
+      if (k == WC_CELL_EMPTY) {
+        id = atomicAdd(G.ncells, 1);
+        if (id >= cell_cap) *G.err = 1, id = -2;
+        else G.hpos[id] = (int)h;
+        __threadfence();
+        atomicExch(&G.cid[h], id);
+        break;
+      }
+    }
+    if (k == key) {
+      while ((id = *((volatile int*)&G.cid[h])) == -1) {
+      }
+      break;
+    }
+  }
+  G.tcell[i] = id;
+  if (id >= 0) atomicAdd(&G.cnt[id], 1);
+}
+
+__global__ void __launch_bounds__(1024) grid_scan(GridBufs G) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int      n = *G.ncells;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? G.cnt[i] : 0;
+    int       incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x], wi = w;
+      for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (threadIdx.x >= d) wi += o;
+      }
+      warp_sums[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < n) G.off[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) G.off[n] = carry;
+}
+
+__global__ void grid_scatter(const double* __restrict__ tf, int tstr, int nt, GridBufs G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  const int id = G.tcell[i];
+  if (id < 0) return;
+  const int     pos = G.off[id] + atomicAdd(&G.cur[id], 1);
+  const double* f   = tf + (size_t)i * tstr;
+  double*       o   = G.sfeat + (size_t)pos * 8;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) o[d] = f[d];
+  o[6] = __longlong_as_double((long long)i);
+  o[7] = 0.0;
+}
+
+__global__ void grid_cleanup(GridBufs G) {
+  const int n = *G.ncells;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int h = G.hpos[i];
+    G.keys[h]   = WC_CELL_EMPTY;
+    G.cid[h]    = -1;
+    G.cnt[i]    = 0;
+    G.cur[i]    = 0;
+  }
+}
+__global__ void grid_reset_count(GridBufs G) { *G.ncells = 0; }
+
+__device__ __forceinline__ bool cand_less(double d, int id, double dk, int ik) { return d < dk || (d == dk && id < ik); }
+
+__global__ void __launch_bounds__(128)
+knn6_grid(const double* __restrict__ q, int qstr, int nq, const double* __restrict__ tf, int tstr, int nt, int k, GridBufs G,
+          int* __restrict__ out_idx, double* __restrict__ out_d2, int* __restrict__ unres, int* __restrict__ n_unres) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  double f[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) f[d] = q[(size_t)i * qstr + d];
+  double dk[KMAX];
+  int    ik[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) dk[j] = INFINITY, ik[j] = 0x7fffffff;
+  double worst  = INFINITY;
+  int    worsti = 0x7fffffff;
+  auto   push   = [&](double r, int id) {
+    if (!cand_less(r, id, worst, worsti)) return;
+#pragma unroll
+    for (int p = KMAX - 1; p > 0; --p) {
+      if (p < k) {
+        const bool shift = cand_less(r, id, dk[p - 1], ik[p - 1]);
+        const bool place = !shift && cand_less(r, id, dk[p], ik[p]);
+        if (shift) dk[p] = dk[p - 1], ik[p] = ik[p - 1];
+        else if (place) dk[p] = r, ik[p] = id;
+      }
+    }
+    if (cand_less(r, id, dk[0], ik[0])) dk[0] = r, ik[0] = id;
+#pragma unroll
+    for (int p = 0; p < KMAX; ++p)
+      if (p == k - 1) worst = dk[p], worsti = ik[p];
+  };
+  auto dist = [&](const double* __restrict__ t) {
+    double r = 0.0;  // flann::L2_Simple accumulation order, no contraction
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      const double diff = __dsub_rn(f[d], t[d]);
+      r                 = __dadd_rn(r, __dmul_rn(diff, diff));
+    }
+    return r;
+  };
+  const double cfx = floor(f[0]), cfy = floor(f[1]), cfz = floor(f[2]);
+  bool         done = false;
+  if (fabs(cfx) < 1e6 && fabs(cfy) < 1e6 && fabs(cfz) < 1e6) {
+    const long long ix = (long long)cfx, iy = (long long)cfy, iz = (long long)cfz;
+#pragma unroll 1
+    for (int r = 0; r <= RMAX && !done; ++r) {
+#pragma unroll 1
+      for (int dz = -r; dz <= r; ++dz)
+#pragma unroll 1
+        for (int dy = -r; dy <= r; ++dy) {
+          const bool face = (dz == -r || dz == r || dy == -r || dy == r);
+#pragma unroll 1
+          for (int dx = -r; dx <= r; dx += (face || r == 0) ? 1 : 2 * r) {
+            const unsigned long long key = cell_key(ix + dx, iy + dy, iz + dz);
+            unsigned long long       h   = mix64(key) & G.mask;
+            int                      id  = -1;
+            for (;; h = (h + 1) & G.mask) {
+              const unsigned long long kk = G.keys[h];
+              if (kk == key) { id = G.cid[h]; break; }
+              if (kk == WC_CELL_EMPTY) break;
+            }
+            if (id < 0) continue;
+            const int p1 = G.off[id + 1];
+#pragma unroll 1
+            for (int p = G.off[id]; p < p1; ++p) {
+              const double* t = G.sfeat + (size_t)p * 8;
+              push(dist(t), (int)__double_as_longlong(t[6]));
+            }
+          }
+        }
+      // every unvisited target is at least b away from the query in one centre coordinate
+      const double b = fmin(fmin(fmin(f[0] - (cfx - r), (cfx + r + 1) - f[0]), fmin(f[1] - (cfy - r), (cfy + r + 1) - f[1])),
+                            fmin(f[2] - (cfz - r), (cfz + r + 1) - f[2]));
+      if (worst < b * b * (1.0 - 1e-12)) done = true;
+    }
+  }
+  if (!done) {  // sparse neighbourhood: hand the query to the warp-per-query exhaustive scan (same total order)
+    unres[atomicAdd(n_unres, 1)] = i;
+  } else {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) out_idx[(size_t)i * k + j] = (ik[j] == 0x7fffffff) ? -1 : ik[j], out_d2[(size_t)i * k + j] = dk[j];
+  }
+}
+
+// Exhaustive exact k-NN for the few queries whose neighbourhood is too sparse for the ring search: one warp per query,
+// lanes stride over the targets keeping a private sorted top-k, then a k-round warp arg-min merge.
+__global__ void __launch_bounds__(256)
+knn6_fallback_warp(const double* __restrict__ q, int qstr, const double* __restrict__ tf, int tstr, int nt, int k,
+                   const int* __restrict__ unres, const int* __restrict__ n_unres, int* __restrict__ out_idx,
+                   double* __restrict__ out_d2) {
+  const int lane = threadIdx.x & 31;
+  const int nw   = gridDim.x * (blockDim.x >> 5);
+  const int n    = *n_unres;
+  for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n; u += nw) {
+    const int i = unres[u];
+    double    f[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) f[d] = q[(size_t)i * qstr + d];
+    double dk[KMAX];
+    int    ik[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) dk[j] = INFINITY, ik[j] = 0x7fffffff;
+    double worst  = INFINITY;
+    int    worsti = 0x7fffffff;
+#pragma unroll 1
+    for (int j = lane; j < nt; j += 32) {
+      const double* t = tf + (size_t)j * tstr;
+      double        r = 0.0;
+#pragma unroll
+      for (int d = 0; d < 6; ++d) {
+        const double diff = __dsub_rn(f[d], t[d]);
+        r                 = __dadd_rn(r, __dmul_rn(diff, diff));
+      }
+      if (!cand_less(r, j, worst, worsti)) continue;
+#pragma unroll
+      for (int p = KMAX - 1; p > 0; --p) {
+        if (p < k) {
+          const bool shift = cand_less(r, j, dk[p - 1], ik[p - 1]);
+          const bool place = !shift && cand_less(r, j, dk[p], ik[p]);
+          if (shift) dk[p] = dk[p - 1], ik[p] = ik[p - 1];
+          else if (place) dk[p] = r, ik[p] = j;
+        }
+      }
+      if (cand_less(r, j, dk[0], ik[0])) dk[0] = r, ik[0] = j;
+#pragma unroll
+      for (int p = 0; p < KMAX; ++p)
+        if (p == k - 1) worst = dk[p], worsti = ik[p];
+    }
+#pragma unroll 1
+    for (int round = 0; round < k; ++round) {  // warp arg-min over the list heads
+      double bd = dk[0];
+      int    bi = ik[0], bl = lane;
+      for (int d = 16; d > 0; d >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, d);
+        const int    oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        const int    ol = __shfl_xor_sync(0xffffffffu, bl, d);
+        if (cand_less(od, oi, bd, bi)) bd = od, bi = oi, bl = ol;
+      }
+      if (lane == 0) out_idx[(size_t)i * k + round] = (bi == 0x7fffffff) ? -1 : bi, out_d2[(size_t)i * k + round] = bd;
+      if (lane == bl) {
+#pragma unroll
+        for (int p = 0; p < KMAX - 1; ++p) dk[p] = dk[p + 1], ik[p] = ik[p + 1];
+        dk[KMAX - 1] = INFINITY, ik[KMAX - 1] = 0x7fffffff;
+      }
+    }
+  }
+}
+
 struct GateParams {
   double time_diff, ang, dist;
   int    k;
@@ -136,19 +418,21 @@ __global__ void resolve_pairs(const int* __restrict__ gated, int nq, int k, int 
   acc_out[i] = take;
 }
 
-// exclusive scan of (acc[i] >= 0) by one CTA, then scatter of the ordered pairs
+// exclusive scan of (acc[i] >= 0) by one CTA (8 items per thread per round), then scatter of the ordered pairs
 __global__ void __launch_bounds__(1024)
 compact_pairs(const int* __restrict__ acc, int nq, const double* __restrict__ qf, const double* __restrict__ tf,
               wc_corr_idx* __restrict__ out, unsigned char* __restrict__ first_is_target, int* __restrict__ n_out) {
+  constexpr int IT = 8;
   __shared__ int warp_sums[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < nq; base += 1024) {
-    const int i    = base + threadIdx.x;
-    const int c    = i < nq ? acc[i] : -1;
-    const int v    = c >= 0 ? 1 : 0;
-    int       incl = v;
+  for (int base = 0; base < nq; base += 1024 * IT) {
+    const int i0 = base + threadIdx.x * IT;
+    int       c[IT], v = 0;
+#pragma unroll
+    for (int u = 0; u < IT; ++u) c[u] = (i0 + u < nq) ? acc[i0 + u] : -1, v += c[u] >= 0;
+    int incl = v;
     for (int d = 1; d < 32; d <<= 1) {
       int o = __shfl_up_sync(0xffffffffu, incl, d);
       if ((threadIdx.x & 31) >= d) incl += o;
@@ -164,15 +448,19 @@ compact_pairs(const int* __restrict__ acc, int nq, const double* __restrict__ qf
       warp_sums[threadIdx.x] = wi - w;
     }
     __syncthreads();
-    const int pos = carry + warp_sums[threadIdx.x >> 5] + incl - v;
-    if (v) {
-      const bool query_first = qf[(size_t)i * FSTR + 12] < tf[(size_t)c * FSTR + 12];  // :41
-      out[pos].s1            = query_first ? i : c;
-      out[pos].s2            = query_first ? c : i;
+    int pos = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+#pragma unroll
+    for (int u = 0; u < IT; ++u) {
+      if (c[u] < 0) continue;
+      const int  i           = i0 + u;
+      const bool query_first = qf[(size_t)i * FSTR + 12] < tf[(size_t)c[u] * FSTR + 12];  // :41
+      out[pos].s1            = query_first ? i : c[u];
+      out[pos].s2            = query_first ? c[u] : i;
       first_is_target[pos]   = query_first ? 0 : 1;
+      ++pos;
     }
     __syncthreads();
-    if (threadIdx.x == 1023) carry = pos + v;
+    if (threadIdx.x == 1023) carry = pos;
     __syncthreads();
   }
   if (threadIdx.x == 0) *n_out = carry;
@@ -196,6 +484,26 @@ static wc_status match_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&c->d_corr_out, ns * sizeof(wc_corr_idx)));
   WC_CUDA(c, cudaMalloc(&c->d_fit_out, ns));
   WC_CUDA(c, cudaMallocHost(&c->h_flag, 16));
+  // uniform-grid index over the targets
+  GridBufs* G = (GridBufs*)calloc(1, sizeof(GridBufs));
+  c->d_grid   = G;
+  const size_t cap = wc_next_pow2(2 * ns);
+  G->mask          = cap - 1;
+  WC_CUDA(c, cudaMalloc(&G->keys, cap * 8));
+  WC_CUDA(c, cudaMalloc(&G->cid, cap * 4));
+  WC_CUDA(c, cudaMalloc(&G->cnt, (ns + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&G->off, (ns + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&G->cur, (ns + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&G->hpos, (ns + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&G->tcell, ns * 4));
+  WC_CUDA(c, cudaMalloc(&G->ncells, 8));
+  G->err = c->d_flag + 2;
+  WC_CUDA(c, cudaMalloc(&G->sfeat, ns * 8 * 8));
+  WC_CUDA(c, cudaMemsetAsync(G->keys, 0xff, cap * 8, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(G->cid, 0xff, cap * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(G->cnt, 0, (ns + 1) * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(G->cur, 0, (ns + 1) * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(G->ncells, 0, 8, c->stream));
   return WC_OK;
 }
 
@@ -205,6 +513,14 @@ void wc_match_free(wc_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_flag) cudaFreeHost(c->h_flag);
+  GridBufs* G = (GridBufs*)c->d_grid;
+  if (G) {
+    void* gp[] = {G->keys, G->cid, G->cnt, G->off, G->cur, G->hpos, G->tcell, G->ncells, G->sfeat};
+    for (void* p : gp)
+      if (p) cudaFree(p);
+    free(G);
+    c->d_grid = nullptr;
+  }
 }
 
 // Device-resident matcher core: query/target surfels already at d_q / d_t.  Leaves the pairs in d_corr_out.
@@ -215,6 +531,7 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
   wc_status as = match_alloc(c);
   if (as) return as;
   cudaStream_t st = c->stream;
+  WC_CUDA(c, cudaMemsetAsync(c->d_flag, 0, 16, st));
   const int    k  = c->prm.knn_candidates;
   if (k < 1 || k > KMAX) WC_FAIL(c, WC_EINVAL, "knn_candidates must be 1..%d", KMAX);
   const unsigned gq = (unsigned)((nq + 255) / 256), gt = (unsigned)((nt + 255) / 256);
@@ -224,10 +541,24 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     { ++c->n_launches; surfel_features<<<gt, 256, 0, st>>>(d_t, (int)nt, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_tfeat); }
     tfeat = c->d_tfeat;
   }
-  { ++c->n_launches; knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
-                                                                       c->d_knn_idx, c->d_knn_d2); }
-  GateParams G{c->prm.time_diff_threshold, c->prm.angular_dist_threshold, c->prm.surfel_dist_threshold, k};
-  { ++c->n_launches; gate_candidates<<<gq, 256, 0, st>>>(c->d_qfeat, (int)nq, tfeat, c->d_knn_idx, G, c->d_gated); }
+  if (nt < (size_t)c->knn_grid_min) {
+    { ++c->n_launches; knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
+                                                                         c->d_knn_idx, c->d_knn_d2); }
+  } else {
+    GridBufs GB = *(GridBufs*)c->d_grid;
+    { ++c->n_launches; grid_count<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB, (int)c->prm.max_surfels); }
+    { ++c->n_launches; grid_scan<<<1, 1024, 0, st>>>(GB); }
+    { ++c->n_launches; grid_scatter<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB); }
+    // d_gated is free until gate_candidates runs: its head holds the unresolved-query list, d_flag[3] the count
+    { ++c->n_launches; knn6_grid<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k, GB,
+                                                                     c->d_knn_idx, c->d_knn_d2, c->d_gated, c->d_flag + 3); }
+    { ++c->n_launches; knn6_fallback_warp<<<c->num_sms * 2, 256, 0, st>>>(c->d_qfeat, FSTR, tfeat, FSTR, (int)nt, k, c->d_gated,
+                                                                          c->d_flag + 3, c->d_knn_idx, c->d_knn_d2); }
+    { ++c->n_launches; grid_cleanup<<<c->num_sms, 256, 0, st>>>(GB); }
+    { ++c->n_launches; grid_reset_count<<<1, 1, 0, st>>>(GB); }
+  }
+  GateParams GP{c->prm.time_diff_threshold, c->prm.angular_dist_threshold, c->prm.surfel_dist_threshold, k};
+  { ++c->n_launches; gate_candidates<<<gq, 256, 0, st>>>(c->d_qfeat, (int)nq, tfeat, c->d_knn_idx, GP, c->d_gated); }
   WC_CUDA(c, cudaMemsetAsync(c->d_acc, 0xff, nq * 4, st));
   int* a = c->d_acc;
   int* b = c->d_acc2;
@@ -246,9 +577,10 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     if (it > (int)nq) WC_FAIL(c, WC_ENUMERIC, "pair de-duplication did not converge");
   }
   { ++c->n_launches; compact_pairs<<<1, 1024, 0, st>>>(a, (int)nq, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
-  WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 4, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 8, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
+  if (c->h_flag[2]) WC_FAIL(c, WC_EINVAL, "surfel centres outside the matcher grid range (+-1e6 cells) or non-finite");
   *n_out = (size_t)c->h_flag[1];
   return WC_OK;
 }

@@ -46,7 +46,7 @@ struct LMState {
   int    num_successful, num_unsuccessful, num_linearizations;
   int    D;              // reduced dimension
   int    err;            // assembly / evaluation errors (wc_status)
-  int    pad;
+  int    pending;        // a candidate has been evaluated and awaits lm_decide
   double radius, decrease_factor;
   double x_cost, x_norm, grad_max, model_cost_change, step_norm, initial_cost;
   double iter_cost[WC_MAX_ITER_LOG];
@@ -272,8 +272,7 @@ __device__ __forceinline__ void lane_block(int lane, int& bi, int& bj) {
   bj = bi + l;
 }
 
-__global__ void __launch_bounds__(LT) lidar_linearize(LinArgs a) {
-  extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* sm, int cta, int ncta) {
   double* Jt    = sm;            // JR x JS
   double* stage = sm + JR * JS;  // NGRP x 28 x 16 (flush staging; separate from Jt: a flush can happen mid-tile)
   __shared__ int sbk[LT];
@@ -301,8 +300,8 @@ __global__ void __launch_bounds__(LT) lidar_linearize(LinArgs a) {
   int    cur_b1 = -2, cur_b2 = -2, cur_bk = -1;
 
   const int ntiles = (a.n_rec + LT - 1) / LT;
-  const int per    = (ntiles + gridDim.x - 1) / gridDim.x;
-  const int tile0 = blockIdx.x * per, tile1 = min(ntiles, tile0 + per);
+  const int per    = (ntiles + ncta - 1) / ncta;
+  const int tile0 = cta * per, tile1 = min(ntiles, tile0 + per);
 
   // flush the per-thread 4x4 partial blocks of the current bucket into the dense normal equations
   auto flush = [&]() {
@@ -426,13 +425,13 @@ __device__ __forceinline__ void add_block(double* jac, int ld, int r0, int c0, c
     for (int j = 0; j < 3; ++j) jac[(r0 + i) * ld + c0 + j] += s * m.m[i][j];
 }
 
-constexpr int IMU_WARPS = 4;
+constexpr int IMU_WARPS = LT / 32;
 constexpr int IMU_LD    = 37;  // 36 Jacobian columns + residual
 
 // One warp per IMU triplet (BuildImuResiduals, lidar_odometry.cc:319-363).
-__global__ void __launch_bounds__(IMU_WARPS * 32) imu_linearize(ImuArgs a) {
-  __shared__ double sj[IMU_WARPS][12 * IMU_LD];
-  __shared__ int    sblk[IMU_WARPS][4];
+__device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm, int cta) {
+  double (*sj)[12 * IMU_LD] = reinterpret_cast<double (*)[12 * IMU_LD]>(sm);
+  __shared__ int sblk[IMU_WARPS][4];
   LMState* st = a.B.st;
   if (st->done || (a.at_candidate && !st->step_valid)) return;
   const int     buf  = a.at_candidate ? 1 - st->cur : st->cur;
@@ -441,7 +440,7 @@ __global__ void __launch_bounds__(IMU_WARPS * 32) imu_linearize(ImuArgs a) {
   double*       g    = a.B.g[buf];
   const int     N    = a.B.N;
   const int     lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int     i    = blockIdx.x * IMU_WARPS + wid;
+  const int     i    = cta * IMU_WARPS + wid;
   if (i + 2 >= a.n_imu) return;
   const wc_imu_state &i1 = a.imu[i], &i2 = a.imu[i + 1], &i3 = a.imu[i + 2];
   if (i1.timestamp < a.ts[0] || i3.timestamp > a.ts[a.K - 1]) return;  // :324-329 (timestamps increase)
@@ -546,8 +545,16 @@ __global__ void __launch_bounds__(IMU_WARPS * 32) imu_linearize(ImuArgs a) {
   }
 }
 
+// lidar tiles on the first n_lidar CTAs, IMU triplets on the rest: one launch per linearisation
+__global__ void __launch_bounds__(LT) window_linearize(LinArgs a, ImuArgs b, int n_lidar) {
+  extern __shared__ __align__(16) double sm[];
+  if ((int)blockIdx.x < n_lidar) lidar_linearize_body(a, sm, blockIdx.x, n_lidar);
+  else imu_linearize_body(b, sm, blockIdx.x - n_lidar);
+}
+
 // ------------------------------------------------------------------------------------------------ K7
 constexpr int LMT = 512;
+constexpr int CB  = 8;  // Cholesky block width
 
 __device__ __forceinline__ int col_of(int i, int fix_first) { return fix_first ? (i < 3 ? i : (i < 6 ? -1 : i - 3)) : i; }
 __device__ __forceinline__ int amb_of(int c, int fix_first) { return fix_first ? (c < 3 ? c : c + 3) : c; }
@@ -608,141 +615,19 @@ __global__ void __launch_bounds__(LMT) lm_init(SolveBufs B, wc_solve_opts o) {
     st->radius = o.initial_trust_region_radius, st->decrease_factor = 2.0;
     st->reuse_diagonal = 0, st->num_consecutive_invalid = 0, st->iteration = 0, st->last_successful = 1;
     st->num_successful = st->num_unsuccessful = 0, st->num_linearizations = 1;
-    st->termination = WC_TERM_NO_CONVERGENCE, st->done = 0, st->step_valid = 0;
+    st->termination = WC_TERM_NO_CONVERGENCE, st->done = 0, st->step_valid = 0, st->pending = 0;
     if (!isfinite(st->x_cost)) st->done = 1, st->termination = WC_TERM_FAILURE;
   }
 }
 
-// FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep: candidate point xc, or an invalid step
-__global__ void __launch_bounds__(LMT) lm_solve_step(SolveBufs B, wc_solve_opts o, int a_in_smem) {
-  extern __shared__ __align__(16) double sA[];
-  __shared__ double red[LMT / 32];
-  __shared__ int    fail;
-  LMState* st = B.st;
-  if (st->done) return;
-  const int t = threadIdx.x;
-  const int N = B.N, ff = B.fix_first, D = st->D;
-  if (t == 0) {
-    int term = -1;
-    if (st->iteration >= o.max_num_iterations) term = WC_TERM_NO_CONVERGENCE;
-    else if (st->last_successful && st->grad_max <= o.gradient_tolerance) term = WC_TERM_GRADIENT_TOL;
-    else if (st->radius < o.min_trust_region_radius) term = WC_TERM_MIN_RADIUS;
-    if (term >= 0) st->done = 1, st->termination = term;
-    fail = 0;
-  }
-  __syncthreads();
-  if (st->done) return;
-  const double* H = B.H[st->cur];
-  const double* g = B.g[st->cur];
-  double*       A = a_in_smem ? sA : B.A;
-  const double  radius = st->radius;
-  // LevenbergMarquardtStrategy::ComputeStep: diagonal of the scaled J^T J, clamped, refreshed only after an
-  // accepted step; A = S H S + diag / radius
-  if (!st->reuse_diagonal)
-    for (int c = t; c < D; c += LMT) {
-      const int    i = amb_of(c, ff);
-      const double d = H[(size_t)i * N + i] * B.scale[c] * B.scale[c];
-      B.diag[c]      = fmin(fmax(d, o.min_lm_diagonal), o.max_lm_diagonal);
-    }
-  __syncthreads();
-  for (int e = t; e < D * D; e += LMT) {
-    const int    r = e / D, c = e % D;
-    const double v = H[(size_t)amb_of(r, ff) * N + amb_of(c, ff)] * B.scale[r] * B.scale[c];
-    double       lm = 0.0;
-    if (r == c) {
-      const double s = sqrt(B.diag[r] / radius);
-      lm             = s * s;
-    }
-    A[e] = v + lm;
-  }
-  __syncthreads();
-  // right-looking Cholesky, lower triangle, in place
-  for (int j = 0; j < D; ++j) {
-    const double djj = A[j * D + j];
-    if (!(djj > 0.0) || !isfinite(djj)) {
-      if (t == 0) fail = 1;
-      break;  // uniform: every thread reads the same value
-    }
-    const double d = sqrt(djj);
-    __syncthreads();
-    for (int i = j + t; i < D; i += LMT) A[i * D + j] = (i == j) ? d : A[i * D + j] / d;
-    __syncthreads();
-    const int m = D - j - 1;
-    for (int e = t; e < m * m; e += LMT) {
-      const int r = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= r) A[r * D + c] -= A[r * D + j] * A[c * D + j];
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  bool valid = !fail;
-  // solve A y = gs, step = -y (column-oriented substitutions)
-  double* y = B.step;
-  if (valid) {
-    for (int c = t; c < D; c += LMT) y[c] = g[amb_of(c, ff)] * B.scale[c];
-    __syncthreads();
-    for (int j = 0; j < D; ++j) {
-      const double yj = y[j] / A[j * D + j];
-      __syncthreads();
-      if (t == 0) y[j] = yj;
-      for (int i = j + 1 + t; i < D; i += LMT) y[i] -= A[i * D + j] * yj;
-      __syncthreads();
-    }
-    for (int j = D - 1; j >= 0; --j) {
-      const double yj = y[j] / A[j * D + j];
-      __syncthreads();
-      if (t == 0) y[j] = yj;
-      for (int i = t; i < j; i += LMT) y[i] -= A[j * D + i] * yj;
-      __syncthreads();
-    }
-    for (int c = t; c < D; c += LMT) y[c] = -y[c];
-    __syncthreads();
-  }
-  // model_cost_change = -step^T (gs + Hs step / 2), Hs = S H S without damping
-  double part = 0.0, bad = 0.0;
-  if (valid)
-    for (int r = t; r < D; r += LMT) {
-      const int i  = amb_of(r, ff);
-      double    hd = 0.0;
-      for (int c = 0; c < D; ++c) hd = fma(H[(size_t)i * N + amb_of(c, ff)] * B.scale[c], y[c], hd);
-      hd *= B.scale[r];
-      part -= y[r] * (g[i] * B.scale[r] + 0.5 * hd);
-      if (!isfinite(y[r])) bad = 1.0;
-    }
-  const double mcc  = block_sum(part, red);
-  const double nbad = block_sum(bad, red);
-  valid             = valid && nbad == 0.0 && mcc > 0.0;
-  // delta = step .* scale, candidate, step norm
-  double sn = 0.0;
-  for (int i = t; i < N; i += LMT) {
-    const int    c = col_of(i, ff);
-    const double d = (valid && c >= 0) ? y[c] * B.scale[c] : 0.0;
-    B.xc[i]        = B.x[i] + d;
-    sn += d * d;
-  }
-  sn = block_sum(sn, red);
-  if (t == 0) {
-    st->iteration += 1;
-    st->last_successful   = 0;
-    st->reuse_diagonal    = 1;
-    st->step_valid        = valid ? 1 : 0;
-    st->model_cost_change = mcc;
-    st->step_norm         = sqrt(sn);
-    const int it          = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
-    st->iter_radius[it]   = radius;
-  }
-}
-
-// after the candidate evaluation: tolerances, accept / reject, trust-region update
-__global__ void __launch_bounds__(LMT) lm_decide(SolveBufs B, wc_solve_opts o) {
-  __shared__ double red[LMT / 32];
-  __shared__ int    accept;
-  LMState* st = B.st;
-  if (st->done) return;
+// ---- decide: after the candidate evaluation — tolerances, accept / reject, trust-region update
+__device__ void lm_decide_dev(const SolveBufs& B, const wc_solve_opts& o, double* red, int* s_accept) {
+  LMState*  st = B.st;
   const int t = threadIdx.x, N = B.N, ff = B.fix_first;
   const int it = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
   if (t == 0) {
-    accept = 0;
+    *s_accept   = 0;
+    st->pending = 0;
     if (!st->step_valid) {  // HandleInvalidStep
       st->num_unsuccessful += 1;
       st->iter_cost[it] = nan(""), st->iter_accepted[it] = 0;
@@ -753,7 +638,7 @@ __global__ void __launch_bounds__(LMT) lm_decide(SolveBufs B, wc_solve_opts o) {
       st->num_linearizations += 1;
       double cand = *B.cost[1 - st->cur];
       if (!isfinite(cand)) cand = DBL_MAX;
-      st->iter_cost[it] = cand;
+      st->iter_cost[it]     = cand;
       st->iter_accepted[it] = 0;
       if (st->step_norm <= o.parameter_tolerance * (st->x_norm + o.parameter_tolerance)) {
         st->done = 1, st->termination = WC_TERM_PARAMETER_TOL;
@@ -762,14 +647,14 @@ __global__ void __launch_bounds__(LMT) lm_decide(SolveBufs B, wc_solve_opts o) {
       } else {
         const double rd = (st->x_cost - cand) / st->model_cost_change;
         if (rd > o.min_relative_decrease) {
-          accept = 1;
+          *s_accept  = 1;
           st->x_cost = cand;
           st->cur    = 1 - st->cur;
           st->iter_accepted[it] = 1;
           st->num_successful += 1;
           st->last_successful = 1;
-          const double d  = 1.0 - pow(2.0 * rd - 1.0, 3);
-          st->radius      = fmin(o.max_trust_region_radius, st->radius / fmax(1.0 / 3.0, d));
+          const double d      = 1.0 - pow(2.0 * rd - 1.0, 3);
+          st->radius          = fmin(o.max_trust_region_radius, st->radius / fmax(1.0 / 3.0, d));
           st->decrease_factor = 2.0, st->reuse_diagonal = 0;
         } else {
           st->num_unsuccessful += 1;
@@ -779,7 +664,7 @@ __global__ void __launch_bounds__(LMT) lm_decide(SolveBufs B, wc_solve_opts o) {
     }
   }
   __syncthreads();
-  if (!accept) return;
+  if (!*s_accept) return;  // uniform
   const double* g = B.g[st->cur];
   double gm = 0.0, xn = 0.0;
   for (int i = t; i < N; i += LMT) {
@@ -791,6 +676,203 @@ __global__ void __launch_bounds__(LMT) lm_decide(SolveBufs B, wc_solve_opts o) {
   gm = block_max(gm, red);
   xn = block_sum(xn, red);
   if (t == 0) st->grad_max = gm, st->x_norm = sqrt(xn);
+  __syncthreads();
+}
+
+// ---- blocked right-looking Cholesky of the D x D matrix A (row-major, lower triangle), one CTA.
+// Per CB-wide block column: the diagonal block is factorised by warp 0, the panel below it by one thread per row,
+// the trailing update by a 32 x 16 thread tile.  3 block barriers per block column instead of 3 per column.
+__device__ void cholesky_blocked(double* A, int D, int* s_fail) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int tx = t & 31, ty = t >> 5;  // 32 x 16
+  for (int k0 = 0; k0 < D; k0 += CB) {
+    const int kb = min(CB, D - k0);
+    if (warp == 0) {
+      for (int j = 0; j < kb; ++j) {
+        const double djj = A[(k0 + j) * D + k0 + j];
+        if (!(djj > 0.0) || !isfinite(djj)) {
+          if (lane == 0) *s_fail = 1;
+          break;  // warp-uniform
+        }
+        const double d = sqrt(djj);
+        __syncwarp();
+        if (lane >= j && lane < kb) A[(k0 + lane) * D + k0 + j] = (lane == j) ? d : A[(k0 + lane) * D + k0 + j] / d;
+        __syncwarp();
+        for (int e = lane; e < CB * CB; e += 32) {
+          const int i = e / CB, k = e % CB;
+          if (k > j && k <= i && i < kb) A[(k0 + i) * D + k0 + k] -= A[(k0 + i) * D + k0 + j] * A[(k0 + k) * D + k0 + j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (*s_fail) return;  // uniform
+    // panel: L[i, k0:k0+kb] = A[i, k0:k0+kb] * Lkk^-T
+    for (int i = k0 + kb + t; i < D; i += LMT) {
+      double x[CB];
+#pragma unroll
+      for (int b = 0; b < CB; ++b) {
+        if (b < kb) {
+          double v = A[i * D + k0 + b];
+#pragma unroll
+          for (int c = 0; c < CB; ++c)
+            if (c < b) v -= x[c] * A[(k0 + b) * D + k0 + c];
+          x[b] = v / A[(k0 + b) * D + k0 + b];
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < CB; ++b)
+        if (b < kb) A[i * D + k0 + b] = x[b];
+    }
+    __syncthreads();
+    // trailing update of the lower triangle
+    const int r0 = k0 + kb;
+    for (int i = r0 + ty; i < D; i += LMT / 32) {
+      double li[CB];
+#pragma unroll
+      for (int b = 0; b < CB; ++b) li[b] = b < kb ? A[i * D + k0 + b] : 0.0;
+      for (int j = r0 + tx; j <= i; j += 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < CB; ++b)
+          if (b < kb) s = fma(li[b], A[j * D + k0 + b], s);
+        A[i * D + j] -= s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// y <- -A^-1 y for the Cholesky factor in A, by warp 0 (lane l owns entries l, l+32, ...): no block barriers
+__device__ void chol_solve_warp(const double* A, int D, double* y) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) return;
+  for (int j = 0; j < D; ++j) {  // forward: L z = y
+    double yj = 0.0;
+    if (lane == (j & 31)) yj = y[j] / A[j * D + j], y[j] = yj;
+    yj = __shfl_sync(0xffffffffu, yj, j & 31);
+    for (int i = j + 1 + ((lane - (j + 1)) & 31); i < D; i += 32) y[i] -= A[i * D + j] * yj;
+    __syncwarp();
+  }
+  for (int j = D - 1; j >= 0; --j) {  // backward: L^T x = z
+    double yj = 0.0;
+    if (lane == (j & 31)) yj = y[j] / A[j * D + j], y[j] = yj;
+    yj = __shfl_sync(0xffffffffu, yj, j & 31);
+    for (int i = lane; i < j; i += 32) y[i] -= A[j * D + i] * yj;
+    __syncwarp();
+  }
+  for (int i = lane; i < D; i += 32) y[i] = -y[i];
+  __syncwarp();
+}
+
+// One LM iteration boundary in one launch:
+//   (1) lm_decide on the outstanding candidate (if any),
+//   (2) FinalizeIterationAndCheckIfMinimizerCanContinue,
+//   (3) LevenbergMarquardtStrategy::ComputeStep + model cost change + candidate point,
+//   (4) clears the normal-equation buffer the next linearisation accumulates into.
+__global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int a_in_smem, int zero_next) {
+  extern __shared__ __align__(16) double sA[];
+  __shared__ double red[LMT / 32];
+  __shared__ int    s_fail, s_accept, s_done, s_pending;
+  LMState*  st = B.st;
+  const int t  = threadIdx.x;
+  // control flags are broadcast through shared memory: thread 0 rewrites them below while other warps may lag
+  if (t == 0) s_done = st->done, s_pending = st->pending;
+  __syncthreads();
+  if (s_done) return;
+  const int N = B.N, ff = B.fix_first, D = st->D;
+  if (s_pending) lm_decide_dev(B, o, red, &s_accept);
+  __syncthreads();
+  if (t == 0) {
+    int term = -1;
+    if (!st->done) {
+      if (st->iteration >= o.max_num_iterations) term = WC_TERM_NO_CONVERGENCE;
+      else if (st->last_successful && st->grad_max <= o.gradient_tolerance) term = WC_TERM_GRADIENT_TOL;
+      else if (st->radius < o.min_trust_region_radius) term = WC_TERM_MIN_RADIUS;
+      if (term >= 0) st->done = 1, st->termination = term;
+    }
+    s_fail = 0;
+    s_done = st->done;
+  }
+  __syncthreads();
+  if (s_done) return;
+  const double* H = B.H[st->cur];
+  const double* g = B.g[st->cur];
+  double*       A = a_in_smem ? sA : B.A;
+  const double  radius = st->radius;
+  if (!st->reuse_diagonal)
+    for (int c = t; c < D; c += LMT) {
+      const int    i = amb_of(c, ff);
+      const double d = H[(size_t)i * N + i] * B.scale[c] * B.scale[c];
+      B.diag[c]      = fmin(fmax(d, o.min_lm_diagonal), o.max_lm_diagonal);
+    }
+  __syncthreads();
+  // A = S H S + diag / radius (lower triangle is what the factorisation reads)
+  for (int r = t >> 5; r < D; r += LMT / 32) {
+    const size_t hrow = (size_t)amb_of(r, ff) * N;
+    const double sr   = B.scale[r];
+    for (int c = t & 31; c <= r; c += 32) {
+      double v = H[hrow + amb_of(c, ff)] * sr * B.scale[c];
+      if (r == c) {
+        const double s = sqrt(B.diag[r] / radius);
+        v += s * s;
+      }
+      A[r * D + c] = v;
+    }
+  }
+  __syncthreads();
+  cholesky_blocked(A, D, &s_fail);
+  __syncthreads();
+  bool    valid = !s_fail;
+  double* y     = B.step;
+  if (valid) {
+    for (int c = t; c < D; c += LMT) y[c] = g[amb_of(c, ff)] * B.scale[c];
+    __syncthreads();
+    chol_solve_warp(A, D, y);
+    __syncthreads();
+  }
+  // model_cost_change = -step^T (gs + Hs step / 2), Hs = S H S without damping (one warp per row)
+  double part = 0.0, bad = 0.0;
+  if (valid)
+    for (int r = t >> 5; r < D; r += LMT / 32) {
+      const size_t hrow = (size_t)amb_of(r, ff) * N;
+      double       hd   = 0.0;
+      for (int c = t & 31; c < D; c += 32) hd = fma(H[hrow + amb_of(c, ff)] * B.scale[c], y[c], hd);
+      for (int d = 16; d > 0; d >>= 1) hd += __shfl_down_sync(0xffffffffu, hd, d);
+      if ((t & 31) == 0) {
+        hd *= B.scale[r];
+        part -= y[r] * (g[amb_of(r, ff)] * B.scale[r] + 0.5 * hd);
+        if (!isfinite(y[r])) bad = 1.0;
+      }
+    }
+  const double mcc  = block_sum(part, red);
+  const double nbad = block_sum(bad, red);
+  valid             = valid && nbad == 0.0 && mcc > 0.0;
+  double sn = 0.0;
+  for (int i = t; i < N; i += LMT) {
+    const int    c = col_of(i, ff);
+    const double d = (valid && c >= 0) ? y[c] * B.scale[c] : 0.0;
+    B.xc[i]        = B.x[i] + d;
+    sn += d * d;
+  }
+  sn = block_sum(sn, red);
+  if (zero_next) {
+    const int nb = 1 - st->cur;
+    for (int i = t; i < N * N; i += LMT) B.H[nb][i] = 0.0;
+    for (int i = t; i < N; i += LMT) B.g[nb][i] = 0.0;
+    if (t == 0) *B.cost[nb] = 0.0;
+  }
+  if (t == 0) {
+    st->iteration += 1;
+    st->last_successful   = 0;
+    st->reuse_diagonal    = 1;
+    st->step_valid        = valid ? 1 : 0;
+    st->pending           = 1;
+    st->model_cost_change = mcc;
+    st->step_norm         = sqrt(sn);
+    const int it          = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
+    st->iter_radius[it]   = radius;
+  }
 }
 
 __global__ void extract_ts(const wc_sample_state* __restrict__ s, int K, double* __restrict__ ts, double* __restrict__ x) {
@@ -864,8 +946,8 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
-  WC_CUDA(c, cudaFuncSetAttribute(lidar_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
-  WC_CUDA(c, cudaFuncSetAttribute(lm_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WC_CUDA(c, cudaFuncSetAttribute(window_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  WC_CUDA(c, cudaFuncSetAttribute(lm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return WC_OK;
 }
 
@@ -986,7 +1068,7 @@ wc_status wc_window_upload_aux(wc_ctx* c, const wc_imu_state* imu, size_t n_imu,
 }
 
 // enqueue one linearisation (lidar + IMU [+ exchange]) on the ctx stream
-static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_solve_opts* o, int at_candidate) {
+static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_solve_opts* o, int at_candidate, int zeroed) {
   wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
   cudaStream_t  st = c->stream;
   SolveBufs     B  = B_in;
@@ -995,24 +1077,25 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     double *pH, *pg, *pc;
     wc_comm_partial_views(c, &pH, &pg, &pc);
     B.H[0] = B.H[1] = pH, B.g[0] = B.g[1] = pg, B.cost[0] = B.cost[1] = pc;
+    zeroed = 0;
   }
-  { ++c->n_launches; zero_buffers<<<64, 256, 0, st>>>(B, at_candidate); }
-  if (c->n_rec) {
-    LinArgs a;
-    a.rec = m->rec, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
-    a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
-    const int ntiles = (int)((c->n_rec + LT - 1) / LT);
-    const int grid   = ntiles < c->num_sms ? ntiles : c->num_sms;
-    { ++c->n_launches; lidar_linearize<<<grid, LT, LIN_SMEM, st>>>(a); }
-  }
+  if (!zeroed) { ++c->n_launches; zero_buffers<<<64, 256, 0, st>>>(B, at_candidate); }
+  LinArgs a;
+  a.rec = m->rec, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
+  a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
+  const int ntiles  = (int)((c->n_rec + LT - 1) / LT);
+  const int n_lidar = ntiles < c->num_sms ? ntiles : c->num_sms;
+  ImuArgs b;
+  memset(&b, 0, sizeof(b));
+  int n_imu_cta = 0;
   if (o->use_imu_factors && c->n_imu >= 3 && c->rank == 0) {
-    ImuArgs a;
-    a.imu = c->d_imu, a.n_imu = (int)c->n_imu, a.ts = m->ts, a.K = (int)c->K, a.B = B, a.at_candidate = at_candidate;
-    a.wg = c->prm.weight_gyr, a.wa = c->prm.weight_acc, a.wbg = c->prm.weight_bg, a.wba = c->prm.weight_ba;
-    a.dt = 1.0 / c->prm.imu_rate;
-    for (int k = 0; k < 3; ++k) a.grav[k] = m->grav[k];
-    { ++c->n_launches; imu_linearize<<<(unsigned)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS), IMU_WARPS * 32, 0, st>>>(a); }
+    b.imu = c->d_imu, b.n_imu = (int)c->n_imu, b.ts = m->ts, b.K = (int)c->K, b.B = B, b.at_candidate = at_candidate;
+    b.wg = c->prm.weight_gyr, b.wa = c->prm.weight_acc, b.wbg = c->prm.weight_bg, b.wba = c->prm.weight_ba;
+    b.dt = 1.0 / c->prm.imu_rate;
+    for (int k = 0; k < 3; ++k) b.grav[k] = m->grav[k];
+    n_imu_cta = (int)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS);
   }
+  if (n_lidar + n_imu_cta > 0) { ++c->n_launches; window_linearize<<<n_lidar + n_imu_cta, LT, LIN_SMEM, st>>>(a, b, n_lidar); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }
@@ -1044,17 +1127,17 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   WC_CUDA(c, cudaEventRecord(c->ev[4], st));
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
-  wc_status s = enqueue_linearize(c, B, &o, 0);
+  wc_status s = enqueue_linearize(c, B, &o, 0, 0);
   if (s) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;
   { ++c->n_launches; lm_init<<<1, LMT, 0, st>>>(B, o); }
-  const int batch = 4;
-  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 8; it += batch) {
+  const int batch = 8;
+  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
     for (int b = 0; b < batch; ++b) {
-      { ++c->n_launches; lm_solve_step<<<1, LMT, smem, st>>>(B, o, a_in_smem); }
-      if ((s = enqueue_linearize(c, B, &o, 1))) return s;
+      // decide(previous candidate) + next trust-region step + clear the candidate buffer, then linearise there
+      { ++c->n_launches; lm_step<<<1, LMT, smem, st>>>(B, o, a_in_smem, c->world == 1); }
+      if ((s = enqueue_linearize(c, B, &o, 1, 1))) return s;
       if ((s = wc_comm_allreduce(c, 1))) return s;
-      { ++c->n_launches; lm_decide<<<1, LMT, 0, st>>>(B, o); }
     }
     WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));
@@ -1106,7 +1189,7 @@ extern "C" wc_status wc_window_evaluate(wc_ctx* c, const wc_surfel* sld, size_t 
   SolveBufs     B  = make_bufs(c, 0);
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, N * 8, cudaMemcpyDeviceToDevice, st));
-  if ((s = enqueue_linearize(c, B, &o, 0))) return s;
+  if ((s = enqueue_linearize(c, B, &o, 0, 0))) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;
   if (cost) WC_CUDA(c, cudaMemcpyAsync(cost, m->cost, 8, cudaMemcpyDeviceToHost, st));
   if (grad) WC_CUDA(c, cudaMemcpyAsync(grad, m->gbuf[0], N * 8, cudaMemcpyDeviceToHost, st));
