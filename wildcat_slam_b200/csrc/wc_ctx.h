@@ -121,6 +121,8 @@ struct wc_ctx {
   unsigned char* d_fit_out;
   int*    d_scan_tmp;
   void*   d_grid;      // GridBufs (host copy of the device pointers)
+  double* d_part_d;    // partial top-k lists of the tiled exhaustive kNN stage
+  int*    d_part_i;
   long long knn_grid_min;  // target count from which the uniform-grid kNN replaces the brute-force scan
 
   // ---- window solve

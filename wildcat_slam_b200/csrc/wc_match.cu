@@ -10,6 +10,8 @@
 //                     query i takes its first gated candidate c unless c < i already took i.  acc[i] depends
 //                     only on acc[c] for c < i, so the fixed point is unique and equals the sequential result.
 //   compact_pairs     output in query order, each pair ordered by time (:41-45)
+#include <stdlib.h>
+
 #include "wc_ctx.h"
 #include "wc_device_math.cuh"
 
@@ -36,6 +38,7 @@ __global__ void surfel_features(const wc_surfel* __restrict__ s, int n, double i
 }
 
 // q: nq records of stride qstr (first 6 doubles = feature); t likewise.
+template <int KM>
 __global__ void __launch_bounds__(TILE)
 knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __restrict__ t, int tstr, int nt, int k,
                 int* __restrict__ out_idx, double* __restrict__ out_d2) {
@@ -45,10 +48,10 @@ knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __
   double     f[6];
 #pragma unroll
   for (int d = 0; d < 6; ++d) f[d] = active ? q[(size_t)i * qstr + d] : 0.0;
-  double dk[KMAX];
-  int    ik[KMAX];
+  double dk[KM];
+  int    ik[KM];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) dk[j] = INFINITY, ik[j] = -1;
+  for (int j = 0; j < KM; ++j) dk[j] = INFINITY, ik[j] = -1;
   double worst = INFINITY;  // dk[k-1]
   for (int base = 0; base < nt; base += TILE) {
     const int m = min(TILE, nt - base);
@@ -67,7 +70,7 @@ knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __
       if (r < worst) {
         const int id = base + j;
 #pragma unroll
-        for (int p = KMAX - 1; p > 0; --p) {
+        for (int p = KM - 1; p > 0; --p) {
           if (p < k) {
             const bool shift = r < dk[p - 1];
             const bool place = !shift && r < dk[p];
@@ -77,14 +80,14 @@ knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __
         }
         if (r < dk[0]) dk[0] = r, ik[0] = id;
 #pragma unroll
-        for (int p = 0; p < KMAX; ++p)
+        for (int p = 0; p < KM; ++p)
           if (p == k - 1) worst = dk[p];
       }
     }
   }
   if (!active) return;
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j)
+  for (int j = 0; j < KM; ++j)
     if (j < k) out_idx[(size_t)i * k + j] = ik[j], out_d2[(size_t)i * k + j] = dk[j];
 }
 
@@ -95,7 +98,6 @@ knn6_bruteforce(const double* __restrict__ q, int qstr, int nq, const double* __
 // b = (distance from the query to the faces of the visited cube) in one centre coordinate, so its squared 6-D distance
 // is >= b^2: the search stops as soon as the k-th best distance is strictly below b^2 — the result is the exact k-NN,
 // identical to brute force, ordered by (distance, target index).
-constexpr int RMAX = 3;
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33;
@@ -121,6 +123,8 @@ struct GridBufs {
   int*                tcell; // per target
   int*                ncells;
   double*             sfeat; // sorted: 8 doubles per target (f[6], index bits, pad)
+  double*             cbox;  // per cell: min[6], max[6] of the member features
+  unsigned long long* ckey;  // per cell: its key
   int*                err;
 };
 
@@ -144,7 +148,7 @@ __global__ void grid_count(const double* __restrict__ tf, int tstr, int nt, Grid
       if (k == WC_CELL_EMPTY) {
         id = atomicAdd(G.ncells, 1);
         if (id >= cell_cap) *G.err = 1, id = -2;
-        else G.hpos[id] = (int)h;
+        else G.hpos[id] = (int)h, G.ckey[id] = key;
         __threadfence();
         atomicExch(&G.cid[h], id);
         break;
@@ -208,6 +212,23 @@ __global__ void grid_scatter(const double* __restrict__ tf, int tstr, int nt, Gr
   o[7] = 0.0;
 }
 
+// 6-D bounding box of every cell's members (for the pruned scan of the cells the ring search does not reach)
+__global__ void grid_boxes(GridBufs G) {
+  const int n = *G.ncells;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    double lo[6], hi[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) lo[d] = INFINITY, hi[d] = -INFINITY;
+    for (int p = G.off[c]; p < G.off[c + 1]; ++p) {
+      const double* t = G.sfeat + (size_t)p * 8;
+#pragma unroll
+      for (int d = 0; d < 6; ++d) lo[d] = fmin(lo[d], t[d]), hi[d] = fmax(hi[d], t[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 6; ++d) G.cbox[(size_t)c * 12 + d] = lo[d], G.cbox[(size_t)c * 12 + 6 + d] = hi[d];
+  }
+}
+
 __global__ void grid_cleanup(GridBufs G) {
   const int n = *G.ncells;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -222,151 +243,130 @@ __global__ void grid_reset_count(GridBufs G) { *G.ncells = 0; }
 
 __device__ __forceinline__ bool cand_less(double d, int id, double dk, int ik) { return d < dk || (d == dk && id < ik); }
 
-__global__ void __launch_bounds__(128)
-knn6_grid(const double* __restrict__ q, int qstr, int nq, const double* __restrict__ tf, int tstr, int nt, int k, GridBufs G,
-          int* __restrict__ out_idx, double* __restrict__ out_d2, int* __restrict__ unres, int* __restrict__ n_unres) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  double f[6];
-#pragma unroll
-  for (int d = 0; d < 6; ++d) f[d] = q[(size_t)i * qstr + d];
-  double dk[KMAX];
-  int    ik[KMAX];
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j) dk[j] = INFINITY, ik[j] = 0x7fffffff;
-  double worst  = INFINITY;
-  int    worsti = 0x7fffffff;
-  auto   push   = [&](double r, int id) {
-    if (!cand_less(r, id, worst, worsti)) return;
-#pragma unroll
-    for (int p = KMAX - 1; p > 0; --p) {
-      if (p < k) {
-        const bool shift = cand_less(r, id, dk[p - 1], ik[p - 1]);
-        const bool place = !shift && cand_less(r, id, dk[p], ik[p]);
-        if (shift) dk[p] = dk[p - 1], ik[p] = ik[p - 1];
-        else if (place) dk[p] = r, ik[p] = id;
-      }
-    }
-    if (cand_less(r, id, dk[0], ik[0])) dk[0] = r, ik[0] = id;
-#pragma unroll
-    for (int p = 0; p < KMAX; ++p)
-      if (p == k - 1) worst = dk[p], worsti = ik[p];
-  };
-  auto dist = [&](const double* __restrict__ t) {
-    double r = 0.0;  // flann::L2_Simple accumulation order, no contraction
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-      const double diff = __dsub_rn(f[d], t[d]);
-      r                 = __dadd_rn(r, __dmul_rn(diff, diff));
-    }
-    return r;
-  };
-  const double cfx = floor(f[0]), cfy = floor(f[1]), cfz = floor(f[2]);
-  bool         done = false;
-  if (fabs(cfx) < 1e6 && fabs(cfy) < 1e6 && fabs(cfz) < 1e6) {
-    const long long ix = (long long)cfx, iy = (long long)cfy, iz = (long long)cfz;
-#pragma unroll 1
-    for (int r = 0; r <= RMAX && !done; ++r) {
-#pragma unroll 1
-      for (int dz = -r; dz <= r; ++dz)
-#pragma unroll 1
-        for (int dy = -r; dy <= r; ++dy) {
-          const bool face = (dz == -r || dz == r || dy == -r || dy == r);
-#pragma unroll 1
-          for (int dx = -r; dx <= r; dx += (face || r == 0) ? 1 : 2 * r) {
-            const unsigned long long key = cell_key(ix + dx, iy + dy, iz + dz);
-            unsigned long long       h   = mix64(key) & G.mask;
-            int                      id  = -1;
-            for (;; h = (h + 1) & G.mask) {
-              const unsigned long long kk = G.keys[h];
-              if (kk == key) { id = G.cid[h]; break; }
-              if (kk == WC_CELL_EMPTY) break;
-            }
-            if (id < 0) continue;
-            const int p1 = G.off[id + 1];
-#pragma unroll 1
-            for (int p = G.off[id]; p < p1; ++p) {
-              const double* t = G.sfeat + (size_t)p * 8;
-              push(dist(t), (int)__double_as_longlong(t[6]));
-            }
-          }
-        }
-      // every unvisited target is at least b away from the query in one centre coordinate
-      const double b = fmin(fmin(fmin(f[0] - (cfx - r), (cfx + r + 1) - f[0]), fmin(f[1] - (cfy - r), (cfy + r + 1) - f[1])),
-                            fmin(f[2] - (cfz - r), (cfz + r + 1) - f[2]));
-      if (worst < b * b * (1.0 - 1e-12)) done = true;
-    }
-  }
-  if (!done) {  // sparse neighbourhood: hand the query to the warp-per-query exhaustive scan (same total order)
-    unres[atomicAdd(n_unres, 1)] = i;
-  } else {
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-      if (j < k) out_idx[(size_t)i * k + j] = (ik[j] == 0x7fffffff) ? -1 : ik[j], out_d2[(size_t)i * k + j] = dk[j];
-  }
-}
-
-// Exhaustive exact k-NN for the few queries whose neighbourhood is too sparse for the ring search: one warp per query,
-// lanes stride over the targets keeping a private sorted top-k, then a k-round warp arg-min merge.
+// One warp per query.  The sorted candidate list lives in registers, one entry per lane (lane j = j-th best, k <= 32),
+// so an insertion is a ballot + popc + shfl_up instead of a per-thread array shuffle, and all 32 lanes always work on
+// the same query: the ring cells are probed in parallel (one cell per lane), the members of a cell are scanned 32 at a
+// time with coalesced 64-byte loads, and the far cells are box-tested 32 at a time.
+//   phase 0: the 27 cells of Chebyshev rings 0..1 around the query's cell; stop if the k-th best distance is strictly
+//            inside the visited cube (nothing outside can be closer);
+//   phase 1: every other cell whose 6-D bounding box can still hold a better (or tying) candidate.
+// Exact k-NN in (distance, target index) order — identical to the brute-force scan.
 __global__ void __launch_bounds__(256)
-knn6_fallback_warp(const double* __restrict__ q, int qstr, const double* __restrict__ tf, int tstr, int nt, int k,
-                   const int* __restrict__ unres, const int* __restrict__ n_unres, int* __restrict__ out_idx,
-                   double* __restrict__ out_d2) {
+knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int* __restrict__ out_idx, double* __restrict__ out_d2) {
   const int lane = threadIdx.x & 31;
   const int nw   = gridDim.x * (blockDim.x >> 5);
-  const int n    = *n_unres;
-  for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n; u += nw) {
-    const int i = unres[u];
-    double    f[6];
+  const int nc   = *G.ncells;
+#pragma unroll 1
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nq; i += nw) {
+    double f[6];
 #pragma unroll
     for (int d = 0; d < 6; ++d) f[d] = q[(size_t)i * qstr + d];
-    double dk[KMAX];
-    int    ik[KMAX];
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) dk[j] = INFINITY, ik[j] = 0x7fffffff;
-    double worst  = INFINITY;
-    int    worsti = 0x7fffffff;
+    double my_d = INFINITY, worst = INFINITY;  // lane j holds the j-th best candidate
+    int    my_i = 0x7fffffff, worsti = 0x7fffffff;
+
+    // scan the members [p0, p1) of one cell, 32 per step, inserting the ones that beat the current k-th best
+    auto scan_cell = [&](int p0, int p1) {
 #pragma unroll 1
-    for (int j = lane; j < nt; j += 32) {
-      const double* t = tf + (size_t)j * tstr;
-      double        r = 0.0;
+      for (int base = p0; base < p1; base += 32) {
+        const int p  = base + lane;
+        double    cd = INFINITY;
+        int       ci = 0x7fffffff;
+        if (p < p1) {
+          const double* t = G.sfeat + (size_t)p * 8;
+          double        rr = 0.0;  // flann::L2_Simple accumulation order, no contraction
 #pragma unroll
-      for (int d = 0; d < 6; ++d) {
-        const double diff = __dsub_rn(f[d], t[d]);
-        r                 = __dadd_rn(r, __dmul_rn(diff, diff));
-      }
-      if (!cand_less(r, j, worst, worsti)) continue;
-#pragma unroll
-      for (int p = KMAX - 1; p > 0; --p) {
-        if (p < k) {
-          const bool shift = cand_less(r, j, dk[p - 1], ik[p - 1]);
-          const bool place = !shift && cand_less(r, j, dk[p], ik[p]);
-          if (shift) dk[p] = dk[p - 1], ik[p] = ik[p - 1];
-          else if (place) dk[p] = r, ik[p] = j;
+          for (int d = 0; d < 6; ++d) {
+            const double diff = __dsub_rn(f[d], t[d]);
+            rr                = __dadd_rn(rr, __dmul_rn(diff, diff));
+          }
+          cd = rr, ci = (int)__double_as_longlong(t[6]);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, ci, worst, worsti));
+        while (m) {
+          const int    src = __ffs(m) - 1;
+          const double bd  = __shfl_sync(0xffffffffu, cd, src);
+          const int    bi  = __shfl_sync(0xffffffffu, ci, src);
+          m &= m - 1;
+          if (!cand_less(bd, bi, worst, worsti)) continue;  // the list moved on since the ballot
+          const int    pos = __popc(__ballot_sync(0xffffffffu, lane < k && cand_less(my_d, my_i, bd, bi)));
+          const double ud  = __shfl_up_sync(0xffffffffu, my_d, 1);
+          const int    ui  = __shfl_up_sync(0xffffffffu, my_i, 1);
+          if (lane == pos) my_d = bd, my_i = bi;
+          else if (lane > pos) my_d = ud, my_i = ui;
+          worst  = __shfl_sync(0xffffffffu, my_d, k - 1);
+          worsti = __shfl_sync(0xffffffffu, my_i, k - 1);
         }
       }
-      if (cand_less(r, j, dk[0], ik[0])) dk[0] = r, ik[0] = j;
-#pragma unroll
-      for (int p = 0; p < KMAX; ++p)
-        if (p == k - 1) worst = dk[p], worsti = ik[p];
-    }
+    };
+
+    const double    cfx = floor(f[0]), cfy = floor(f[1]), cfz = floor(f[2]);
+    const bool      rings_ok = fabs(cfx) < 1e6 && fabs(cfy) < 1e6 && fabs(cfz) < 1e6;
+    const long long ix = rings_ok ? (long long)cfx : 0, iy = rings_ok ? (long long)cfy : 0, iz = rings_ok ? (long long)cfz : 0;
+    bool            done = false;
+    if (rings_ok) {
+      // phase 0: lane l < 27 probes cell (dx, dy, dz) = (l % 3 - 1, (l / 3) % 3 - 1, l / 9 - 1)
+      int c0 = 0, c1 = 0;
+      if (lane < 27) {
+        const unsigned long long key = cell_key(ix + lane % 3 - 1, iy + (lane / 3) % 3 - 1, iz + lane / 9 - 1);
+        unsigned long long       h   = mix64(key) & G.mask;
+        for (;; h = (h + 1) & G.mask) {
+          const unsigned long long kk = G.keys[h];
+          if (kk == key) {
+            const int id = G.cid[h];
+            c0 = G.off[id], c1 = G.off[id + 1];
+            break;
+          }
+          if (kk == WC_CELL_EMPTY) break;
+        }
+      }
+      // own cell first (lane 13), then the rest
 #pragma unroll 1
-    for (int round = 0; round < k; ++round) {  // warp arg-min over the list heads
-      double bd = dk[0];
-      int    bi = ik[0], bl = lane;
-      for (int d = 16; d > 0; d >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, bd, d);
-        const int    oi = __shfl_xor_sync(0xffffffffu, bi, d);
-        const int    ol = __shfl_xor_sync(0xffffffffu, bl, d);
-        if (cand_less(od, oi, bd, bi)) bd = od, bi = oi, bl = ol;
+      for (int cc = 0; cc < 27; ++cc) {
+        const int src = cc == 0 ? 13 : (cc <= 13 ? cc - 1 : cc);
+        const int p0 = __shfl_sync(0xffffffffu, c0, src), p1 = __shfl_sync(0xffffffffu, c1, src);
+        if (p1 > p0) scan_cell(p0, p1);
       }
-      if (lane == 0) out_idx[(size_t)i * k + round] = (bi == 0x7fffffff) ? -1 : bi, out_d2[(size_t)i * k + round] = bd;
-      if (lane == bl) {
+      const double b = fmin(fmin(fmin(f[0] - (cfx - 1), (cfx + 2) - f[0]), fmin(f[1] - (cfy - 1), (cfy + 2) - f[1])),
+                            fmin(f[2] - (cfz - 1), (cfz + 2) - f[2]));
+      done = worst < b * b * (1.0 - 1e-12);
+    }
+    if (!done) {
+      // phase 1: box-test the remaining cells 32 at a time, scan the survivors one by one
+#pragma unroll 1
+      for (int cb = 0; cb < nc; cb += 32) {
+        const int cell = cb + lane;
+        bool      take = false;
+        int       p0 = 0, p1 = 0;
+        if (cell < nc) {
+          bool visited = false;
+          if (rings_ok) {
+            const unsigned long long key = G.ckey[cell];
+            const long long cx = (long long)(key >> 42) - (1 << 20), cy = (long long)((key >> 21) & 0x1fffff) - (1 << 20),
+                            cz = (long long)(key & 0x1fffff) - (1 << 20);
+            visited = llabs(cx - ix) <= 1 && llabs(cy - iy) <= 1 && llabs(cz - iz) <= 1;
+          }
+          if (!visited) {
+            const double* bx = G.cbox + (size_t)cell * 12;
+            double        lb = 0.0;
 #pragma unroll
-        for (int p = 0; p < KMAX - 1; ++p) dk[p] = dk[p + 1], ik[p] = ik[p + 1];
-        dk[KMAX - 1] = INFINITY, ik[KMAX - 1] = 0x7fffffff;
+            for (int d = 0; d < 6; ++d) {
+              const double ee = fmax(fmax(bx[d] - f[d], f[d] - bx[6 + d]), 0.0);
+              lb += ee * ee;
+            }
+            take = !(lb * (1.0 - 1e-12) > worst);  // skipped only if it cannot hold a better or tying candidate
+            p0 = G.off[cell], p1 = G.off[cell + 1];
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, take);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
+          scan_cell(q0, q1);  // (the bound was tested against an older, larger k-th distance: still exact)
+        }
       }
     }
+    if (lane < k) out_idx[(size_t)i * k + lane] = (my_i == 0x7fffffff) ? -1 : my_i, out_d2[(size_t)i * k + lane] = my_d;
   }
 }
 
@@ -499,6 +499,8 @@ static wc_status match_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&G->ncells, 8));
   G->err = c->d_flag + 2;
   WC_CUDA(c, cudaMalloc(&G->sfeat, ns * 8 * 8));
+  WC_CUDA(c, cudaMalloc(&G->cbox, (ns + 1) * 12 * 8));
+  WC_CUDA(c, cudaMalloc(&G->ckey, (ns + 1) * 8));
   WC_CUDA(c, cudaMemsetAsync(G->keys, 0xff, cap * 8, c->stream));
   WC_CUDA(c, cudaMemsetAsync(G->cid, 0xff, cap * 4, c->stream));
   WC_CUDA(c, cudaMemsetAsync(G->cnt, 0, (ns + 1) * 4, c->stream));
@@ -509,13 +511,13 @@ static wc_status match_alloc(wc_ctx* c) {
 
 void wc_match_free(wc_ctx* c) {
   void* ptrs[] = {c->d_msurf_q, c->d_msurf_t, c->d_qfeat, c->d_tfeat, c->d_knn_idx, c->d_knn_d2, c->d_gated,
-                  c->d_acc,     c->d_acc2,    c->d_flag,  c->d_corr_out, c->d_fit_out};
+                  c->d_acc,     c->d_acc2,    c->d_flag,  c->d_corr_out, c->d_fit_out, c->d_part_d, c->d_part_i};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   GridBufs* G = (GridBufs*)c->d_grid;
   if (G) {
-    void* gp[] = {G->keys, G->cid, G->cnt, G->off, G->cur, G->hpos, G->tcell, G->ncells, G->sfeat};
+    void* gp[] = {G->keys, G->cid, G->cnt, G->off, G->cur, G->hpos, G->tcell, G->ncells, G->sfeat, G->cbox, G->ckey};
     for (void* p : gp)
       if (p) cudaFree(p);
     free(G);
@@ -542,18 +544,17 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     tfeat = c->d_tfeat;
   }
   if (nt < (size_t)c->knn_grid_min) {
-    { ++c->n_launches; knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
+    if (k <= 10) { ++c->n_launches; knn6_bruteforce<10><<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
+                                                                         c->d_knn_idx, c->d_knn_d2); }
+    else { ++c->n_launches; knn6_bruteforce<KMAX><<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
                                                                          c->d_knn_idx, c->d_knn_d2); }
   } else {
     GridBufs GB = *(GridBufs*)c->d_grid;
     { ++c->n_launches; grid_count<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB, (int)c->prm.max_surfels); }
     { ++c->n_launches; grid_scan<<<1, 1024, 0, st>>>(GB); }
     { ++c->n_launches; grid_scatter<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB); }
-    // d_gated is free until gate_candidates runs: its head holds the unresolved-query list, d_flag[3] the count
-    { ++c->n_launches; knn6_grid<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k, GB,
-                                                                     c->d_knn_idx, c->d_knn_d2, c->d_gated, c->d_flag + 3); }
-    { ++c->n_launches; knn6_fallback_warp<<<c->num_sms * 2, 256, 0, st>>>(c->d_qfeat, FSTR, tfeat, FSTR, (int)nt, k, c->d_gated,
-                                                                          c->d_flag + 3, c->d_knn_idx, c->d_knn_d2); }
+    { ++c->n_launches; grid_boxes<<<c->num_sms, 256, 0, st>>>(GB); }
+    { ++c->n_launches; knn6_warp<<<c->num_sms * 8, 256, 0, st>>>(c->d_qfeat, FSTR, (int)nq, k, GB, c->d_knn_idx, c->d_knn_d2); }
     { ++c->n_launches; grid_cleanup<<<c->num_sms, 256, 0, st>>>(GB); }
     { ++c->n_launches; grid_reset_count<<<1, 1, 0, st>>>(GB); }
   }
@@ -577,11 +578,12 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     if (it > (int)nq) WC_FAIL(c, WC_ENUMERIC, "pair de-duplication did not converge");
   }
   { ++c->n_launches; compact_pairs<<<1, 1024, 0, st>>>(a, (int)nq, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
-  WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 8, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 12, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
   if (c->h_flag[2]) WC_FAIL(c, WC_EINVAL, "surfel centres outside the matcher grid range (+-1e6 cells) or non-finite");
   *n_out = (size_t)c->h_flag[1];
+  if (getenv("WC_DEBUG")) fprintf(stderr, "[wc_match] nq=%zu nt=%zu self=%d pairs=%d\n", nq, nt, self_match, c->h_flag[1]);
   return WC_OK;
 }
 
@@ -630,7 +632,7 @@ extern "C" wc_status wc_knn6(wc_ctx* c, const double* query6, size_t nq, const d
   WC_CUDA(c, cudaMemcpyAsync(c->d_qfeat, query6, nq * 48, cudaMemcpyHostToDevice, st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_tfeat, target6, nt * 48, cudaMemcpyHostToDevice, st));
   if (nq && nt)
-    { ++c->n_launches; knn6_bruteforce<<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, 6, (int)nq, c->d_tfeat, 6, (int)nt, k,
+    { ++c->n_launches; knn6_bruteforce<KMAX><<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, 6, (int)nq, c->d_tfeat, 6, (int)nt, k,
                                                                          c->d_knn_idx, c->d_knn_d2); }
   WC_CUDA(c, cudaGetLastError());
   WC_CUDA(c, cudaMemcpyAsync(out_idx, c->d_knn_idx, nq * k * 4, cudaMemcpyDeviceToHost, st));

@@ -679,90 +679,119 @@ __device__ void lm_decide_dev(const SolveBufs& B, const wc_solve_opts& o, double
   __syncthreads();
 }
 
-// ---- blocked right-looking Cholesky of the D x D matrix A (row-major, lower triangle), one CTA.
-// Per CB-wide block column: the diagonal block is factorised by warp 0, the panel below it by one thread per row,
-// the trailing update by a 32 x 16 thread tile.  3 block barriers per block column instead of 3 per column.
-__device__ void cholesky_blocked(double* A, int D, int* s_fail) {
+// ---- blocked right-looking Cholesky with the right-hand side carried as an extra row.
+// A holds D+1 rows of D doubles (row-major, lower triangle): rows 0..D-1 the SPD matrix, row D the right-hand side g^T.
+// After the call rows 0..D-1 hold L and row D holds z = L^-1 g (the forward substitution happens inside the
+// factorisation).  Linv receives the inverses of the CB x CB diagonal blocks for the backward substitution.
+// Per block column: (a) diagonal block factorised + inverted by warp 0 in registers (shuffles, no barriers),
+// (b) panel rows = A_panel * Lkk^-T, one thread per row, (c) trailing update on a 32 x 16 thread tile.
+__device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tx = t & 31, ty = t >> 5;  // 32 x 16
-  for (int k0 = 0; k0 < D; k0 += CB) {
+  for (int k0 = 0, blk = 0; k0 < D; k0 += CB, ++blk) {
     const int kb = min(CB, D - k0);
+    double*   Li = Linv + blk * CB * CB;
     if (warp == 0) {
-      for (int j = 0; j < kb; ++j) {
-        const double djj = A[(k0 + j) * D + k0 + j];
-        if (!(djj > 0.0) || !isfinite(djj)) {
-          if (lane == 0) *s_fail = 1;
-          break;  // warp-uniform
-        }
+      // lane i < kb owns row i of the diagonal block
+      double a[CB];
+#pragma unroll
+      for (int c = 0; c < CB; ++c) a[c] = (lane < kb && c <= lane && c < kb) ? A[(k0 + lane) * D + k0 + c] : (c == lane ? 1.0 : 0.0);
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) {
+        const double djj = __shfl_sync(0xffffffffu, a[j], j);
+        if (j < kb && (!(djj > 0.0) || !isfinite(djj))) bad = true;
         const double d = sqrt(djj);
-        __syncwarp();
-        if (lane >= j && lane < kb) A[(k0 + lane) * D + k0 + j] = (lane == j) ? d : A[(k0 + lane) * D + k0 + j] / d;
-        __syncwarp();
-        for (int e = lane; e < CB * CB; e += 32) {
-          const int i = e / CB, k = e % CB;
-          if (k > j && k <= i && i < kb) A[(k0 + i) * D + k0 + k] -= A[(k0 + i) * D + k0 + j] * A[(k0 + k) * D + k0 + j];
+        if (lane >= j) a[j] = (lane == j) ? d : a[j] / d;
+#pragma unroll
+        for (int k = j + 1; k < CB; ++k) {
+          const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+          if (lane >= k) a[k] -= a[j] * lkj;
         }
-        __syncwarp();
       }
+      if (bad && lane == 0) *s_fail = 1;
+      if (lane < kb)
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+          if (c <= lane) A[(k0 + lane) * D + k0 + c] = a[c];
+      // inverse of the lower-triangular block: lane c < CB solves L x = e_c (rows beyond kb are identity)
+      double x[CB];
+#pragma unroll
+      for (int r = 0; r < CB; ++r) {
+        double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+          if (c < r) v -= __shfl_sync(0xffffffffu, a[c], r) * x[c];
+        x[r] = v / __shfl_sync(0xffffffffu, a[r], r);
+      }
+      if (lane < CB)
+#pragma unroll
+        for (int r = 0; r < CB; ++r) Li[r * CB + lane] = x[r];  // Linv[r][c], zero above the diagonal
     }
     __syncthreads();
     if (*s_fail) return;  // uniform
-    // panel: L[i, k0:k0+kb] = A[i, k0:k0+kb] * Lkk^-T
-    for (int i = k0 + kb + t; i < D; i += LMT) {
-      double x[CB];
+    // (b) panel rows k0+kb .. D (row D = right-hand side): L[i][b] = sum_{c<=b} A[i][k0+c] * Linv[b][c]
+    for (int i = k0 + kb + t; i <= D; i += LMT) {
+      double ai[CB], li[CB];
+#pragma unroll
+      for (int c = 0; c < CB; ++c) ai[c] = c < kb ? A[i * D + k0 + c] : 0.0;
 #pragma unroll
       for (int b = 0; b < CB; ++b) {
-        if (b < kb) {
-          double v = A[i * D + k0 + b];
+        double v = 0.0;
 #pragma unroll
-          for (int c = 0; c < CB; ++c)
-            if (c < b) v -= x[c] * A[(k0 + b) * D + k0 + c];
-          x[b] = v / A[(k0 + b) * D + k0 + b];
-        }
+        for (int c = 0; c < CB; ++c)
+          if (c <= b) v = fma(ai[c], Li[b * CB + c], v);
+        li[b] = v;
       }
 #pragma unroll
       for (int b = 0; b < CB; ++b)
-        if (b < kb) A[i * D + k0 + b] = x[b];
+        if (b < kb) A[i * D + k0 + b] = li[b];
     }
     __syncthreads();
-    // trailing update of the lower triangle
+    // (c) trailing update of the lower triangle, including the right-hand-side row
     const int r0 = k0 + kb;
-    for (int i = r0 + ty; i < D; i += LMT / 32) {
+    for (int i = r0 + ty; i <= D; i += LMT / 32) {
       double li[CB];
 #pragma unroll
       for (int b = 0; b < CB; ++b) li[b] = b < kb ? A[i * D + k0 + b] : 0.0;
-      for (int j = r0 + tx; j <= i; j += 32) {
-        double s = 0.0;
+      const int jend = i < D ? i : D - 1;
+      for (int j = r0 + tx; j <= jend; j += 32) {
+        double sacc = 0.0;
 #pragma unroll
         for (int b = 0; b < CB; ++b)
-          if (b < kb) s = fma(li[b], A[j * D + k0 + b], s);
-        A[i * D + j] -= s;
+          if (b < kb) sacc = fma(li[b], A[j * D + k0 + b], sacc);
+        A[i * D + j] -= sacc;
       }
     }
     __syncthreads();
   }
 }
 
-// y <- -A^-1 y for the Cholesky factor in A, by warp 0 (lane l owns entries l, l+32, ...): no block barriers
-__device__ void chol_solve_warp(const double* A, int D, double* y) {
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x >= 32) return;
-  for (int j = 0; j < D; ++j) {  // forward: L z = y
-    double yj = 0.0;
-    if (lane == (j & 31)) yj = y[j] / A[j * D + j], y[j] = yj;
-    yj = __shfl_sync(0xffffffffu, yj, j & 31);
-    for (int i = j + 1 + ((lane - (j + 1)) & 31); i < D; i += 32) y[i] -= A[i * D + j] * yj;
-    __syncwarp();
+// backward substitution L^T x = z by blocks; z = row D of A; result x (length D) is written negated into y
+__device__ void chol_backward_blocked(const double* A, int D, const double* Linv, double* zrow, double* y, double* xblk) {
+  const int t    = threadIdx.x;
+  const int nblk = (D + CB - 1) / CB;
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int     k0 = blk * CB, kb = min(CB, D - k0);
+    const double* Li = Linv + blk * CB * CB;
+    if (t < kb) {  // x_blk = Linv^T z_blk
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < CB; ++r)
+        if (r >= t && r < kb) v = fma(Li[r * CB + t], zrow[k0 + r], v);
+      xblk[t]   = v;
+      y[k0 + t] = -v;
+    }
+    __syncthreads();
+    for (int i = t; i < k0; i += LMT) {
+      double v = zrow[i];
+#pragma unroll
+      for (int b = 0; b < CB; ++b)
+        if (b < kb) v = fma(-A[(k0 + b) * D + i], xblk[b], v);
+      zrow[i] = v;
+    }
+    __syncthreads();
   }
-  for (int j = D - 1; j >= 0; --j) {  // backward: L^T x = z
-    double yj = 0.0;
-    if (lane == (j & 31)) yj = y[j] / A[j * D + j], y[j] = yj;
-    yj = __shfl_sync(0xffffffffu, yj, j & 31);
-    for (int i = lane; i < j; i += 32) y[i] -= A[j * D + i] * yj;
-    __syncwarp();
-  }
-  for (int i = lane; i < D; i += 32) y[i] = -y[i];
-  __syncwarp();
 }
 
 // One LM iteration boundary in one launch:
@@ -774,6 +803,7 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   extern __shared__ __align__(16) double sA[];
   __shared__ double red[LMT / 32];
   __shared__ int    s_fail, s_accept, s_done, s_pending;
+  __shared__ double xblk[CB];
   LMState*  st = B.st;
   const int t  = threadIdx.x;
   // control flags are broadcast through shared memory: thread 0 rewrites them below while other warps may lag
@@ -781,8 +811,15 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   __syncthreads();
   if (s_done) return;
   const int N = B.N, ff = B.fix_first, D = st->D;
+#ifdef WC_LM_TIMING
+  long long tk[8];
+  tk[0] = clock64();
+#endif
   if (s_pending) lm_decide_dev(B, o, red, &s_accept);
   __syncthreads();
+#ifdef WC_LM_TIMING
+  tk[1] = clock64();
+#endif
   if (t == 0) {
     int term = -1;
     if (!st->done) {
@@ -798,7 +835,8 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   if (s_done) return;
   const double* H = B.H[st->cur];
   const double* g = B.g[st->cur];
-  double*       A = a_in_smem ? sA : B.A;
+  double*       A    = a_in_smem ? sA : B.A;                      // (D + 1) x D
+  double*       Linv = (a_in_smem ? sA : B.A) + (size_t)(D + 1) * D;  // diagonal-block inverses
   const double  radius = st->radius;
   if (!st->reuse_diagonal)
     for (int c = t; c < D; c += LMT) {
@@ -821,16 +859,24 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
     }
   }
   __syncthreads();
-  cholesky_blocked(A, D, &s_fail);
+  // right-hand side g_s = S g as row D
+  for (int c = t; c < D; c += LMT) A[D * D + c] = g[amb_of(c, ff)] * B.scale[c];
   __syncthreads();
+#ifdef WC_LM_TIMING
+  tk[2] = clock64();
+#endif
+  cholesky_blocked_rhs(A, D, Linv, &s_fail);
+  __syncthreads();
+#ifdef WC_LM_TIMING
+  tk[3] = clock64();
+#endif
   bool    valid = !s_fail;
   double* y     = B.step;
-  if (valid) {
-    for (int c = t; c < D; c += LMT) y[c] = g[amb_of(c, ff)] * B.scale[c];
-    __syncthreads();
-    chol_solve_warp(A, D, y);
-    __syncthreads();
-  }
+  if (valid) chol_backward_blocked(A, D, Linv, A + D * D, y, xblk);  // y = -(S H S + diag/radius)^-1 g_s
+  __syncthreads();
+#ifdef WC_LM_TIMING
+  tk[4] = clock64();
+#endif
   // model_cost_change = -step^T (gs + Hs step / 2), Hs = S H S without damping (one warp per row)
   double part = 0.0, bad = 0.0;
   if (valid)
@@ -856,6 +902,9 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
     sn += d * d;
   }
   sn = block_sum(sn, red);
+#ifdef WC_LM_TIMING
+  tk[5] = clock64();
+#endif
   if (zero_next) {
     const int nb = 1 - st->cur;
     for (int i = t; i < N * N; i += LMT) B.H[nb][i] = 0.0;
@@ -872,6 +921,12 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
     st->step_norm         = sqrt(sn);
     const int it          = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
     st->iter_radius[it]   = radius;
+#ifdef WC_LM_TIMING
+    tk[6] = clock64();
+    if (st->iteration == 3)
+      printf("lm_step cycles: decide %lld build %lld chol %lld back %lld mcc %lld zero %lld total %lld\n", tk[1] - tk[0],
+             tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[6] - tk[0]);
+#endif
   }
 }
 
@@ -939,7 +994,7 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->scale, N * 8));
   WC_CUDA(c, cudaMalloc(&m->diag, N * 8));
   WC_CUDA(c, cudaMalloc(&m->step, N * 8));
-  WC_CUDA(c, cudaMalloc(&m->A, N * N * 8));
+  WC_CUDA(c, cudaMalloc(&m->A, ((N + 1) * N + (N / CB + 1) * CB * CB) * 8));
   WC_CUDA(c, cudaMalloc(&c->d_x, N * 8));
   WC_CUDA(c, cudaMalloc(&c->d_xc, N * 8));
   WC_CUDA(c, cudaMalloc(&c->d_x0, N * 8));
@@ -1122,8 +1177,9 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   const int     N  = (int)(12 * c->K);
   SolveBufs     B  = make_bufs(c, o.fix_first_position ? 1 : 0);
   const int     D  = o.fix_first_position ? N - 3 : N;
-  const int     a_in_smem   = (size_t)D * D * 8 <= 200 * 1024;
-  const size_t  smem        = a_in_smem ? (size_t)D * D * 8 : 0;
+  const size_t  a_bytes     = ((size_t)(D + 1) * D + (size_t)((D + CB - 1) / CB) * CB * CB) * 8;
+  const int     a_in_smem   = a_bytes <= 200 * 1024;
+  const size_t  smem        = a_in_smem ? a_bytes : 0;
   WC_CUDA(c, cudaEventRecord(c->ev[4], st));
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
