@@ -319,6 +319,31 @@ __device__ __forceinline__ void mom_add(Mom& a, const Mom& b) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) a.ss[k] += b.ss[k];
 }
+// per-entry record: moments about the voxel centre + exact time sums + time extrema, 14 doubles
+//   [0] n, [1..3] s, [4..9] ss, [10] n*bin, [11] sum(Q - bin<<31) (both exact integers < 2^53), [12] tmin_inv bits, [13] tmax bits
+constexpr int REC = 14;
+__device__ __forceinline__ void rec_from_slot(const wc_slot* __restrict__ sl, unsigned lb, double q0, double q1, double* r) {
+  Mom m;
+  mom_zero(m);
+  mom_add_slot(m, sl, (int)(lb >> 12), q0, q1);
+  r[0] = m.n;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r[1 + k] = m.s[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r[4 + k] = m.ss[k];
+  r[10] = (double)(sl->n * (long long)(lb & 4095u));
+  r[11] = (double)sl->st;
+  r[12] = __longlong_as_double((long long)sl->tmin_inv);
+  r[13] = __longlong_as_double((long long)sl->tmax);
+}
+__device__ __forceinline__ void mom_add_rec(Mom& m, const double* r) {
+  m.n += r[0];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m.s[k] += r[1 + k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) m.ss[k] += r[4 + k];
+}
+
 // InitPlane / ClusterSurfels statistics: mean, population covariance, ascending eigen-pairs, likeness
 struct PlaneFit {
   double mu[3], cov[6], ev[3], like;
@@ -367,7 +392,9 @@ __device__ void bitonic_sort_smem(unsigned* keys, int npad) {
 }
 
 // One CTA per voxel whose entry count E lies in (E_LO, ECAP].
-template <int ECAP, int NT>
+// STAGE: the voxel's entry records are converted once and kept in shared memory (the per-node / per-cluster loops then
+// read ~30-cycle shared memory instead of chasing 128-byte slots through L2).
+template <int ECAP, int NT, bool STAGE>
 __global__ void __launch_bounds__(NT)
 cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg, const int* __restrict__ vox_off,
                  const unsigned long long* __restrict__ vox_key, wc_extract_status* __restrict__ st, EmitParams P, int e_lo,
@@ -378,9 +405,19 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
   unsigned*      leafbin = skey + ECAP;                                // ECAP
   int*           sid     = reinterpret_cast<int*>(leafbin + ECAP);     // ECAP slot ids
   unsigned char* flag    = reinterpret_cast<unsigned char*>(sid + ECAP);  // ECAP: 1 group head, 2 node head, 4 cluster head
+  double*        rec     = reinterpret_cast<double*>(smem_raw + ECAP * 16);  // STAGE: ECAP x REC doubles
+  // entry e -> its record (shared memory when staged, else built from the slot in L2)
+  auto get_rec = [&](int e, double* tmp) -> const double* {
+    if (STAGE) return rec + e * REC;
+    rec_from_slot(slots + sid[e], leafbin[e], P.q0, P.q1, tmp);
+    return tmp;
+  };
   __shared__ Mom           tot[73];   // 0 root, 1..8 layer 1, 9..72 layer 2
   __shared__ unsigned char emit[73];
   __shared__ unsigned char l1_cut[8];  // layer-1 child analysed and not planar => its children exist
+  __shared__ unsigned      bitmap[128];   // presence bits of the 64 x 64 (node, local bin) key space
+  __shared__ unsigned      bprefix[128];
+  __shared__ int           s_bmin, s_bmax;
 
   const int nv = st->n_voxels;
   for (int v = blockIdx.x; v < nv; v += gridDim.x) {
@@ -400,12 +437,22 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
         sid[e]                       = s;
         leafbin[e]                   = (unsigned)(key & 0x3ffffu);
         skey[e]                      = ((unsigned)(key & 0x3ffffu) << 14) | (unsigned)e;
+        if (STAGE) rec_from_slot(slots + s, (unsigned)(key & 0x3ffffu), P.q0, P.q1, rec + e * REC);
       } else {
         skey[e] = 0xffffffffu;
       }
     }
     for (int k = threadIdx.x; k < 73; k += NT) mom_zero(tot[k]), emit[k] = 0;
+    if (threadIdx.x == 0) s_bmin = 4096, s_bmax = -1;
     __syncthreads();
+    for (int e = threadIdx.x; e < E; e += NT) {
+      const int b = (int)(leafbin[e] & 4095u);
+      atomicMin(&s_bmin, b);
+      atomicMax(&s_bmax, b);
+    }
+    __syncthreads();
+    const int  bmin = s_bmin, nbl = s_bmax - s_bmin + 1;
+    const bool rank_sort = nbl <= 64;  // (leaf, local bin) fits a 4096-bit map: sort by ranking unique keys, no comparisons
     // voxel centre (surfel_extraction.cc:209-211)
     const unsigned long long vk = vox_key[v];
     const int vx = (int)((vk >> 30) & 32767u) - WC_VOX_BIAS + P.vox0[0], vy = (int)((vk >> 15) & 32767u) - WC_VOX_BIAS + P.vox0[1],
@@ -418,7 +465,50 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
           skey[e] = e < E ? ((level_key(leafbin[e], level) << 14) | (unsigned)e) : 0xffffffffu;
         __syncthreads();
       }
-      bitonic_sort_smem<NT>(skey, npad);
+      if (rank_sort) {
+        // keys are unique per entry, so the sorted position of an entry is the number of present keys below its own:
+        // set a presence bit per entry in the compact key space, prefix-popcount the 128 words, rank = prefix + popc.
+        auto compact = [&](unsigned lb) -> unsigned {
+          const unsigned leaf = lb >> 12, bl = (lb & 4095u) - (unsigned)bmin;
+          if (level == 2) return leaf * (unsigned)nbl + bl;
+          if (level == 1) return ((leaf >> 3) * (unsigned)nbl + bl) * 8u + (leaf & 7u);
+          return bl * 64u + leaf;
+        };
+        for (int w = threadIdx.x; w < 128; w += NT) bitmap[w] = 0u;
+        __syncthreads();
+        for (int e = threadIdx.x; e < E; e += NT) {
+          const unsigned ck = compact(leafbin[e]);
+          atomicOr(&bitmap[ck >> 5], 1u << (ck & 31u));
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive prefix of the word popcounts, 4 words per lane
+          unsigned c4[4], sum = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) c4[u] = __popc(bitmap[threadIdx.x * 4 + u]), sum += c4[u];
+          unsigned incl = sum;
+          for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)threadIdx.x >= d) incl += o;
+          }
+          unsigned run = incl - sum;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) bprefix[threadIdx.x * 4 + u] = run, run += c4[u];
+        }
+        __syncthreads();
+        unsigned mykey[(ECAP + NT - 1) / NT];
+        int      cnt = 0;
+        for (int e = threadIdx.x; e < E; e += NT) mykey[cnt++] = skey[e];
+        __syncthreads();
+        cnt = 0;
+        for (int e = threadIdx.x; e < E; e += NT) {
+          const unsigned ck   = compact(leafbin[e]);
+          const unsigned rank = bprefix[ck >> 5] + __popc(bitmap[ck >> 5] & ((1u << (ck & 31u)) - 1u));
+          skey[rank]          = mykey[cnt++];
+        }
+        __syncthreads();
+      } else {
+        bitonic_sort_smem<NT>(skey, npad);
+      }
       // head flags
       for (int i = threadIdx.x; i < E; i += NT) {
         const unsigned lk = skey[i] >> 14;
@@ -439,7 +529,8 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
           const int leaf = (int)(skey[i] >> 26);
           Mom       m;
           mom_zero(m);
-          for (int j = i; j < E && (j == i || !(flag[j] & 2)); ++j) mom_add_slot(m, slots + sid[skey[j] & 16383u], leaf, P.q0, P.q1);
+          double tmp[REC];
+          for (int j = i; j < E && (j == i || !(flag[j] & 2)); ++j) mom_add_rec(m, get_rec(skey[j] & 16383u, tmp));
           tot[9 + leaf] = m;
         }
         __syncthreads();
@@ -494,9 +585,13 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
         bool start = (f & 2) != 0;
         if (!start) {
           unsigned long long gmin_inv = 0, pmax = 0;
-          for (int j = i; j < E && (j == i || !(flag[j] & 1)); ++j) gmin_inv = max(gmin_inv, slots[sid[skey[j] & 16383u]].tmin_inv);
+          for (int j = i; j < E && (j == i || !(flag[j] & 1)); ++j) {
+            const int e = skey[j] & 16383u;
+            gmin_inv = max(gmin_inv, STAGE ? (unsigned long long)__double_as_longlong(rec[e * REC + 12]) : slots[sid[e]].tmin_inv);
+          }
           for (int j = i - 1; j >= 0; --j) {
-            pmax = max(pmax, slots[sid[skey[j] & 16383u]].tmax);
+            const int e = skey[j] & 16383u;
+            pmax = max(pmax, STAGE ? (unsigned long long)__double_as_longlong(rec[e * REC + 13]) : slots[sid[e]].tmax);
             if (flag[j] & 1) break;
           }
           // points[i].timestamp - cluster.back().timestamp > 0.05  (surfel_extraction.cc:24)
@@ -511,15 +606,12 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
         const unsigned lk0 = skey[i] >> 14;
         Mom            m;
         mom_zero(m);
-        long long tA = 0, tB = 0;
+        double tA = 0.0, tB = 0.0, tmp[REC];  // exact integer sums (< 2^53)
         for (int j = i; j < E && (j == i || !(flag[j] & 6)); ++j) {
-          const unsigned w    = skey[j];
-          const int      e    = w & 16383u;
-          const wc_slot* sl   = slots + sid[e];
-          const unsigned lb   = leafbin[e];
-          mom_add_slot(m, sl, (int)(lb >> 12), P.q0, P.q1);
-          tA += sl->n * (long long)(lb & 4095u);
-          tB += sl->st;
+          const double* r = get_rec(skey[j] & 16383u, tmp);
+          mom_add_rec(m, r);
+          tA += r[10];
+          tB += r[11];
         }
         if (m.n < (double)P.cmin) continue;  // surfel_extraction.cc:33
         PlaneFit f;
@@ -533,7 +625,7 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
           st->err_capacity = 1;
           continue;
         }
-        const double tmean = P.t_first + ((double)tA * 2147483648.0 + (double)tB) / (m.n * WC_TIME_SCALE);
+        const double tmean = P.t_first + (tA * 2147483648.0 + tB) / (m.n * WC_TIME_SCALE);
         wc_surfel    s;
         s.timestamp           = tmean;
         s.resolution          = level == 0 ? P.voxel : (level == 1 ? 2.0 * P.q0 : 2.0 * P.q1);  // (float)(quarter*4)
@@ -688,7 +780,8 @@ static wc_status extract_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->slot_cap * sizeof(wc_slot), c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_count, 0, (np + 1) * 4, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_cursor, 0, (np + 1) * 4, c->stream));
-  WC_CUDA(c, cudaFuncSetAttribute(cluster_eig_emit<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 13));
+  WC_CUDA(c, cudaFuncSetAttribute((cluster_eig_emit<512, 128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * (16 + 8 * REC)));
+  WC_CUDA(c, cudaFuncSetAttribute((cluster_eig_emit<8192, 256, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
   return WC_OK;
 }
 
@@ -753,12 +846,13 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   for (int k = 0; k < 3; ++k) E.view[k] = c->prm.view_point[k], E.vox0[k] = c->vox0[k], E.lps[k] = c->prm.layer_point_size[k];
   E.cmin = c->prm.cluster_min_points, E.max_layer = c->prm.max_layer;
   E.surf_cap = (int)c->prm.max_surfels;
-  { ++c->n_launches; cluster_eig_emit<256, 64><<<c->num_sms * 16, 64, 256 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 0,
-                                                                   c->d_surf_raw, c->d_sort_hi, c->d_sort_lo); }
-  { ++c->n_launches; cluster_eig_emit<2048, 128><<<c->num_sms * 4, 128, 2048 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
-                                                                     256, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo); }
-  { ++c->n_launches; cluster_eig_emit<8192, 256><<<c->num_sms * 2, 256, 8192 * 13, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
-                                                                     2048, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo); }
+  c->n_launches += 3;
+  cluster_eig_emit<128, 64, true><<<c->num_sms * 12, 64, 128 * (16 + 8 * REC), st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 0,
+                                                                                     c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  cluster_eig_emit<512, 128, true><<<c->num_sms * 3, 128, 512 * (16 + 8 * REC), st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat,
+                                                                                        E, 128, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 512,
+                                                                         c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
   WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
   { ++c->n_launches; extract_cleanup<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_hkeys, c->d_hslot, c->d_vkeys, c->d_vslot,
                                                   c->d_vox_hpos, c->d_vox_count, c->d_vox_cursor); }
