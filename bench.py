@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -71,7 +71,13 @@ class ClockSampler:
             except Exception:
                 pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+            try:  # the -lms loop produced nothing (very short timed region): take one sample now
+                out = subprocess.check_output(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                              text=True, stderr=subprocess.DEVNULL)
+                r = [c.strip() for c in out.strip().split(",")]
+                return {"sm_mhz": float(r[1]), "sm_max_mhz": float(r[2]), "reasons": ["single post-run sample"]}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
 
 

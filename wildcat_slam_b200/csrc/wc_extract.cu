@@ -54,27 +54,27 @@ __global__ void repack_points(const wc_point48* __restrict__ raw, int n, float4*
 }
 
 // ---------------------------------------------------------------------------------------------- K1
-// Insert-or-find in the open-addressed cell table; returns the dense slot index.
+// Insert-or-find in the open-addressed cell table; returns the slot index.  `fresh` is a slot id reserved by the caller
+// (one global counter bump per tile, not per cell: a single-address atomic per new cell serialises in L2); it is
+// consumed only if this call creates the cell, otherwise it stays an unused (all-zero, n == 0) slot that K2 skips.
 __device__ __forceinline__ int cell_slot(unsigned long long* __restrict__ keys, int* __restrict__ hslot,
                                          unsigned long long capmask, unsigned long long key, wc_slot* __restrict__ slots,
-                                         int slot_cap, wc_extract_status* st) {
+                                         int fresh, int slot_cap, wc_extract_status* st) {
   unsigned long long h = mix64(key) & capmask;
   for (unsigned long long probe = 0; probe <= capmask; ++probe, h = (h + 1) & capmask) {
     unsigned long long k = *((volatile unsigned long long*)&keys[h]);
     if (k == WC_KEY_EMPTY) {
       k = atomicCAS(&keys[h], WC_KEY_EMPTY, key);
-      if (k == WC_KEY_EMPTY) {  // we created the cell: allocate its dense slot and publish it
-        int s = atomicAdd(&st->n_slots, 1);
-        if (s >= slot_cap) {
+      if (k == WC_KEY_EMPTY) {  // we created the cell: publish its slot
+        if (fresh >= slot_cap) {
           st->err_capacity = 1;
           atomicExch(&hslot[h], -2);
           return -2;
         }
-        slots[s].key       = key;
-        slots[s].table_pos = (int)h;
-        __threadfence();
-        atomicExch(&hslot[h], s);
-        return s;
+        slots[fresh].key       = key;
+        slots[fresh].table_pos = (int)h;
+        atomicExch(&hslot[h], fresh);
+        return fresh;
       }
     }
     if (k == key) {
@@ -88,81 +88,146 @@ __device__ __forceinline__ int cell_slot(unsigned long long* __restrict__ keys, 
   return -2;
 }
 
-__global__ void __launch_bounds__(256)
+// Tile version: a CTA takes 2048 consecutive points, computes their cell keys, sorts (key hash, index) words in shared
+// memory so that the points of a cell become adjacent, and then one thread per run of equal keys sums the run and
+// performs ONE slot lookup + 13 RED atomics for it.  A spinning lidar revisits a 0.2 m cell with a handful of adjacent
+// azimuth columns, all inside one tile, so the atomics per point drop by the run length (5-10x).
+constexpr int KT = 2048, KNT = 256, KPT = KT / KNT;
+struct __align__(16) PtRec {
+  unsigned long long key, tob;
+  int                xi, yi, zi, qrel;
+};
+constexpr int K1_SMEM = KT * (int)sizeof(PtRec) + KT * 8 + KT * 2 + 64;
+
+__global__ void __launch_bounds__(KNT, 2)
 voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ time, ExtractParams P,
                   unsigned long long* __restrict__ keys, int* __restrict__ hslot, unsigned long long capmask,
                   wc_slot* __restrict__ slots, int slot_cap, wc_extract_status* __restrict__ st,
                   wc_point_assign* __restrict__ assign) {
-  const int lane   = threadIdx.x & 31;
-  const int stride = gridDim.x * blockDim.x;
-  const int n_pad  = (P.n + 31) & ~31;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-    const bool valid = i < P.n;
-    unsigned long long key = 0x8000000000000000ull | (unsigned long long)lane;  // never equal to a real key
-    int                xi = 0, yi = 0, zi = 0, qrel = 0;
-    unsigned long long tob = 0;
-    if (valid) {
-      const float4 p = xyz[i];
-      const double t = time[i];
-      if (i > 0 && t < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
-      const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-      // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
-      const int vx = (int)floor(__ddiv_rn(x, P.voxel));
-      const int vy = (int)floor(__ddiv_rn(y, P.voxel));
-      const int vz = (int)floor(__ddiv_rn(z, P.voxel));
-      // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
-      double cx = __dmul_rn(0.5 + (double)vx, P.voxel), cy = __dmul_rn(0.5 + (double)vy, P.voxel),
-             cz = __dmul_rn(0.5 + (double)vz, P.voxel);
-      int bx = x > cx, by = y > cy, bz = z > cz;
-      const int c1 = 4 * bx + 2 * by + bz;
-      cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
-      bx = x > cx, by = y > cy, bz = z > cz;
-      const int c2 = 4 * bx + 2 * by + bz;
-      cx += bx ? P.q1 : -P.q1, cy += by ? P.q1 : -P.q1, cz += bz ? P.q1 : -P.q1;
-      const int leaf = 8 * c1 + c2;
-      if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
-      // exact fixed-point coordinates relative to the leaf-cell centre, exact fixed-point time
-      xi = (int)__double2ll_rn((x - cx) * WC_COORD_SCALE);
-      yi = (int)__double2ll_rn((y - cy) * WC_COORD_SCALE);
-      zi = (int)__double2ll_rn((z - cz) * WC_COORD_SCALE);
-      const long long Q   = __double2ll_rn((t - P.t_first) * WC_TIME_SCALE);
-      const long long bin = Q >> WC_BIN_SHIFT;
-      qrel                = (int)(Q - (bin << WC_BIN_SHIFT));
-      tob                 = OrderedBits(t);
-      const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
-      if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
-          Q < 0 || bin >= WC_MAX_BINS) {
-        st->err_range = 1;
-      } else {
-        key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) | ((unsigned long long)rz << 18) |
-              ((unsigned long long)leaf << 12) | (unsigned long long)bin;
+  extern __shared__ __align__(16) unsigned char k1_smem[];
+  PtRec*              rec  = reinterpret_cast<PtRec*>(k1_smem);
+  unsigned long long* sw   = reinterpret_cast<unsigned long long*>(k1_smem + KT * sizeof(PtRec));  // hash32 << 32 | index
+  unsigned short*     rs   = reinterpret_cast<unsigned short*>(k1_smem + KT * sizeof(PtRec) + KT * 8);  // run start positions
+  __shared__ int      wsum[KNT / 32];
+  __shared__ int      s_nruns, s_base;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int ntiles = (P.n + KT - 1) / KT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * KT;
+    // ---- keys and exact fixed-point payload of this tile's points (coalesced loads)
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+      const int l = t + KNT * u, i = base + l;
+      PtRec     r;
+      r.key = WC_KEY_EMPTY, r.tob = 0, r.xi = r.yi = r.zi = r.qrel = 0;
+      if (i < P.n) {
+        const float4 p  = xyz[i];
+        const double tt = time[i];
+        if (i > 0 && tt < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
+        const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+        // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
+        const int vx = (int)floor(__ddiv_rn(x, P.voxel));
+        const int vy = (int)floor(__ddiv_rn(y, P.voxel));
+        const int vz = (int)floor(__ddiv_rn(z, P.voxel));
+        // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
+        double cx = __dmul_rn(0.5 + (double)vx, P.voxel), cy = __dmul_rn(0.5 + (double)vy, P.voxel),
+               cz = __dmul_rn(0.5 + (double)vz, P.voxel);
+        int bx = x > cx, by = y > cy, bz = z > cz;
+        const int c1 = 4 * bx + 2 * by + bz;
+        cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
+        bx = x > cx, by = y > cy, bz = z > cz;
+        const int c2 = 4 * bx + 2 * by + bz;
+        cx += bx ? P.q1 : -P.q1, cy += by ? P.q1 : -P.q1, cz += bz ? P.q1 : -P.q1;
+        const int leaf = 8 * c1 + c2;
+        if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
+        // exact fixed-point coordinates relative to the leaf-cell centre, exact fixed-point time
+        r.xi = (int)__double2ll_rn((x - cx) * WC_COORD_SCALE);
+        r.yi = (int)__double2ll_rn((y - cy) * WC_COORD_SCALE);
+        r.zi = (int)__double2ll_rn((z - cz) * WC_COORD_SCALE);
+        const long long Q   = __double2ll_rn((tt - P.t_first) * WC_TIME_SCALE);
+        const long long bin = Q >> WC_BIN_SHIFT;
+        r.qrel              = (int)(Q - (bin << WC_BIN_SHIFT));
+        r.tob               = OrderedBits(tt);
+        const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
+        if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
+            Q < 0 || bin >= WC_MAX_BINS) {
+          st->err_range = 1;
+        } else {
+          r.key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) | ((unsigned long long)rz << 18) |
+                  ((unsigned long long)leaf << 12) | (unsigned long long)bin;
+        }
+      }
+      rec[l] = r;
+      // invalid points sort to the end; equal keys share the hash, so they end up adjacent (a hash collision between
+      // different keys only splits a run, which is still exact because runs are delimited by the full key)
+      sw[l] = r.key == WC_KEY_EMPTY ? (0xffffffff00000000ull | (unsigned)l) : (((mix64(r.key) >> 32) << 32) | (unsigned)l);
+    }
+    __syncthreads();
+    // ---- bitonic sort of the 2048 words
+    for (int k = 2; k <= KT; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int u = 0; u < KT / 2 / KNT; ++u) {
+          const int q = t + KNT * u;
+          const int i = 2 * q - (q & (j - 1)), ixj = i + j;
+          const unsigned long long a = sw[i], b = sw[ixj];
+          if ((a > b) == ((i & k) == 0)) sw[i] = b, sw[ixj] = a;
+        }
+        __syncthreads();
+      }
+    // ---- run heads -> compact list of run start positions (block-wide exclusive scan of the head flags)
+    int           nh = 0;
+    unsigned char hd[KPT];
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+      const int                p  = t * KPT + u;
+      const unsigned long long kp = rec[sw[p] & 0xffffu].key;
+      const bool               h  = kp != WC_KEY_EMPTY && (p == 0 || rec[sw[p - 1] & 0xffffu].key != kp);
+      hd[u]                       = h;
+      nh += h;
+    }
+    int incl = nh;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (t < 32) {
+      int w = t < KNT / 32 ? wsum[t] : 0, wi = w;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (t >= d) wi += o;
+      }
+      if (t < KNT / 32) wsum[t] = wi - w;
+      if (t == KNT / 32 - 1) {
+        s_nruns = wi;
+        s_base  = atomicAdd(&st->n_slots, wi);  // reserve one slot id per run of this tile
       }
     }
-    // ---- warp aggregation: lanes holding the same cell reduce into the lowest lane of their group
-    const unsigned grp    = __match_any_sync(0xffffffffu, key);
-    const int      leader = __ffs(grp) - 1;
-    const int      gsz    = __popc(grp);
-    const bool     real   = (key >> 63) == 0;
-    const int      maxg   = __reduce_max_sync(0xffffffffu, real ? gsz : 1);
-    long long      a_n = 1, a_t = qrel, a_x = xi, a_y = yi, a_z = zi;
-    long long a_xx = (long long)xi * xi, a_xy = (long long)xi * yi, a_xz = (long long)xi * zi, a_yy = (long long)yi * yi,
-              a_yz = (long long)yi * zi, a_zz = (long long)zi * zi;
-    unsigned long long a_tmin = ~tob, a_tmax = tob;
-    for (int j = 1; j < maxg; ++j) {
-      const unsigned src = __fns(grp, 0, j + 1);  // lane of the (j+1)-th member, 0xffffffff if none
-      const int      sl  = src & 31;
-      const int      ox = __shfl_sync(0xffffffffu, xi, sl), oy = __shfl_sync(0xffffffffu, yi, sl),
-                oz = __shfl_sync(0xffffffffu, zi, sl), oq = __shfl_sync(0xffffffffu, qrel, sl);
-      const unsigned long long ot = __shfl_sync(0xffffffffu, tob, sl);
-      if (lane == leader && j < gsz) {
-        a_n += 1, a_t += oq, a_x += ox, a_y += oy, a_z += oz;
-        a_xx += (long long)ox * ox, a_xy += (long long)ox * oy, a_xz += (long long)ox * oz;
-        a_yy += (long long)oy * oy, a_yz += (long long)oy * oz, a_zz += (long long)oz * oz;
-        a_tmin = max(a_tmin, ~ot), a_tmax = max(a_tmax, ot);
+    __syncthreads();
+    int pos = wsum[warp] + incl - nh;
+#pragma unroll
+    for (int u = 0; u < KPT; ++u)
+      if (hd[u]) rs[pos++] = (unsigned short)(t * KPT + u);
+    __syncthreads();
+    // ---- one thread per run: sum it, then one slot lookup and 13 REDs
+    const int nruns = s_nruns;
+    for (int r = t; r < nruns; r += KNT) {
+      int                      p   = rs[r];
+      const PtRec              f0  = rec[sw[p] & 0xffffu];
+      const unsigned long long key = f0.key;
+      long long a_n = 0, a_t = 0, a_x = 0, a_y = 0, a_z = 0, a_xx = 0, a_xy = 0, a_xz = 0, a_yy = 0, a_yz = 0, a_zz = 0;
+      unsigned long long a_tmin = 0, a_tmax = 0;
+      for (; p < KT; ++p) {
+        const PtRec e = rec[sw[p] & 0xffffu];
+        if (e.key != key) break;
+        a_n += 1, a_t += e.qrel, a_x += e.xi, a_y += e.yi, a_z += e.zi;
+        a_xx += (long long)e.xi * e.xi, a_xy += (long long)e.xi * e.yi, a_xz += (long long)e.xi * e.zi;
+        a_yy += (long long)e.yi * e.yi, a_yz += (long long)e.yi * e.zi, a_zz += (long long)e.zi * e.zi;
+        a_tmin = max(a_tmin, ~e.tob), a_tmax = max(a_tmax, e.tob);
       }
-    }
-    if (real && lane == leader) {
-      const int s = cell_slot(keys, hslot, capmask, key, slots, slot_cap, st);
+      const int s = cell_slot(keys, hslot, capmask, key, slots, s_base + r, slot_cap, st);
       if (s >= 0) {
         wc_slot* sl = slots + s;
         atomicAdd((unsigned long long*)&sl->n, (unsigned long long)a_n);
@@ -180,6 +245,7 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
         atomicMax(&sl->tmax, a_tmax);
       }
     }
+    __syncthreads();
   }
 }
 
@@ -190,6 +256,10 @@ __global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __re
                             int* __restrict__ vox_hpos, int vox_cap) {
   const int ns = min(st->n_slots, INT_MAX);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
+    if (slots[s].n == 0) {  // reserved but never used (its run found an existing cell)
+      slots[s].vid = -1;
+      continue;
+    }
     const unsigned long long key = slots[s].key >> 18;
     unsigned long long       h   = mix64(key) & vmask;
     int                      vid = -2;
@@ -206,8 +276,7 @@ __global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __re
             vox_key[vid]  = key;
             vox_hpos[vid] = (int)h;  // remember the table position for cleanup
           }
-          __threadfence();
-          atomicExch(&vslot[h], vid);
+            atomicExch(&vslot[h], vid);
           break;
         }
       }
@@ -657,6 +726,10 @@ __global__ void extract_cleanup(wc_slot* __restrict__ slots, const wc_extract_st
   const int ns = st->n_slots, nv = st->n_voxels;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int s = tid; s < ns; s += nth) {
+    if (slots[s].n == 0) {
+      slots[s].vid = 0;
+      continue;
+    }
     const int h = slots[s].table_pos;
     keys[h]     = WC_KEY_EMPTY;
     hslot[h]    = -1;
@@ -780,6 +853,7 @@ static wc_status extract_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->slot_cap * sizeof(wc_slot), c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_count, 0, (np + 1) * 4, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_cursor, 0, (np + 1) * 4, c->stream));
+  WC_CUDA(c, cudaFuncSetAttribute(voxel_key_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
   WC_CUDA(c, cudaFuncSetAttribute((cluster_eig_emit<512, 128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * (16 + 8 * REC)));
   WC_CUDA(c, cudaFuncSetAttribute((cluster_eig_emit<8192, 256, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
   return WC_OK;
@@ -832,8 +906,9 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
 
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
   WC_CUDA(c, cudaMemsetAsync(c->d_xstat, 0, sizeof(wc_extract_status), st));
-  const int grid1 = c->num_sms * 8;
-  { ++c->n_launches; voxel_key_moments<<<grid1, 256, 0, st>>>(c->d_xyz, c->d_time, P, c->d_hkeys, c->d_hslot, c->hcap - 1, c->d_slots,
+  const int ntiles = (n + KT - 1) / KT;
+  const int grid1  = ntiles < c->num_sms * 2 ? ntiles : c->num_sms * 2;
+  { ++c->n_launches; voxel_key_moments<<<grid1, KNT, K1_SMEM, st>>>(c->d_xyz, c->d_time, P, c->d_hkeys, c->d_hslot, c->hcap - 1, c->d_slots,
                                            (int)c->slot_cap, c->d_xstat, c->want_assign ? c->d_assign : nullptr); }
   WC_CUDA(c, cudaEventRecord(c->ev[1], st));
   { ++c->n_launches; voxel_index<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,

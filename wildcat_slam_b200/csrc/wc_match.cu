@@ -149,7 +149,6 @@ __global__ void grid_count(const double* __restrict__ tf, int tstr, int nt, Grid
         id = atomicAdd(G.ncells, 1);
         if (id >= cell_cap) *G.err = 1, id = -2;
         else G.hpos[id] = (int)h, G.ckey[id] = key;
-        __threadfence();
         atomicExch(&G.cid[h], id);
         break;
       }

@@ -696,13 +696,15 @@ __device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail
       double a[CB];
 #pragma unroll
       for (int c = 0; c < CB; ++c) a[c] = (lane < kb && c <= lane && c < kb) ? A[(k0 + lane) * D + k0 + c] : (c == lane ? 1.0 : 0.0);
-      bool bad = false;
+      bool   bad = false;
+      double rinv = 1.0;  // 1 / L[lane][lane]
 #pragma unroll
       for (int j = 0; j < CB; ++j) {
         const double djj = __shfl_sync(0xffffffffu, a[j], j);
         if (j < kb && (!(djj > 0.0) || !isfinite(djj))) bad = true;
-        const double d = sqrt(djj);
-        if (lane >= j) a[j] = (lane == j) ? d : a[j] / d;
+        const double rs = rsqrt(djj);  // one reciprocal square root instead of sqrt + divide on the pivot chain
+        if (lane == j) rinv = rs;
+        if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
 #pragma unroll
         for (int k = j + 1; k < CB; ++k) {
           const double lkj = __shfl_sync(0xffffffffu, a[j], k);
@@ -722,7 +724,7 @@ __device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail
 #pragma unroll
         for (int c = 0; c < CB; ++c)
           if (c < r) v -= __shfl_sync(0xffffffffu, a[c], r) * x[c];
-        x[r] = v / __shfl_sync(0xffffffffu, a[r], r);
+        x[r] = v * __shfl_sync(0xffffffffu, rinv, r);
       }
       if (lane < CB)
 #pragma unroll

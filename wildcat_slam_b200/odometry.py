@@ -32,6 +32,15 @@ class Context:
         if st != T.WC_OK:
             raise abi.WildcatError(st, "wc_create", "(no CUDA device? the library has no CPU fallback)")
         self.device = device
+        self._bufs = {}
+
+    def buffer(self, name, n, dtype):
+        """persistent host output buffer (grown on demand) — avoids a capacity-sized allocation + memset per call"""
+        b = self._bufs.get(name)
+        if b is None or len(b) < n or b.dtype != dtype:
+            b = np.zeros(max(n, 1), dtype=dtype)
+            self._bufs[name] = b
+        return b
 
     def close(self):
         if self._h:
@@ -87,7 +96,7 @@ def BuildSurfels(cloud, ctx=None, want_assign=False, timing=None):
     ctx = ctx or default_context()
     cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
     cap = int(ctx.params.max_surfels)
-    out = np.zeros(cap, dtype=T.SURFEL)
+    out = ctx.buffer("surfels", cap, T.SURFEL)
     assign = np.zeros(len(cloud), dtype=T.ASSIGN) if want_assign else None
     n_out = C.c_size_t(0)
     ms = C.c_double(0)
@@ -130,8 +139,8 @@ class KnnSurfelMatcher:
             return np.zeros(0, T.CORR), np.zeros(0, np.uint8)
         t = self.target_surfels_
         self_match = int(t.ctypes.data == q.ctypes.data or (len(t) == len(q) and t.tobytes() == q.tobytes()))
-        out = np.zeros(len(q), dtype=T.CORR)
-        fit = np.zeros(len(q), dtype=np.uint8)
+        out = self.ctx.buffer("corr", len(q), T.CORR)
+        fit = self.ctx.buffer("fit", len(q), np.dtype(np.uint8))
         n = C.c_size_t(0)
         ms = C.c_double(0)
         st = self.ctx.lib.wc_match(self.ctx.handle, T.ptr(q), len(q), T.ptr(t), len(t), self_match, T.ptr(out), len(out),
@@ -260,7 +269,7 @@ class ResidentSweep:
 
     def fetch(self):
         cap = int(self.ctx.params.max_surfels)
-        out = np.zeros(cap, dtype=T.SURFEL)
+        out = self.ctx.buffer("surfels", cap, T.SURFEL)
         n = C.c_size_t(0)
         self.ctx.check(self.ctx.lib.wc_surfels_fetch(self.ctx.handle, T.ptr(out), cap, C.byref(n)), "wc_surfels_fetch")
         return out[: n.value].copy()
