@@ -230,20 +230,22 @@ def main():
         pts = pin.numpy().view(T.POINT48)
         pts[:] = w.points
         ctx2 = ctx
+        fix_p = ctx.pinned(len(fix), T.SURFEL)
+        fix_p[:] = fix
 
         def e2e_step():
             flush.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            s = od.BuildSurfels(pts, ctx=ctx2)
-            sld = od.UpdateSurfelPoses(w.imu, s, ctx=ctx2)
+            # host arrays live in pinned memory (wc_host_alloc); every call still moves them host<->device
+            sld = od.UpdateSurfelPoses(w.imu, od.BuildSurfels(pts, ctx=ctx2, copy=False), ctx=ctx2, inplace=True)
             m = od.KnnSurfelMatcher(ctx2)
             m.BuildIndex(sld)
             cs, _ = m.Match(sld)
             m2 = od.KnnSurfelMatcher(ctx2)
-            m2.BuildIndex(fix)
+            m2.BuildIndex(fix_p)
             cf, _ = m2.Match(sld)
-            smp, sg = od.SolveWindow(sld, fix, cs, cf, w.imu, w.samples, ctx=ctx2)
+            smp, sg = od.SolveWindow(sld, fix_p, cs, cf, w.imu, w.samples, ctx=ctx2)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             ns, nf = len(sld), len(fix)

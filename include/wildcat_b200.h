@@ -187,6 +187,9 @@ wc_status   wc_create(const wc_params* p, int device, wc_ctx** out);
 void        wc_destroy(wc_ctx* ctx);
 const char* wc_last_error(const wc_ctx* ctx);
 const char* wc_status_str(wc_status s);
+/* page-locked host memory (cudaMallocHost) for the caller's POD arrays: H2D / D2H of pinned buffers run at full PCIe rate */
+void*       wc_host_alloc(size_t bytes);
+void        wc_host_free(void* p);
 /* the CUDA stream (cudaStream_t) all work of this ctx is issued on; for CUDA-event timing by callers */
 void*       wc_stream(wc_ctx* ctx);
 

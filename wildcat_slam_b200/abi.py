@@ -45,6 +45,10 @@ def load():
     lib.wc_last_error.restype = C.c_char_p
     lib.wc_status_str.argtypes = [i32]
     lib.wc_status_str.restype = C.c_char_p
+    lib.wc_host_alloc.argtypes = [sz]
+    lib.wc_host_alloc.restype = vp
+    lib.wc_host_free.argtypes = [vp]
+    lib.wc_host_free.restype = None
     lib.wc_stream.argtypes = [vp]
     lib.wc_stream.restype = vp
     lib.wc_build_surfels.argtypes = [vp, vp, sz, vp, sz, P(sz), vp, P(dbl)]
@@ -71,7 +75,7 @@ def load():
     for name in declared_symbols():
         f = getattr(lib, name)  # raises AttributeError if the library lacks a declared entry point
         if name not in ("wc_abi_version", "wc_default_params", "wc_default_solve_opts", "wc_destroy", "wc_last_error",
-                        "wc_status_str", "wc_stream", "wc_launch_count"):
+                        "wc_status_str", "wc_stream", "wc_launch_count", "wc_host_alloc", "wc_host_free"):
             f.restype = i32
     _lib = lib
     return lib

@@ -97,6 +97,8 @@ extern "C" wc_status wc_create(const wc_params* p, int device, wc_ctx** out) {
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { free(c); return WC_ECUDA; }
   c->rank = 0, c->world = 1;
   c->knn_grid_min = 512;
+  c->lm_batch = 8;
+  if (const char* e = getenv("WC_LM_BATCH")) c->lm_batch = atoi(e);
   if (const char* e = getenv("WC_KNN_GRID_MIN")) c->knn_grid_min = atoll(e);  // test hook: force either exact search
   *out = c;
   return WC_OK;
@@ -118,3 +120,14 @@ extern "C" void wc_destroy(wc_ctx* c) {
 
 extern "C" const char* wc_last_error(const wc_ctx* c) { return c ? c->err : "null context"; }
 extern "C" void*       wc_stream(wc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// Pinned host memory for callers that want fast, truly asynchronous transfers of the POD arrays they pass to the
+// host-buffer entry points (bench.py's e2e leg, the Python mirror's persistent output buffers).
+extern "C" void* wc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void wc_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}

@@ -148,6 +148,7 @@ struct wc_ctx {
   int*             d_status;  // assemble errors
   void*            d_spline;  // wc_spline_mem
   int              n_imu_blocks;
+  int              lm_batch;  // LM iterations enqueued between host checks of the termination flag
 
   // ---- multi-GPU exchange
   int     rank, world;

@@ -679,60 +679,84 @@ __device__ void lm_decide_dev(const SolveBufs& B, const wc_solve_opts& o, double
   __syncthreads();
 }
 
-// ---- blocked right-looking Cholesky with the right-hand side carried as an extra row.
+// ---- blocked right-looking Cholesky with the right-hand side carried as an extra row, with look-ahead.
 // A holds D+1 rows of D doubles (row-major, lower triangle): rows 0..D-1 the SPD matrix, row D the right-hand side g^T.
 // After the call rows 0..D-1 hold L and row D holds z = L^-1 g (the forward substitution happens inside the
 // factorisation).  Linv receives the inverses of the CB x CB diagonal blocks for the backward substitution.
-// Per block column: (a) diagonal block factorised + inverted by warp 0 in registers (shuffles, no barriers),
-// (b) panel rows = A_panel * Lkk^-T, one thread per row, (c) trailing update on a 32 x 16 thread tile.
-__device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail) {
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int tx = t & 31, ty = t >> 5;  // 32 x 16
-  for (int k0 = 0, blk = 0; k0 < D; k0 += CB, ++blk) {
-    const int kb = min(CB, D - k0);
-    double*   Li = Linv + blk * CB * CB;
-    if (warp == 0) {
-      // lane i < kb owns row i of the diagonal block
-      double a[CB];
+// Per block column k: (b) panel rows = A_panel * Lkk^-T (one thread per row); (c1) trailing update of block column
+// k+1 only; then warp 0 factorises + inverts diagonal block k+1 in registers (shuffles, reciprocal square roots, no
+// divisions on the pivot chain) WHILE the other warps finish the trailing update (c2) — the serial pivot chain is
+// hidden behind the bulk update.
+__device__ __forceinline__ void chol_diag_block(double* A, int D, int k0, int kb, double* Li, int* s_fail) {
+  const int lane = threadIdx.x & 31;
+  double    a[CB];
 #pragma unroll
-      for (int c = 0; c < CB; ++c) a[c] = (lane < kb && c <= lane && c < kb) ? A[(k0 + lane) * D + k0 + c] : (c == lane ? 1.0 : 0.0);
-      bool   bad = false;
-      double rinv = 1.0;  // 1 / L[lane][lane]
+  for (int c = 0; c < CB; ++c) a[c] = (lane < kb && c <= lane && c < kb) ? A[(k0 + lane) * D + k0 + c] : (c == lane ? 1.0 : 0.0);
+  bool   bad  = false;
+  double rinv = 1.0;  // 1 / L[lane][lane]
 #pragma unroll
-      for (int j = 0; j < CB; ++j) {
-        const double djj = __shfl_sync(0xffffffffu, a[j], j);
-        if (j < kb && (!(djj > 0.0) || !isfinite(djj))) bad = true;
-        const double rs = rsqrt(djj);  // one reciprocal square root instead of sqrt + divide on the pivot chain
-        if (lane == j) rinv = rs;
-        if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
+  for (int j = 0; j < CB; ++j) {
+    const double djj = __shfl_sync(0xffffffffu, a[j], j);
+    if (j < kb && (!(djj > 0.0) || !isfinite(djj))) bad = true;
+    const double rs = rsqrt(djj);
+    if (lane == j) rinv = rs;
+    if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
 #pragma unroll
-        for (int k = j + 1; k < CB; ++k) {
-          const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-          if (lane >= k) a[k] -= a[j] * lkj;
-        }
-      }
-      if (bad && lane == 0) *s_fail = 1;
-      if (lane < kb)
-#pragma unroll
-        for (int c = 0; c < CB; ++c)
-          if (c <= lane) A[(k0 + lane) * D + k0 + c] = a[c];
-      // inverse of the lower-triangular block: lane c < CB solves L x = e_c (rows beyond kb are identity)
-      double x[CB];
-#pragma unroll
-      for (int r = 0; r < CB; ++r) {
-        double v = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int c = 0; c < CB; ++c)
-          if (c < r) v -= __shfl_sync(0xffffffffu, a[c], r) * x[c];
-        x[r] = v * __shfl_sync(0xffffffffu, rinv, r);
-      }
-      if (lane < CB)
-#pragma unroll
-        for (int r = 0; r < CB; ++r) Li[r * CB + lane] = x[r];  // Linv[r][c], zero above the diagonal
+    for (int k = j + 1; k < CB; ++k) {
+      const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+      if (lane >= k) a[k] -= a[j] * lkj;
     }
-    __syncthreads();
-    if (*s_fail) return;  // uniform
-    // (b) panel rows k0+kb .. D (row D = right-hand side): L[i][b] = sum_{c<=b} A[i][k0+c] * Linv[b][c]
+  }
+  if (bad && lane == 0) *s_fail = 1;
+  if (lane < kb)
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c <= lane) A[(k0 + lane) * D + k0 + c] = a[c];
+  double x[CB];  // lane c solves L x = e_c (rows beyond kb are identity)
+#pragma unroll
+  for (int r = 0; r < CB; ++r) {
+    double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c < r) v -= __shfl_sync(0xffffffffu, a[c], r) * x[c];
+    x[r] = v * __shfl_sync(0xffffffffu, rinv, r);
+  }
+  if (lane < CB)
+#pragma unroll
+    for (int r = 0; r < CB; ++r) Li[r * CB + lane] = x[r];  // Linv[r][c], zero above the diagonal
+}
+
+// trailing update A[i][j] -= sum_b L[i][k0+b] L[j][k0+b] for rows i in [r0, D] (row D = rhs) and columns j in
+// [j0, min(j1, i)] — rows dealt to `nw` warps starting at warp `w0`, lanes over the columns
+__device__ __forceinline__ void chol_trailing(double* A, int D, int k0, int kb, int r0, int j0, int j1, int w0, int nw) {
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) - w0;
+  if (warp < 0) return;
+  for (int i = r0 + warp; i <= D; i += nw) {
+    double li[CB];
+#pragma unroll
+    for (int b = 0; b < CB; ++b) li[b] = b < kb ? A[i * D + k0 + b] : 0.0;
+    const int jend = min(j1, i < D ? i : D - 1);
+    for (int j = j0 + lane; j <= jend; j += 32) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int b = 0; b < CB; b += 2) {
+        if (b < kb) s0 = fma(li[b], A[j * D + k0 + b], s0);
+        if (b + 1 < kb) s1 = fma(li[b + 1], A[j * D + k0 + b + 1], s1);
+      }
+      A[i * D + j] -= s0 + s1;
+    }
+  }
+}
+
+__device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail) {
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) chol_diag_block(A, D, 0, min(CB, D), Linv, s_fail);
+  __syncthreads();
+  for (int k0 = 0, blk = 0; k0 < D; k0 += CB, ++blk) {
+    if (*s_fail) return;  // uniform (written before the last barrier)
+    const int     kb = min(CB, D - k0);
+    const double* Li = Linv + blk * CB * CB;
+    // (b) panel rows k0+kb .. D: L[i][b] = sum_{c<=b} A[i][k0+c] * Linv[b][c]
     for (int i = k0 + kb + t; i <= D; i += LMT) {
       double ai[CB], li[CB];
 #pragma unroll
@@ -750,21 +774,16 @@ __device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail
         if (b < kb) A[i * D + k0 + b] = li[b];
     }
     __syncthreads();
-    // (c) trailing update of the lower triangle, including the right-hand-side row
     const int r0 = k0 + kb;
-    for (int i = r0 + ty; i <= D; i += LMT / 32) {
-      double li[CB];
-#pragma unroll
-      for (int b = 0; b < CB; ++b) li[b] = b < kb ? A[i * D + k0 + b] : 0.0;
-      const int jend = i < D ? i : D - 1;
-      for (int j = r0 + tx; j <= jend; j += 32) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int b = 0; b < CB; ++b)
-          if (b < kb) sacc = fma(li[b], A[j * D + k0 + b], sacc);
-        A[i * D + j] -= sacc;
-      }
+    if (r0 >= D) {  // last block column: only the right-hand-side row remains, nothing to update
+      break;
     }
+    // (c1) block column k+1 first (all warps), so that its diagonal block can be factorised ahead
+    chol_trailing(A, D, k0, kb, r0, r0, r0 + CB - 1, 0, LMT / 32);
+    __syncthreads();
+    // (a) next diagonal block by warp 0  ||  (c2) rest of the trailing update by warps 1..15
+    if (warp == 0) chol_diag_block(A, D, r0, min(CB, D - r0), Linv + (blk + 1) * CB * CB, s_fail);
+    else chol_trailing(A, D, k0, kb, r0 + CB, r0 + CB, D - 1, 1, LMT / 32 - 1);
     __syncthreads();
   }
 }
@@ -847,18 +866,16 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
       B.diag[c]      = fmin(fmax(d, o.min_lm_diagonal), o.max_lm_diagonal);
     }
   __syncthreads();
-  // A = S H S + diag / radius (lower triangle is what the factorisation reads)
-  for (int r = t >> 5; r < D; r += LMT / 32) {
-    const size_t hrow = (size_t)amb_of(r, ff) * N;
-    const double sr   = B.scale[r];
-    for (int c = t & 31; c <= r; c += 32) {
-      double v = H[hrow + amb_of(c, ff)] * sr * B.scale[c];
-      if (r == c) {
-        const double s = sqrt(B.diag[r] / radius);
-        v += s * s;
-      }
-      A[r * D + c] = v;
+  // A = S H S + diag / radius (the factorisation reads the lower triangle); flat loop: ~40 independent loads per thread
+  for (int e = t; e < D * D; e += LMT) {
+    const int r = e / D, c = e - r * D;
+    if (c > r) continue;
+    double v = H[(size_t)amb_of(r, ff) * N + amb_of(c, ff)] * B.scale[r] * B.scale[c];
+    if (r == c) {
+      const double sq = sqrt(B.diag[r] / radius);
+      v += sq * sq;
     }
+    A[e] = v;
   }
   __syncthreads();
   // right-hand side g_s = S g as row D
@@ -879,19 +896,14 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 #ifdef WC_LM_TIMING
   tk[4] = clock64();
 #endif
-  // model_cost_change = -step^T (gs + Hs step / 2), Hs = S H S without damping (one warp per row)
+  // model_cost_change = -y^T (g_s + H_s y / 2).  y solves (H_s + Dg) y = -g_s with Dg = diag / radius, hence
+  // H_s y = -g_s - Dg y and the change is (y^T Dg y - y^T g_s) / 2: no matrix-vector product needed.
   double part = 0.0, bad = 0.0;
   if (valid)
-    for (int r = t >> 5; r < D; r += LMT / 32) {
-      const size_t hrow = (size_t)amb_of(r, ff) * N;
-      double       hd   = 0.0;
-      for (int c = t & 31; c < D; c += 32) hd = fma(H[hrow + amb_of(c, ff)] * B.scale[c], y[c], hd);
-      for (int d = 16; d > 0; d >>= 1) hd += __shfl_down_sync(0xffffffffu, hd, d);
-      if ((t & 31) == 0) {
-        hd *= B.scale[r];
-        part -= y[r] * (g[amb_of(r, ff)] * B.scale[r] + 0.5 * hd);
-        if (!isfinite(y[r])) bad = 1.0;
-      }
+    for (int c = t; c < D; c += LMT) {
+      const double sq = sqrt(B.diag[c] / radius);
+      part += 0.5 * y[c] * (sq * sq * y[c] - g[amb_of(c, ff)] * B.scale[c]);
+      if (!isfinite(y[c])) bad = 1.0;
     }
   const double mcc  = block_sum(part, red);
   const double nbad = block_sum(bad, red);
@@ -1189,7 +1201,7 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   if (s) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;
   { ++c->n_launches; lm_init<<<1, LMT, 0, st>>>(B, o); }
-  const int batch = 8;
+  const int batch = c->lm_batch > 0 ? c->lm_batch : 8;
   for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
     for (int b = 0; b < batch; ++b) {
       // decide(previous candidate) + next trust-region step + clear the candidate buffer, then linearise there

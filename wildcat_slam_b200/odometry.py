@@ -33,18 +33,35 @@ class Context:
             raise abi.WildcatError(st, "wc_create", "(no CUDA device? the library has no CPU fallback)")
         self.device = device
         self._bufs = {}
+        self._pinned = []
+
+    def pinned(self, n, dtype):
+        """numpy array of n records backed by page-locked memory from wc_host_alloc (freed with the context)"""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n), 1) * dtype.itemsize
+        p = self.lib.wc_host_alloc(nbytes)
+        if not p:
+            raise abi.WildcatError(T.WC_ECUDA, "wc_host_alloc", f"{nbytes} bytes")
+        self._pinned.append(p)
+        raw = (C.c_uint8 * nbytes).from_address(p)
+        return np.frombuffer(raw, dtype=dtype, count=max(int(n), 1))
 
     def buffer(self, name, n, dtype):
-        """persistent host output buffer (grown on demand) — avoids a capacity-sized allocation + memset per call"""
+        """persistent pinned host buffer (grown on demand): no capacity-sized allocation + memset per call, and the
+        D2H of results / H2D of arrays handed on to the next stage run at full PCIe rate"""
         b = self._bufs.get(name)
-        if b is None or len(b) < n or b.dtype != dtype:
-            b = np.zeros(max(n, 1), dtype=dtype)
+        if b is None or len(b) < n or b.dtype != np.dtype(dtype):
+            b = self.pinned(max(n, 1), dtype)
             self._bufs[name] = b
         return b
 
     def close(self):
         if self._h:
+            self._bufs = {}
             self.lib.wc_destroy(self._h)
+            for p in self._pinned:
+                self.lib.wc_host_free(p)
+            self._pinned = []
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -88,7 +105,7 @@ def default_context():
     return _default_ctx
 
 
-def BuildSurfels(cloud, ctx=None, want_assign=False, timing=None):
+def BuildSurfels(cloud, ctx=None, want_assign=False, timing=None, copy=True):
     """void BuildSurfels(const std::vector<hilti_ros::Point>&, std::deque<Surfel::Ptr>&, GlobalMap&).
 
     cloud: POINT48 array with non-decreasing time.  Returns the surfels sorted by timestamp (world frame), and the
@@ -105,15 +122,19 @@ def BuildSurfels(cloud, ctx=None, want_assign=False, timing=None):
     ctx.check(st, "wc_build_surfels")
     if timing is not None:
         timing["gpu_ms"] = ms.value
-    surfels = out[: n_out.value].copy()
+    # copy=False: a view of the context's pinned result buffer, valid until the next BuildSurfels on this context
+    surfels = out[: n_out.value].copy() if copy else out[: n_out.value]
     return (surfels, assign) if want_assign else surfels
 
 
-def UpdateSurfelPoses(imu_states, surfels, ctx=None):
-    """UpdateSurfelPoses(const std::deque<ImuState>&, std::deque<Surfel::Ptr>&): returns the updated copy."""
+def UpdateSurfelPoses(imu_states, surfels, ctx=None, inplace=False):
+    """UpdateSurfelPoses(const std::deque<ImuState>&, std::deque<Surfel::Ptr>&): returns the updated copy (or updates the
+    given array in place, like the reference, with inplace=True)."""
     ctx = ctx or default_context()
     imu = np.ascontiguousarray(imu_states, dtype=T.IMU)
-    s = np.ascontiguousarray(surfels, dtype=T.SURFEL).copy()
+    s = np.ascontiguousarray(surfels, dtype=T.SURFEL)
+    if not inplace:
+        s = s.copy()
     ctx.check(ctx.lib.wc_update_surfel_poses(ctx.handle, T.ptr(imu), len(imu), T.ptr(s), len(s)), "wc_update_surfel_poses")
     return s
 
@@ -130,7 +151,7 @@ class KnnSurfelMatcher:
             return
         self.target_surfels_ = np.ascontiguousarray(surfels, dtype=T.SURFEL)
 
-    def Match(self, surfels, timing=None):
+    def Match(self, surfels, timing=None, copy=True):
         """Returns (correspondences CORR[], first_is_target uint8[]).  When the query array is the array the index
         was built from, both indices address it (sliding-window matcher); otherwise s1/s2 are time ordered and
         first_is_target tells which array s1 indexes (fixed-window matcher: always the target)."""
@@ -148,6 +169,8 @@ class KnnSurfelMatcher:
         self.ctx.check(st, "wc_match")
         if timing is not None:
             timing["gpu_ms"] = ms.value
+        if not copy:  # views of the context's pinned buffers, valid until the next Match on this context
+            return out[: n.value], fit[: n.value]
         return out[: n.value].copy(), fit[: n.value].copy()
 
     def KNearestSearchVectors(self, query6, target6, k=10):
