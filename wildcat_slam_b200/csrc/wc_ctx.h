@@ -77,8 +77,7 @@ struct wc_ctx {
   float4*             d_xyz;      // resident points
   double*             d_time;
   size_t              n_pts;
-  unsigned long long* d_hkeys;    // cell hash: keys
-  int*                d_hslot;    // cell hash: published slot index
+  void*               d_htab;     // cell hash: 16-byte {key, published slot id} entries
   size_t              hcap;
   wc_slot*            d_slots;
   size_t              slot_cap;

@@ -54,139 +54,111 @@ __global__ void repack_points(const wc_point48* __restrict__ raw, int n, float4*
 }
 
 // ---------------------------------------------------------------------------------------------- K1
-// Insert-or-find in the open-addressed cell table; returns the slot index.  `fresh` is a slot id reserved by the caller
-// (one global counter bump per tile, not per cell: a single-address atomic per new cell serialises in L2); it is
-// consumed only if this call creates the cell, otherwise it stays an unused (all-zero, n == 0) slot that K2 skips.
-__device__ __forceinline__ int cell_slot(unsigned long long* __restrict__ keys, int* __restrict__ hslot,
-                                         unsigned long long capmask, unsigned long long key, wc_slot* __restrict__ slots,
-                                         int fresh, int slot_cap, wc_extract_status* st) {
-  unsigned long long h = mix64(key) & capmask;
-  for (unsigned long long probe = 0; probe <= capmask; ++probe, h = (h + 1) & capmask) {
-    unsigned long long k = *((volatile unsigned long long*)&keys[h]);
-    if (k == WC_KEY_EMPTY) {
-      k = atomicCAS(&keys[h], WC_KEY_EMPTY, key);
-      if (k == WC_KEY_EMPTY) {  // we created the cell: publish its slot
-        if (fresh >= slot_cap) {
-          st->err_capacity = 1;
-          atomicExch(&hslot[h], -2);
-          return -2;
-        }
-        slots[fresh].key       = key;
-        slots[fresh].table_pos = (int)h;
-        atomicExch(&hslot[h], fresh);
-        return fresh;
-      }
-    }
-    if (k == key) {
-      int s;
-      while ((s = *((volatile int*)&hslot[h])) == -1) {
-      }
-      return s;
-    }
-  }
-  st->err_capacity = 1;
-  return -2;
-}
-
-// Tile version: a CTA takes 2048 consecutive points, computes their cell keys, sorts (key hash, index) words in shared
-// memory so that the points of a cell become adjacent, and then one thread per run of equal keys sums the run and
-// performs ONE slot lookup + 13 RED atomics for it.  A spinning lidar revisits a 0.2 m cell with a handful of adjacent
-// azimuth columns, all inside one tile, so the atomics per point drop by the run length (5-10x).
-constexpr int KT = 2048, KNT = 256, KPT = KT / KNT;
-struct __align__(16) PtRec {
-  unsigned long long key, tob;
-  int                xi, yi, zi, qrel;
+// Cell table entry: key and published slot id share one 16-byte word, so a probe touches one sector.
+struct __align__(16) HEnt {
+  unsigned long long key;
+  int                slot;  // -1 until the creator has written its slot record
+  int                pad;
 };
-constexpr int K1_SMEM = KT * (int)sizeof(PtRec) + KT * 8 + KT * 2 + 64;
+
+// Tile kernel: a CTA takes KT consecutive points, computes their cell keys, and groups equal keys with a shared-memory
+// hash table + counting sort (O(points), no comparison sort).  One thread per distinct key then sums that key's points in
+// exact 64-bit fixed point and writes ONE 128-byte run record with plain stores (the tile's records are contiguous: one
+// counter bump per tile reserves them).  No global atomics, fences or dependent probes here: a cell that straddles a
+// tile boundary simply yields two records, which voxel_index merges through the global cell table afterwards.  A
+// spinning lidar revisits a 0.2 m cell with a handful of adjacent rings x azimuth columns, all inside one tile, so the
+// record traffic per point drops by the run length (4-6x at C3).
+constexpr int KT = 2048, KNT = 512, KPT = KT / KNT, KTAB = 4096;
+constexpr int K1_SMEM = KTAB * 8 + KT * 16 + (KTAB / 2) * 4 + KTAB * 2 + KT * 2 + KT * 2;
 
 __global__ void __launch_bounds__(KNT, 2)
-voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ time, ExtractParams P,
-                  unsigned long long* __restrict__ keys, int* __restrict__ hslot, unsigned long long capmask,
-                  wc_slot* __restrict__ slots, int slot_cap, wc_extract_status* __restrict__ st,
-                  wc_point_assign* __restrict__ assign) {
+voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ time, ExtractParams P, wc_slot* __restrict__ slots,
+                  int slot_cap, wc_extract_status* __restrict__ st, wc_point_assign* __restrict__ assign) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
-  PtRec*              rec  = reinterpret_cast<PtRec*>(k1_smem);
-  unsigned long long* sw   = reinterpret_cast<unsigned long long*>(k1_smem + KT * sizeof(PtRec));  // hash32 << 32 | index
-  unsigned short*     rs   = reinterpret_cast<unsigned short*>(k1_smem + KT * sizeof(PtRec) + KT * 8);  // run start positions
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(k1_smem);           // KTAB keys
+  int4*               pay  = reinterpret_cast<int4*>(k1_smem + KTAB * 8);               // KT payloads (xi, yi, zi, qrel)
+  unsigned*           cnt2 = reinterpret_cast<unsigned*>(k1_smem + KTAB * 8 + KT * 16);  // KTAB packed 16-bit counters
+  unsigned short*     off  = reinterpret_cast<unsigned short*>(cnt2 + KTAB / 2);        // KTAB exclusive offsets
+  unsigned short*     runh = off + KTAB;                                                // table position of each run
+  unsigned short*     perm = runh + KT;                                                 // point ids grouped by run
   __shared__ int      wsum[KNT / 32];
   __shared__ int      s_nruns, s_base;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int ntiles = (P.n + KT - 1) / KT;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int base = tile * KT;
-    // ---- keys and exact fixed-point payload of this tile's points (coalesced loads)
+  const int base = blockIdx.x * KT;
+
+  for (int k = t; k < KTAB; k += KNT) skey[k] = WC_KEY_EMPTY;
+  for (int k = t; k < KTAB / 2; k += KNT) cnt2[k] = 0u;
+  __syncthreads();
+
+  // ---- keys, exact fixed-point payload, shared-memory insert + rank of the point inside its key group
+  int hpos[KPT], rank[KPT];
 #pragma unroll
-    for (int u = 0; u < KPT; ++u) {
-      const int l = t + KNT * u, i = base + l;
-      PtRec     r;
-      r.key = WC_KEY_EMPTY, r.tob = 0, r.xi = r.yi = r.zi = r.qrel = 0;
-      if (i < P.n) {
-        const float4 p  = xyz[i];
-        const double tt = time[i];
-        if (i > 0 && tt < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
-        const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-        // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
-        const int vx = (int)floor(__ddiv_rn(x, P.voxel));
-        const int vy = (int)floor(__ddiv_rn(y, P.voxel));
-        const int vz = (int)floor(__ddiv_rn(z, P.voxel));
-        // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
-        double cx = __dmul_rn(0.5 + (double)vx, P.voxel), cy = __dmul_rn(0.5 + (double)vy, P.voxel),
-               cz = __dmul_rn(0.5 + (double)vz, P.voxel);
-        int bx = x > cx, by = y > cy, bz = z > cz;
-        const int c1 = 4 * bx + 2 * by + bz;
-        cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
-        bx = x > cx, by = y > cy, bz = z > cz;
-        const int c2 = 4 * bx + 2 * by + bz;
-        cx += bx ? P.q1 : -P.q1, cy += by ? P.q1 : -P.q1, cz += bz ? P.q1 : -P.q1;
-        const int leaf = 8 * c1 + c2;
-        if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
-        // exact fixed-point coordinates relative to the leaf-cell centre, exact fixed-point time
-        r.xi = (int)__double2ll_rn((x - cx) * WC_COORD_SCALE);
-        r.yi = (int)__double2ll_rn((y - cy) * WC_COORD_SCALE);
-        r.zi = (int)__double2ll_rn((z - cz) * WC_COORD_SCALE);
-        const long long Q   = __double2ll_rn((tt - P.t_first) * WC_TIME_SCALE);
-        const long long bin = Q >> WC_BIN_SHIFT;
-        r.qrel              = (int)(Q - (bin << WC_BIN_SHIFT));
-        r.tob               = OrderedBits(tt);
-        const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
-        if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
-            Q < 0 || bin >= WC_MAX_BINS) {
-          st->err_range = 1;
-        } else {
-          r.key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) | ((unsigned long long)rz << 18) |
-                  ((unsigned long long)leaf << 12) | (unsigned long long)bin;
+  for (int u = 0; u < KPT; ++u) {
+    const int l = t + KNT * u, i = base + l;
+    hpos[u] = -1, rank[u] = 0;
+    if (i < P.n) {
+      const float4 p  = xyz[i];
+      const double tt = time[i];
+      if (i > 0 && tt < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
+      const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+      // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
+      const int vx = (int)floor(__ddiv_rn(x, P.voxel));
+      const int vy = (int)floor(__ddiv_rn(y, P.voxel));
+      const int vz = (int)floor(__ddiv_rn(z, P.voxel));
+      // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
+      double cx = __dmul_rn(0.5 + (double)vx, P.voxel), cy = __dmul_rn(0.5 + (double)vy, P.voxel),
+             cz = __dmul_rn(0.5 + (double)vz, P.voxel);
+      int bx = x > cx, by = y > cy, bz = z > cz;
+      const int c1 = 4 * bx + 2 * by + bz;
+      cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
+      bx = x > cx, by = y > cy, bz = z > cz;
+      const int c2 = 4 * bx + 2 * by + bz;
+      cx += bx ? P.q1 : -P.q1, cy += by ? P.q1 : -P.q1, cz += bz ? P.q1 : -P.q1;
+      const int leaf = 8 * c1 + c2;
+      if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
+      // exact fixed-point coordinates relative to the leaf-cell centre, exact fixed-point time
+      int4 q;
+      q.x = (int)__double2ll_rn((x - cx) * WC_COORD_SCALE);
+      q.y = (int)__double2ll_rn((y - cy) * WC_COORD_SCALE);
+      q.z = (int)__double2ll_rn((z - cz) * WC_COORD_SCALE);
+      const long long Q   = __double2ll_rn((tt - P.t_first) * WC_TIME_SCALE);
+      const long long bin = Q >> WC_BIN_SHIFT;
+      q.w                 = (int)(Q - (bin << WC_BIN_SHIFT));
+      pay[l]              = q;
+      const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
+      if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
+          Q < 0 || bin >= WC_MAX_BINS) {
+        st->err_range = 1;
+      } else {
+        const unsigned long long key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) |
+                                       ((unsigned long long)rz << 18) | ((unsigned long long)leaf << 12) | (unsigned long long)bin;
+        unsigned h = (unsigned)(mix64(key) >> 40) & (KTAB - 1);
+        for (;;) {  // at most KT distinct keys in KTAB = 2 KT positions: always terminates
+          unsigned long long k = skey[h];
+          if (k == WC_KEY_EMPTY) k = atomicCAS(&skey[h], WC_KEY_EMPTY, key);
+          if (k == WC_KEY_EMPTY || k == key) break;
+          h = (h + 1) & (KTAB - 1);
         }
+        hpos[u]          = (int)h;
+        const unsigned sh = (h & 1u) * 16u;
+        rank[u]          = (int)((atomicAdd(&cnt2[h >> 1], 1u << sh) >> sh) & 0xffffu);
       }
-      rec[l] = r;
-      // invalid points sort to the end; equal keys share the hash, so they end up adjacent (a hash collision between
-      // different keys only splits a run, which is still exact because runs are delimited by the full key)
-      sw[l] = r.key == WC_KEY_EMPTY ? (0xffffffff00000000ull | (unsigned)l) : (((mix64(r.key) >> 32) << 32) | (unsigned)l);
     }
-    __syncthreads();
-    // ---- bitonic sort of the 2048 words
-    for (int k = 2; k <= KT; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
+  }
+  __syncthreads();
+  // ---- exclusive scan of the per-position counts (8 positions per thread) -> offsets and the compact run list
+  {
+    unsigned c[8];
+    int      tot = 0, nz = 0;
 #pragma unroll
-        for (int u = 0; u < KT / 2 / KNT; ++u) {
-          const int q = t + KNT * u;
-          const int i = 2 * q - (q & (j - 1)), ixj = i + j;
-          const unsigned long long a = sw[i], b = sw[ixj];
-          if ((a > b) == ((i & k) == 0)) sw[i] = b, sw[ixj] = a;
-        }
-        __syncthreads();
-      }
-    // ---- run heads -> compact list of run start positions (block-wide exclusive scan of the head flags)
-    int           nh = 0;
-    unsigned char hd[KPT];
-#pragma unroll
-    for (int u = 0; u < KPT; ++u) {
-      const int                p  = t * KPT + u;
-      const unsigned long long kp = rec[sw[p] & 0xffffu].key;
-      const bool               h  = kp != WC_KEY_EMPTY && (p == 0 || rec[sw[p - 1] & 0xffffu].key != kp);
-      hd[u]                       = h;
-      nh += h;
+    for (int k = 0; k < 4; ++k) {
+      const unsigned w = cnt2[4 * t + k];
+      c[2 * k] = w & 0xffffu, c[2 * k + 1] = w >> 16;
+      tot += (int)(c[2 * k] + c[2 * k + 1]);
+      nz += (c[2 * k] != 0) + (c[2 * k + 1] != 0);
     }
-    int incl = nh;
+    const int mine = (tot << 16) | nz;  // both prefix sums stay below 2^12
+    int       incl = mine;
     for (int d = 1; d < 32; d <<= 1) {
       const int o = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += o;
@@ -194,73 +166,118 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     if (t < 32) {
-      int w = t < KNT / 32 ? wsum[t] : 0, wi = w;
+      const int w  = t < KNT / 32 ? wsum[t] : 0;
+      int       wi = w;
       for (int d = 1; d < 32; d <<= 1) {
         const int o = __shfl_up_sync(0xffffffffu, wi, d);
         if (t >= d) wi += o;
       }
       if (t < KNT / 32) wsum[t] = wi - w;
       if (t == KNT / 32 - 1) {
-        s_nruns = wi;
-        s_base  = atomicAdd(&st->n_slots, wi);  // reserve one slot id per run of this tile
+        s_nruns = wi & 0xffff;
+        s_base  = atomicAdd(&st->n_slots, wi & 0xffff);  // reserve one slot id per run of this tile
       }
     }
     __syncthreads();
-    int pos = wsum[warp] + incl - nh;
+    const int ex = wsum[warp] + incl - mine;
+    int       o = ex >> 16, r = ex & 0xffff;
 #pragma unroll
-    for (int u = 0; u < KPT; ++u)
-      if (hd[u]) rs[pos++] = (unsigned short)(t * KPT + u);
-    __syncthreads();
-    // ---- one thread per run: sum it, then one slot lookup and 13 REDs
-    const int nruns = s_nruns;
-    for (int r = t; r < nruns; r += KNT) {
-      int                      p   = rs[r];
-      const PtRec              f0  = rec[sw[p] & 0xffffu];
-      const unsigned long long key = f0.key;
-      long long a_n = 0, a_t = 0, a_x = 0, a_y = 0, a_z = 0, a_xx = 0, a_xy = 0, a_xz = 0, a_yy = 0, a_yz = 0, a_zz = 0;
-      unsigned long long a_tmin = 0, a_tmax = 0;
-      for (; p < KT; ++p) {
-        const PtRec e = rec[sw[p] & 0xffffu];
-        if (e.key != key) break;
-        a_n += 1, a_t += e.qrel, a_x += e.xi, a_y += e.yi, a_z += e.zi;
-        a_xx += (long long)e.xi * e.xi, a_xy += (long long)e.xi * e.yi, a_xz += (long long)e.xi * e.zi;
-        a_yy += (long long)e.yi * e.yi, a_yz += (long long)e.yi * e.zi, a_zz += (long long)e.zi * e.zi;
-        a_tmin = max(a_tmin, ~e.tob), a_tmax = max(a_tmax, e.tob);
-      }
-      const int s = cell_slot(keys, hslot, capmask, key, slots, s_base + r, slot_cap, st);
-      if (s >= 0) {
-        wc_slot* sl = slots + s;
-        atomicAdd((unsigned long long*)&sl->n, (unsigned long long)a_n);
-        atomicAdd((unsigned long long*)&sl->st, (unsigned long long)a_t);
-        atomicAdd((unsigned long long*)&sl->s[0], (unsigned long long)a_x);
-        atomicAdd((unsigned long long*)&sl->s[1], (unsigned long long)a_y);
-        atomicAdd((unsigned long long*)&sl->s[2], (unsigned long long)a_z);
-        atomicAdd((unsigned long long*)&sl->ss[0], (unsigned long long)a_xx);
-        atomicAdd((unsigned long long*)&sl->ss[1], (unsigned long long)a_xy);
-        atomicAdd((unsigned long long*)&sl->ss[2], (unsigned long long)a_xz);
-        atomicAdd((unsigned long long*)&sl->ss[3], (unsigned long long)a_yy);
-        atomicAdd((unsigned long long*)&sl->ss[4], (unsigned long long)a_yz);
-        atomicAdd((unsigned long long*)&sl->ss[5], (unsigned long long)a_zz);
-        atomicMax(&sl->tmin_inv, a_tmin);
-        atomicMax(&sl->tmax, a_tmax);
-      }
+    for (int k = 0; k < 8; ++k) {
+      off[8 * t + k] = (unsigned short)o;
+      if (c[k]) runh[r++] = (unsigned short)(8 * t + k);
+      o += (int)c[k];
     }
-    __syncthreads();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < KPT; ++u)
+    if (hpos[u] >= 0) perm[off[hpos[u]] + rank[u]] = (unsigned short)(t + KNT * u);
+  __syncthreads();
+  // ---- one thread per run: sum it, then merge it into the global cell table
+  const int nruns = s_nruns;
+  for (int r = t; r < nruns; r += KNT) {
+    const int                h   = runh[r];
+    const unsigned long long key = skey[h];
+    const int                p0  = off[h];
+    const int                np  = (int)((cnt2[h >> 1] >> ((h & 1) * 16)) & 0xffffu);
+    long long a_t = 0, a_x = 0, a_y = 0, a_z = 0, a_xx = 0, a_xy = 0, a_xz = 0, a_yy = 0, a_yz = 0, a_zz = 0;
+    int       lmin = KT, lmax = -1;
+    for (int j = 0; j < np; ++j) {
+      const int  l = perm[p0 + j];
+      const int4 e = pay[l];
+      lmin = min(lmin, l), lmax = max(lmax, l);
+      a_t += e.w, a_x += e.x, a_y += e.y, a_z += e.z;
+      a_xx += (long long)e.x * e.x, a_xy += (long long)e.x * e.y, a_xz += (long long)e.x * e.z;
+      a_yy += (long long)e.y * e.y, a_yz += (long long)e.y * e.z, a_zz += (long long)e.z * e.z;
+    }
+    // timestamps are non-decreasing in the point index (checked above), so the run's extrema sit at its end points
+    const unsigned long long tmin_inv = ~OrderedBits(time[base + lmin]), tmax = OrderedBits(time[base + lmax]);
+    const int                fresh    = s_base + r;
+    if (fresh >= slot_cap) {
+      st->err_capacity = 1;
+      continue;
+    }
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(slots + fresh);
+    d[0] = make_ulonglong2(key, (unsigned long long)np);
+    d[1] = make_ulonglong2((unsigned long long)a_t, (unsigned long long)a_x);
+    d[2] = make_ulonglong2((unsigned long long)a_y, (unsigned long long)a_z);
+    d[3] = make_ulonglong2((unsigned long long)a_xx, (unsigned long long)a_xy);
+    d[4] = make_ulonglong2((unsigned long long)a_xz, (unsigned long long)a_yy);
+    d[5] = make_ulonglong2((unsigned long long)a_yz, (unsigned long long)a_zz);
+    d[6] = make_ulonglong2(tmin_inv, tmax);
+    d[7] = make_ulonglong2(0ull, 0ull);  // table_pos / vid
   }
 }
 
 // ---------------------------------------------------------------------------------------------- K2a-c
-__global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __restrict__ st,
-                            unsigned long long* __restrict__ vkeys, int* __restrict__ vslot, unsigned long long vmask,
-                            int* __restrict__ vox_count, unsigned long long* __restrict__ vox_key,
+// One thread per run record.  (1) Merge records of the same (voxel, leaf cell, time bin) through the global cell table:
+// the first record to claim the key becomes the cell's slot, later ones add their exact integer moments to it with
+// native 64-bit RED atomics and retire (n = 0).  The records were completed by the previous kernel, so no fences are
+// needed — the only dependent chain is one CAS.  (2) Surviving slots register with their voxel (voxel table -> dense
+// voxel id, per-voxel slot count).
+__global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __restrict__ st, HEnt* __restrict__ tab,
+                            unsigned long long capmask, unsigned long long* __restrict__ vkeys, int* __restrict__ vslot,
+                            unsigned long long vmask, int* __restrict__ vox_count, unsigned long long* __restrict__ vox_key,
                             int* __restrict__ vox_hpos, int vox_cap) {
   const int ns = min(st->n_slots, INT_MAX);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
-    if (slots[s].n == 0) {  // reserved but never used (its run found an existing cell)
-      slots[s].vid = -1;
+    const unsigned long long ckey = slots[s].key;
+    int                      owner = -2;
+    {
+      unsigned long long h = mix64(ckey) & capmask;
+      for (unsigned long long probe = 0; probe <= capmask; ++probe, h = (h + 1) & capmask) {
+        const unsigned long long k = atomicCAS(&tab[h].key, WC_KEY_EMPTY, ckey);
+        if (k == WC_KEY_EMPTY) {
+          *((volatile int*)&tab[h].slot) = s;
+          owner                          = s;
+          break;
+        }
+        if (k == ckey) {
+          while ((owner = *((volatile int*)&tab[h].slot)) == -1) {
+          }
+          break;
+        }
+      }
+    }
+    if (owner != s) {
+      if (owner < 0) {
+        st->err_capacity = 1;
+      } else {
+        wc_slot*       sl = slots + owner;
+        const wc_slot* me = slots + s;
+        atomicAdd((unsigned long long*)&sl->n, (unsigned long long)me->n);
+        atomicAdd((unsigned long long*)&sl->st, (unsigned long long)me->st);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd((unsigned long long*)&sl->s[k], (unsigned long long)me->s[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd((unsigned long long*)&sl->ss[k], (unsigned long long)me->ss[k]);
+        atomicMax(&sl->tmin_inv, me->tmin_inv);
+        atomicMax(&sl->tmax, me->tmax);
+      }
+      slots[s].vid = -1;  // retired: voxel_scatter skips it
       continue;
     }
-    const unsigned long long key = slots[s].key >> 18;
+    const unsigned long long key = ckey >> 18;
     unsigned long long       h   = mix64(key) & vmask;
     int                      vid = -2;
     for (unsigned long long probe = 0; probe <= vmask; ++probe, h = (h + 1) & vmask) {
@@ -276,7 +293,7 @@ __global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __re
             vox_key[vid]  = key;
             vox_hpos[vid] = (int)h;  // remember the table position for cleanup
           }
-            atomicExch(&vslot[h], vid);
+          atomicExch(&vslot[h], vid);
           break;
         }
       }
@@ -717,32 +734,19 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
   }
 }
 
-// leave the tables and slots clean for the next call (only the touched entries are reset)
-__global__ void extract_cleanup(wc_slot* __restrict__ slots, const wc_extract_status* __restrict__ st,
-                                unsigned long long* __restrict__ keys, int* __restrict__ hslot,
-                                unsigned long long* __restrict__ vkeys, int* __restrict__ vslot,
-                                const int* __restrict__ vox_hpos, int* __restrict__ vox_count,
+// leave the voxel table and counters clean for the next call (only the touched entries are reset; the cell table is
+// re-initialised by one memset per call and the slot records are fully rewritten by their creators)
+__global__ void extract_cleanup(const wc_extract_status* __restrict__ st, unsigned long long* __restrict__ vkeys,
+                                int* __restrict__ vslot, const int* __restrict__ vox_hpos, int* __restrict__ vox_count,
                                 int* __restrict__ vox_cursor) {
-  const int ns = st->n_slots, nv = st->n_voxels;
+  const int nv  = st->n_voxels;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (int s = tid; s < ns; s += nth) {
-    if (slots[s].n == 0) {
-      slots[s].vid = 0;
-      continue;
-    }
-    const int h = slots[s].table_pos;
-    keys[h]     = WC_KEY_EMPTY;
-    hslot[h]    = -1;
-    uint4* z    = reinterpret_cast<uint4*>(slots + s);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) z[k] = make_uint4(0, 0, 0, 0);
-  }
   for (int v = tid; v < nv; v += nth) {
-    const int h = vox_hpos[v];
-    vkeys[h]    = WC_KEY_EMPTY;
-    vslot[h]                   = -1;
-    vox_count[v]               = 0;
-    vox_cursor[v]              = 0;
+    const int h   = vox_hpos[v];
+    vkeys[h]      = WC_KEY_EMPTY;
+    vslot[h]      = -1;
+    vox_count[v]  = 0;
+    vox_cursor[v] = 0;
   }
 }
 
@@ -820,14 +824,13 @@ __global__ void gather_surfels(const wc_surfel* __restrict__ in, const unsigned*
 static wc_status extract_alloc(wc_ctx* c) {
   if (c->d_xyz) return WC_OK;
   const size_t np = (size_t)c->prm.max_points;
-  c->hcap         = wc_next_pow2(2 * np);
+  c->hcap         = wc_next_pow2(np < 1024 ? 1024 : np);
   c->slot_cap     = np;
   c->vcap         = wc_next_pow2(2 * np);
   WC_CUDA(c, cudaMalloc(&c->d_raw, np * sizeof(wc_point48)));
   WC_CUDA(c, cudaMalloc(&c->d_xyz, np * sizeof(float4)));
   WC_CUDA(c, cudaMalloc(&c->d_time, np * sizeof(double)));
-  WC_CUDA(c, cudaMalloc(&c->d_hkeys, c->hcap * 8));
-  WC_CUDA(c, cudaMalloc(&c->d_hslot, c->hcap * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_htab, c->hcap * sizeof(HEnt)));
   WC_CUDA(c, cudaMalloc(&c->d_slots, c->slot_cap * sizeof(wc_slot)));
   WC_CUDA(c, cudaMalloc(&c->d_vkeys, c->vcap * 8));
   WC_CUDA(c, cudaMalloc(&c->d_vslot, c->vcap * 4));
@@ -846,11 +849,8 @@ static wc_status extract_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&c->d_sort_lo, sc * 8));
   WC_CUDA(c, cudaMalloc(&c->d_sort_idx, sc * 4));
   WC_CUDA(c, cudaMalloc(&c->d_assign, np * sizeof(wc_point_assign)));
-  WC_CUDA(c, cudaMemsetAsync(c->d_hkeys, 0xff, c->hcap * 8, c->stream));
-  WC_CUDA(c, cudaMemsetAsync(c->d_hslot, 0xff, c->hcap * 4, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vkeys, 0xff, c->vcap * 8, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vslot, 0xff, c->vcap * 4, c->stream));
-  WC_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->slot_cap * sizeof(wc_slot), c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_count, 0, (np + 1) * 4, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_cursor, 0, (np + 1) * 4, c->stream));
   WC_CUDA(c, cudaFuncSetAttribute(voxel_key_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
@@ -860,7 +860,7 @@ static wc_status extract_alloc(wc_ctx* c) {
 }
 
 void wc_extract_free(wc_ctx* c) {
-  void* ptrs[] = {c->d_raw,     c->d_xyz,      c->d_time,    c->d_hkeys,   c->d_hslot,   c->d_slots,    c->d_vkeys,
+  void* ptrs[] = {c->d_raw,     c->d_xyz,      c->d_time,    c->d_htab,   c->d_slots,    c->d_vkeys,
                   c->d_vslot,   c->d_vox_count, c->d_vox_off, c->d_vox_cursor, c->d_vox_key, c->d_vox_hpos, c->d_seg,   c->d_xstat,
                   c->d_surf_raw, c->d_surf,    c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, c->d_assign};
   for (void* p : ptrs)
@@ -906,12 +906,15 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
 
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
   WC_CUDA(c, cudaMemsetAsync(c->d_xstat, 0, sizeof(wc_extract_status), st));
+  // cell table sized to this sweep (worst case one cell per point still fits; typical load is ~0.2)
+  const size_t hcap = wc_next_pow2(n < 1024 ? 1024 : (size_t)n);
+  WC_CUDA(c, cudaMemsetAsync(c->d_htab, 0xff, hcap * sizeof(HEnt), st));
+  WC_CUDA(c, cudaEventRecord(c->ev[4], st));
   const int ntiles = (n + KT - 1) / KT;
-  const int grid1  = ntiles < c->num_sms * 2 ? ntiles : c->num_sms * 2;
-  { ++c->n_launches; voxel_key_moments<<<grid1, KNT, K1_SMEM, st>>>(c->d_xyz, c->d_time, P, c->d_hkeys, c->d_hslot, c->hcap - 1, c->d_slots,
-                                           (int)c->slot_cap, c->d_xstat, c->want_assign ? c->d_assign : nullptr); }
+  { ++c->n_launches; voxel_key_moments<<<ntiles, KNT, K1_SMEM, st>>>(c->d_xyz, c->d_time, P, c->d_slots, (int)c->slot_cap, c->d_xstat,
+                                           c->want_assign ? c->d_assign : nullptr); }
   WC_CUDA(c, cudaEventRecord(c->ev[1], st));
-  { ++c->n_launches; voxel_index<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
+  { ++c->n_launches; voxel_index<<<c->num_sms * 8, 256, 0, st>>>(c->d_slots, c->d_xstat, (HEnt*)c->d_htab, hcap - 1, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
                                               c->d_vox_key, c->d_vox_hpos, (int)c->prm.max_points); }
   { ++c->n_launches; voxel_scan<<<1, 1024, 0, st>>>(c->d_vox_count, c->d_vox_off, c->d_xstat); }
   { ++c->n_launches; voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vox_off, c->d_vox_cursor, c->d_seg); }
@@ -929,8 +932,8 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 512,
                                                                          c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
   WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
-  { ++c->n_launches; extract_cleanup<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_hkeys, c->d_hslot, c->d_vkeys, c->d_vslot,
-                                                  c->d_vox_hpos, c->d_vox_count, c->d_vox_cursor); }
+  { ++c->n_launches; extract_cleanup<<<c->num_sms, 256, 0, st>>>(c->d_xstat, c->d_vkeys, c->d_vslot, c->d_vox_hpos, c->d_vox_count,
+                                              c->d_vox_cursor); }
   WC_CUDA(c, cudaEventRecord(c->ev[2], st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   const wc_extract_status hs = *c->h_xstat;
@@ -956,7 +959,7 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
   float ms;
-  if (gpu_ms_keys) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); *gpu_ms_keys = ms; }
+  if (gpu_ms_keys) { cudaEventElapsedTime(&ms, c->ev[4], c->ev[1]); *gpu_ms_keys = ms; }
   if (gpu_ms_emit) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[3]); *gpu_ms_emit = ms; }
   if (gpu_ms_total) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); *gpu_ms_total = ms; }
   if (n_out) *n_out = (size_t)S;
