@@ -680,24 +680,28 @@ __device__ void lm_decide_dev(const SolveBufs& B, const wc_solve_opts& o, double
 }
 
 // ---- blocked right-looking Cholesky with the right-hand side carried as an extra row, with look-ahead.
-// A holds D+1 rows of D doubles (row-major, lower triangle): rows 0..D-1 the SPD matrix, row D the right-hand side g^T.
-// After the call rows 0..D-1 hold L and row D holds z = L^-1 g (the forward substitution happens inside the
-// factorisation).  Linv receives the inverses of the CB x CB diagonal blocks for the backward substitution.
-// Per block column k: (b) panel rows = A_panel * Lkk^-T (one thread per row); (c1) trailing update of block column
-// k+1 only; then warp 0 factorises + inverts diagonal block k+1 in registers (shuffles, reciprocal square roots, no
-// divisions on the pivot chain) WHILE the other warps finish the trailing update (c2) — the serial pivot chain is
-// hidden behind the bulk update.
-__device__ __forceinline__ void chol_diag_block(double* A, int D, int k0, int kb, double* Li, int* s_fail) {
+// Layout: Dp = D rounded up to the block width CB (padding rows/columns are identity), leading dimension LD even with
+// LD/2 odd (16-byte row segments of consecutive rows fall into distinct bank groups), Dp + 4 rows: rows 0..Dp-1 the SPD
+// matrix (lower triangle), row Dp the right-hand side g^T, rows Dp+1..Dp+3 zero (so every row tile of 4 is full).
+// After the call rows 0..Dp-1 hold L and row Dp holds z = L^-1 g (the forward substitution rides along).
+// Per block column k the critical path is  panel(k) -> update of block column k+1 -> factor(k+1):
+//   S1 panel rows = A_panel * Lkk^-T by forward substitution, one thread per row (no explicit inverse);
+//   S2 the next block column only (all threads, 1 x 4 strips);
+//   S3 warp 0 factorises diagonal block k+1 in registers (shuffles, reciprocal square roots, no divisions on the pivot
+//      chain) WHILE warps 1..15 finish the trailing update in 4 x 4 register tiles fed by 16-byte shared loads.
+__device__ __forceinline__ int chol_ld(int Dp) { return ((Dp >> 1) & 1) ? Dp : Dp + 2; }
+
+__device__ __forceinline__ void chol_factor_diag(double* A, int LD, int k0, double* rinv_out, int* s_fail) {
   const int lane = threadIdx.x & 31;
   double    a[CB];
 #pragma unroll
-  for (int c = 0; c < CB; ++c) a[c] = (lane < kb && c <= lane && c < kb) ? A[(k0 + lane) * D + k0 + c] : (c == lane ? 1.0 : 0.0);
+  for (int c = 0; c < CB; ++c) a[c] = (lane < CB && c <= lane) ? A[(k0 + lane) * LD + k0 + c] : (c == lane ? 1.0 : 0.0);
   bool   bad  = false;
   double rinv = 1.0;  // 1 / L[lane][lane]
 #pragma unroll
   for (int j = 0; j < CB; ++j) {
     const double djj = __shfl_sync(0xffffffffu, a[j], j);
-    if (j < kb && (!(djj > 0.0) || !isfinite(djj))) bad = true;
+    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
     const double rs = rsqrt(djj);
     if (lane == j) rinv = rs;
     if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
@@ -708,107 +712,146 @@ __device__ __forceinline__ void chol_diag_block(double* A, int D, int k0, int kb
     }
   }
   if (bad && lane == 0) *s_fail = 1;
-  if (lane < kb)
+  if (lane < CB) {
 #pragma unroll
     for (int c = 0; c < CB; ++c)
-      if (c <= lane) A[(k0 + lane) * D + k0 + c] = a[c];
-  double x[CB];  // lane c solves L x = e_c (rows beyond kb are identity)
-#pragma unroll
-  for (int r = 0; r < CB; ++r) {
-    double v = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int c = 0; c < CB; ++c)
-      if (c < r) v -= __shfl_sync(0xffffffffu, a[c], r) * x[c];
-    x[r] = v * __shfl_sync(0xffffffffu, rinv, r);
+      if (c <= lane) A[(k0 + lane) * LD + k0 + c] = a[c];
+    rinv_out[lane] = rinv;
   }
-  if (lane < CB)
-#pragma unroll
-    for (int r = 0; r < CB; ++r) Li[r * CB + lane] = x[r];  // Linv[r][c], zero above the diagonal
 }
 
-// trailing update A[i][j] -= sum_b L[i][k0+b] L[j][k0+b] for rows i in [r0, D] (row D = rhs) and columns j in
-// [j0, min(j1, i)] — rows dealt to `nw` warps starting at warp `w0`, lanes over the columns
-__device__ __forceinline__ void chol_trailing(double* A, int D, int k0, int kb, int r0, int j0, int j1, int w0, int nw) {
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) - w0;
-  if (warp < 0) return;
-  for (int i = r0 + warp; i <= D; i += nw) {
-    double li[CB];
+// load 8 consecutive doubles (16-byte aligned) as four 128-bit accesses
+__device__ __forceinline__ void ld8(const double* p, double* v) {
+  const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
-    for (int b = 0; b < CB; ++b) li[b] = b < kb ? A[i * D + k0 + b] : 0.0;
-    const int jend = min(j1, i < D ? i : D - 1);
-    for (int j = j0 + lane; j <= jend; j += 32) {
-      double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    const double2 d = q[k];
+    v[2 * k] = d.x, v[2 * k + 1] = d.y;
+  }
+}
+
+// S1: rows i in [k0 + CB, Dp]: L[i][k0..k0+CB) = A[i][k0..k0+CB) * Lkk^-T
+__device__ __forceinline__ void chol_panel(double* A, int LD, int Dp, int k0, const double* rinv) {
+  const int i = k0 + CB + (int)threadIdx.x;
+  if (i > Dp) return;
+  double ai[CB], li[CB];
+  ld8(A + i * LD + k0, ai);
 #pragma unroll
-      for (int b = 0; b < CB; b += 2) {
-        if (b < kb) s0 = fma(li[b], A[j * D + k0 + b], s0);
-        if (b + 1 < kb) s1 = fma(li[b + 1], A[j * D + k0 + b + 1], s1);
+  for (int b = 0; b < CB; ++b) {
+    double v = ai[b];
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c < b) v = fma(-li[c], A[(k0 + b) * LD + k0 + c], v);
+    li[b] = v * rinv[b];
+  }
+  double2* q = reinterpret_cast<double2*>(A + i * LD + k0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = make_double2(li[2 * k], li[2 * k + 1]);
+}
+
+// S2: block column [r0, r0 + CB) for rows i in [r0, Dp]: one (row, 4-column strip) per thread
+__device__ __forceinline__ void chol_update_next_col(double* A, int LD, int Dp, int k0, int r0) {
+  const int item = threadIdx.x, i = r0 + (item >> 1), j0 = r0 + 4 * (item & 1);
+  if (i > Dp) return;
+  double li[CB], lj[CB];
+  ld8(A + i * LD + k0, li);
+  double2* out = reinterpret_cast<double2*>(A + i * LD + j0);
+  double2  o0 = out[0], o1 = out[1];
+  double   s[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ld8(A + (j0 + c) * LD + k0, lj);
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int b = 0; b < CB; b += 2) s0 = fma(li[b], lj[b], s0), s1 = fma(li[b + 1], lj[b + 1], s1);
+    s[c] = s0 + s1;
+  }
+  o0.x -= s[0], o0.y -= s[1], o1.x -= s[2], o1.y -= s[3];
+  out[0] = o0, out[1] = o1;  // entries above the diagonal of the next diagonal block are never read
+}
+
+// S3 (warps w0..): rows [r1, Dp + 4), columns [r1, min(row, Dp - 1)] in 4 x 4 tiles
+__device__ __forceinline__ void chol_trailing_tiles(double* A, int LD, int Dp, int k0, int r1, int tid, int nth) {
+  const int m     = (Dp - r1) >> 2;           // regular row tiles; tile row m is the right-hand-side tile row
+  const int ntri  = m * (m + 1) / 2, ntile = ntri + m;
+  for (int q = tid; q < ntile; q += nth) {
+    int ti, tj;
+    if (q < ntri) {
+      ti = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
+      while (ti * (ti + 1) / 2 > q) --ti;
+      while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+      tj = q - ti * (ti + 1) / 2;
+    } else {
+      ti = m, tj = q - ntri;
+    }
+    const int i0 = r1 + 4 * ti, j0 = r1 + 4 * tj;
+    double    lj[4][CB], li[CB];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ld8(A + (j0 + c) * LD + k0, lj[c]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      ld8(A + (i0 + r) * LD + k0, li);
+      double2* out = reinterpret_cast<double2*>(A + (i0 + r) * LD + j0);
+      double2  o0 = out[0], o1 = out[1];
+      double   s[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < CB; b += 2) s0 = fma(li[b], lj[c][b], s0), s1 = fma(li[b + 1], lj[c][b + 1], s1);
+        s[c] = s0 + s1;
       }
-      A[i * D + j] -= s0 + s1;
+      o0.x -= s[0], o0.y -= s[1], o1.x -= s[2], o1.y -= s[3];
+      out[0] = o0, out[1] = o1;
     }
   }
 }
 
-__device__ void cholesky_blocked_rhs(double* A, int D, double* Linv, int* s_fail) {
-  const int t = threadIdx.x, warp = t >> 5;
-  if (warp == 0) chol_diag_block(A, D, 0, min(CB, D), Linv, s_fail);
+__device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fail) {
+  const int t = threadIdx.x, warp = t >> 5, LD = chol_ld(Dp);
+  if (warp == 0) chol_factor_diag(A, LD, 0, rinv, s_fail);
   __syncthreads();
-  for (int k0 = 0, blk = 0; k0 < D; k0 += CB, ++blk) {
+  for (int k0 = 0; k0 < Dp; k0 += CB) {
     if (*s_fail) return;  // uniform (written before the last barrier)
-    const int     kb = min(CB, D - k0);
-    const double* Li = Linv + blk * CB * CB;
-    // (b) panel rows k0+kb .. D: L[i][b] = sum_{c<=b} A[i][k0+c] * Linv[b][c]
-    for (int i = k0 + kb + t; i <= D; i += LMT) {
-      double ai[CB], li[CB];
-#pragma unroll
-      for (int c = 0; c < CB; ++c) ai[c] = c < kb ? A[i * D + k0 + c] : 0.0;
-#pragma unroll
-      for (int b = 0; b < CB; ++b) {
-        double v = 0.0;
-#pragma unroll
-        for (int c = 0; c < CB; ++c)
-          if (c <= b) v = fma(ai[c], Li[b * CB + c], v);
-        li[b] = v;
-      }
-#pragma unroll
-      for (int b = 0; b < CB; ++b)
-        if (b < kb) A[i * D + k0 + b] = li[b];
-    }
+    chol_panel(A, LD, Dp, k0, rinv + k0);
     __syncthreads();
-    const int r0 = k0 + kb;
-    if (r0 >= D) {  // last block column: only the right-hand-side row remains, nothing to update
-      break;
-    }
-    // (c1) block column k+1 first (all warps), so that its diagonal block can be factorised ahead
-    chol_trailing(A, D, k0, kb, r0, r0, r0 + CB - 1, 0, LMT / 32);
+    const int r0 = k0 + CB;
+    if (r0 >= Dp) break;  // last block column: only the right-hand-side row remained
+    chol_update_next_col(A, LD, Dp, k0, r0);
     __syncthreads();
-    // (a) next diagonal block by warp 0  ||  (c2) rest of the trailing update by warps 1..15
-    if (warp == 0) chol_diag_block(A, D, r0, min(CB, D - r0), Linv + (blk + 1) * CB * CB, s_fail);
-    else chol_trailing(A, D, k0, kb, r0 + CB, r0 + CB, D - 1, 1, LMT / 32 - 1);
+    if (warp == 0) chol_factor_diag(A, LD, r0, rinv + r0, s_fail);
+    else chol_trailing_tiles(A, LD, Dp, k0, r0 + CB, t - 32, LMT - 32);
     __syncthreads();
   }
 }
 
-// backward substitution L^T x = z by blocks; z = row D of A; result x (length D) is written negated into y
-__device__ void chol_backward_blocked(const double* A, int D, const double* Linv, double* zrow, double* y, double* xblk) {
-  const int t    = threadIdx.x;
-  const int nblk = (D + CB - 1) / CB;
-  for (int blk = nblk - 1; blk >= 0; --blk) {
-    const int     k0 = blk * CB, kb = min(CB, D - k0);
-    const double* Li = Linv + blk * CB * CB;
-    if (t < kb) {  // x_blk = Linv^T z_blk
-      double v = 0.0;
+// backward substitution L^T x = z by blocks; z = row Dp of A; result x is written negated into y (length D)
+__device__ void chol_backward_blocked(const double* A, int D, int Dp, const double* rinv, double* zrow, double* y, double* xblk) {
+  const int t = threadIdx.x, LD = chol_ld(Dp);
+  for (int k0 = Dp - CB; k0 >= 0; k0 -= CB) {
+    if (t < 32) {  // 8 x 8 transposed triangular solve by lanes 0..7 of warp 0
+      const int lane = t;
+      double    v    = lane < CB ? zrow[k0 + lane] : 0.0;
+      double    lcol[CB];  // lcol[r] = L[k0 + r][k0 + lane]
 #pragma unroll
-      for (int r = 0; r < CB; ++r)
-        if (r >= t && r < kb) v = fma(Li[r * CB + t], zrow[k0 + r], v);
-      xblk[t]   = v;
-      y[k0 + t] = -v;
+      for (int r = 0; r < CB; ++r) lcol[r] = (lane < CB && r > lane) ? A[(k0 + r) * LD + k0 + lane] : 0.0;
+      const double ri = lane < CB ? rinv[k0 + lane] : 0.0;
+#pragma unroll
+      for (int r = CB - 1; r >= 0; --r) {
+        if (lane == r) v *= ri;
+        const double xr = __shfl_sync(0xffffffffu, v, r);
+        if (lane < r) v = fma(-lcol[r], xr, v);
+      }
+      if (lane < CB) {
+        xblk[lane] = v;
+        if (k0 + lane < D) y[k0 + lane] = -v;
+      }
     }
     __syncthreads();
     for (int i = t; i < k0; i += LMT) {
       double v = zrow[i];
 #pragma unroll
-      for (int b = 0; b < CB; ++b)
-        if (b < kb) v = fma(-A[(k0 + b) * D + i], xblk[b], v);
+      for (int b = 0; b < CB; ++b) v = fma(-A[(k0 + b) * LD + i], xblk[b], v);
       zrow[i] = v;
     }
     __syncthreads();
@@ -856,8 +899,9 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   if (s_done) return;
   const double* H = B.H[st->cur];
   const double* g = B.g[st->cur];
-  double*       A    = a_in_smem ? sA : B.A;                      // (D + 1) x D
-  double*       Linv = (a_in_smem ? sA : B.A) + (size_t)(D + 1) * D;  // diagonal-block inverses
+  const int     Dp = (D + CB - 1) / CB * CB, LD = chol_ld(Dp);
+  double*       A    = a_in_smem ? sA : B.A;            // (Dp + 4) x LD
+  double*       rinv = A + (size_t)(Dp + 4) * LD;       // reciprocal pivots
   const double  radius = st->radius;
   if (!st->reuse_diagonal)
     for (int c = t; c < D; c += LMT) {
@@ -866,32 +910,39 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
       B.diag[c]      = fmin(fmax(d, o.min_lm_diagonal), o.max_lm_diagonal);
     }
   __syncthreads();
-  // A = S H S + diag / radius (the factorisation reads the lower triangle); flat loop: ~40 independent loads per thread
-  for (int e = t; e < D * D; e += LMT) {
-    const int r = e / D, c = e - r * D;
-    if (c > r) continue;
-    double v = H[(size_t)amb_of(r, ff) * N + amb_of(c, ff)] * B.scale[r] * B.scale[c];
-    if (r == c) {
-      const double sq = sqrt(B.diag[r] / radius);
-      v += sq * sq;
+  // A = S H S + diag / radius, lower triangle only: one warp per row, lanes over the columns (coalesced rows of H);
+  // padding rows are identity, row Dp is the right-hand side g_s = S g, rows Dp+1..Dp+3 are zero
+  for (int r = t >> 5; r < Dp + 4; r += LMT / 32) {
+    double* Ar = A + (size_t)r * LD;
+    if (r < D) {
+      const double  sr = B.scale[r];
+      const double* Hr = H + (size_t)amb_of(r, ff) * N;
+      for (int c = t & 31; c <= r; c += 32) {
+        double v = Hr[amb_of(c, ff)] * sr * B.scale[c];
+        if (r == c) {
+          const double sq = sqrt(B.diag[r] / radius);
+          v += sq * sq;
+        }
+        Ar[c] = v;
+      }
+    } else if (r < Dp) {
+      for (int c = t & 31; c <= r; c += 32) Ar[c] = c == r ? 1.0 : 0.0;
+    } else {
+      for (int c = t & 31; c < Dp; c += 32) Ar[c] = (r == Dp && c < D) ? g[amb_of(c, ff)] * B.scale[c] : 0.0;
     }
-    A[e] = v;
   }
-  __syncthreads();
-  // right-hand side g_s = S g as row D
-  for (int c = t; c < D; c += LMT) A[D * D + c] = g[amb_of(c, ff)] * B.scale[c];
   __syncthreads();
 #ifdef WC_LM_TIMING
   tk[2] = clock64();
 #endif
-  cholesky_blocked_rhs(A, D, Linv, &s_fail);
+  cholesky_blocked_rhs(A, Dp, rinv, &s_fail);
   __syncthreads();
 #ifdef WC_LM_TIMING
   tk[3] = clock64();
 #endif
   bool    valid = !s_fail;
   double* y     = B.step;
-  if (valid) chol_backward_blocked(A, D, Linv, A + D * D, y, xblk);  // y = -(S H S + diag/radius)^-1 g_s
+  if (valid) chol_backward_blocked(A, D, Dp, rinv, A + (size_t)Dp * LD, y, xblk);  // y = -(S H S + diag/radius)^-1 g_s
   __syncthreads();
 #ifdef WC_LM_TIMING
   tk[4] = clock64();
@@ -1008,7 +1059,7 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->scale, N * 8));
   WC_CUDA(c, cudaMalloc(&m->diag, N * 8));
   WC_CUDA(c, cudaMalloc(&m->step, N * 8));
-  WC_CUDA(c, cudaMalloc(&m->A, ((N + 1) * N + (N / CB + 1) * CB * CB) * 8));
+  WC_CUDA(c, cudaMalloc(&m->A, ((N + 12) * (N + 10) + N + 8) * 8));
   WC_CUDA(c, cudaMalloc(&c->d_x, N * 8));
   WC_CUDA(c, cudaMalloc(&c->d_xc, N * 8));
   WC_CUDA(c, cudaMalloc(&c->d_x0, N * 8));
@@ -1191,7 +1242,8 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   const int     N  = (int)(12 * c->K);
   SolveBufs     B  = make_bufs(c, o.fix_first_position ? 1 : 0);
   const int     D  = o.fix_first_position ? N - 3 : N;
-  const size_t  a_bytes     = ((size_t)(D + 1) * D + (size_t)((D + CB - 1) / CB) * CB * CB) * 8;
+  const int     Dp          = (D + CB - 1) / CB * CB, LD = ((Dp >> 1) & 1) ? Dp : Dp + 2;
+  const size_t  a_bytes     = ((size_t)(Dp + 4) * LD + Dp) * 8;
   const int     a_in_smem   = a_bytes <= 200 * 1024;
   const size_t  smem        = a_in_smem ? a_bytes : 0;
   WC_CUDA(c, cudaEventRecord(c->ev[4], st));
