@@ -14,6 +14,7 @@
 //                       damping, dense Cholesky in shared memory, step, accept/reject, radius update, termination —
 //                       one CTA, state resident on the device
 #include <float.h>
+#include <stdlib.h>
 
 #include "wc_ctx.h"
 #include "wc_device_math.cuh"
@@ -621,8 +622,7 @@ __global__ void __launch_bounds__(LMT) lm_init(SolveBufs B, wc_solve_opts o) {
 }
 
 // ---- decide: after the candidate evaluation — tolerances, accept / reject, trust-region update
-__device__ void lm_decide_dev(const SolveBufs& B, const wc_solve_opts& o, double* red, int* s_accept) {
-  LMState*  st = B.st;
+__device__ void lm_decide_dev(const SolveBufs& B, LMState* st, const wc_solve_opts& o, double* red, int* s_accept) {
   const int t = threadIdx.x, N = B.N, ff = B.fix_first;
   const int it = st->iteration < WC_MAX_ITER_LOG ? st->iteration : WC_MAX_ITER_LOG - 1;
   if (t == 0) {
@@ -688,36 +688,44 @@ __device__ void lm_decide_dev(const SolveBufs& B, const wc_solve_opts& o, double
 //   S1 panel rows = A_panel * Lkk^-T by forward substitution, one thread per row (no explicit inverse);
 //   S2 the next block column only (all threads, 1 x 4 strips);
 //   S3 warp 0 factorises diagonal block k+1 in registers (shuffles, reciprocal square roots, no divisions on the pivot
-//      chain) WHILE warps 1..15 finish the trailing update in 4 x 4 register tiles fed by 16-byte shared loads.
+//      chain) WHILE the warps of the other three schedulers finish the trailing update in 4 x 4 register tiles fed by
+//      16-byte shared loads.
 __device__ __forceinline__ int chol_ld(int Dp) { return ((Dp >> 1) & 1) ? Dp : Dp + 2; }
 
+// Diagonal block factor by one warp: the CB x CB block is spread over the lanes (lane = 8 * (c & 3) + r holds a[r][c]
+// and a[r][c + 4]) and factorised by a ROLLED pivot loop — a few dozen instructions that stay in the L0 instruction
+// cache, instead of a fully unrolled register-array version whose straight-line code is instruction-fetch bound on a
+// single warp.  Per pivot j: broadcast d = a[j][j], rs = rsqrt(d), gather column j for the lane's row and its two
+// columns, then a[r][c] -= (a[r][j] rs)(a[c][j] rs) for r, c > j and a[r][j] *= rs.  Runs while the other warps are
+// idle or in light phases (shuffles share the shared-memory pipe).
 __device__ __forceinline__ void chol_factor_diag(double* A, int LD, int k0, double* rinv_out, int* s_fail) {
-  const int lane = threadIdx.x & 31;
-  double    a[CB];
-#pragma unroll
-  for (int c = 0; c < CB; ++c) a[c] = (lane < CB && c <= lane) ? A[(k0 + lane) * LD + k0 + c] : (c == lane ? 1.0 : 0.0);
-  bool   bad  = false;
-  double rinv = 1.0;  // 1 / L[lane][lane]
-#pragma unroll
+  const int lane = threadIdx.x & 31, r = lane & 7, c0 = lane >> 3;
+  double    e0 = A[(k0 + r) * LD + k0 + c0], e1 = A[(k0 + r) * LD + k0 + c0 + 4];  // upper-triangle values are ignored
+  bool      bad = false;
+#pragma unroll 1
   for (int j = 0; j < CB; ++j) {
-    const double djj = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
-    const double rs = rsqrt(djj);
-    if (lane == j) rinv = rs;
-    if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
-#pragma unroll
-    for (int k = j + 1; k < CB; ++k) {
-      const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-      if (lane >= k) a[k] -= a[j] * lkj;
+    const int    src = (j & 3) * 8;              // lanes holding column j
+    const double colv = j < 4 ? e0 : e1;          // this lane's value IF it holds column j (only read from such lanes)
+    const double d    = __shfl_sync(0xffffffffu, colv, src + j);
+    const double ar   = __shfl_sync(0xffffffffu, colv, src + r);
+    const double ac0  = __shfl_sync(0xffffffffu, colv, src + c0);
+    const double ac1  = __shfl_sync(0xffffffffu, colv, src + c0 + 4);
+    if (!(d > 0.0) || !isfinite(d)) bad = true;
+    const double rs = rsqrt(d);
+    const double lr = ar * rs;
+    if (r > j) {
+      if (c0 > j) e0 = fma(-lr, ac0 * rs, e0);
+      if (c0 + 4 > j) e1 = fma(-lr, ac1 * rs, e1);
     }
+    if (r >= j) {  // column j becomes final: L[r][j] = a[r][j] rs (the diagonal: d rs = sqrt(d))
+      if (c0 == j) e0 = lr;
+      if (c0 + 4 == j) e1 = lr;
+    }
+    if (lane == j) rinv_out[j] = rs;
   }
   if (bad && lane == 0) *s_fail = 1;
-  if (lane < CB) {
-#pragma unroll
-    for (int c = 0; c < CB; ++c)
-      if (c <= lane) A[(k0 + lane) * LD + k0 + c] = a[c];
-    rinv_out[lane] = rinv;
-  }
+  if (c0 <= r) A[(k0 + r) * LD + k0 + c0] = e0;
+  if (c0 + 4 <= r) A[(k0 + r) * LD + k0 + c0 + 4] = e1;
 }
 
 // load 8 consecutive doubles (16-byte aligned) as four 128-bit accesses
@@ -730,10 +738,8 @@ __device__ __forceinline__ void ld8(const double* p, double* v) {
   }
 }
 
-// S1: rows i in [k0 + CB, Dp]: L[i][k0..k0+CB) = A[i][k0..k0+CB) * Lkk^-T
-__device__ __forceinline__ void chol_panel(double* A, int LD, int Dp, int k0, const double* rinv) {
-  const int i = k0 + CB + (int)threadIdx.x;
-  if (i > Dp) return;
+// panel row i: L[i][k0..k0+CB) = A[i][k0..k0+CB) * Lkk^-T by forward substitution
+__device__ __forceinline__ void chol_panel_row(double* A, int LD, int i, int k0, const double* rinv) {
   double ai[CB], li[CB];
   ld8(A + i * LD + k0, ai);
 #pragma unroll
@@ -749,80 +755,107 @@ __device__ __forceinline__ void chol_panel(double* A, int LD, int Dp, int k0, co
   for (int k = 0; k < 4; ++k) q[k] = make_double2(li[2 * k], li[2 * k + 1]);
 }
 
-// S2: block column [r0, r0 + CB) for rows i in [r0, Dp]: one (row, 4-column strip) per thread
-__device__ __forceinline__ void chol_update_next_col(double* A, int LD, int Dp, int k0, int r0) {
-  const int item = threadIdx.x, i = r0 + (item >> 1), j0 = r0 + 4 * (item & 1);
-  if (i > Dp) return;
-  double li[CB], lj[CB];
-  ld8(A + i * LD + k0, li);
-  double2* out = reinterpret_cast<double2*>(A + i * LD + j0);
-  double2  o0 = out[0], o1 = out[1];
-  double   s[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    ld8(A + (j0 + c) * LD + k0, lj);
+// warp 0: next diagonal block D' = A[r0..r0+CB)[r0..r0+CB) - P P^T (lower triangle, 36 entries over the lanes)
+__device__ __forceinline__ void chol_update_next_diag(double* A, int LD, int k0, int r0) {
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < CB * (CB + 1) / 2; e += 32) {
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= e) ++r;
+    const int c = e - r * (r + 1) / 2;
+    double    pr[CB], pc[CB];
+    ld8(A + (r0 + r) * LD + k0, pr);
+    ld8(A + (r0 + c) * LD + k0, pc);
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int b = 0; b < CB; b += 2) s0 = fma(li[b], lj[b], s0), s1 = fma(li[b + 1], lj[b + 1], s1);
-    s[c] = s0 + s1;
+    for (int b = 0; b < CB; b += 2) s0 = fma(pr[b], pc[b], s0), s1 = fma(pr[b + 1], pc[b + 1], s1);
+    A[(r0 + r) * LD + r0 + c] -= s0 + s1;
   }
-  o0.x -= s[0], o0.y -= s[1], o1.x -= s[2], o1.y -= s[3];
-  out[0] = o0, out[1] = o1;  // entries above the diagonal of the next diagonal block are never read
 }
 
-// S3 (warps w0..): rows [r1, Dp + 4), columns [r1, min(row, Dp - 1)] in 4 x 4 tiles
-__device__ __forceinline__ void chol_trailing_tiles(double* A, int LD, int Dp, int k0, int r1, int tid, int nth) {
-  const int m     = (Dp - r1) >> 2;           // regular row tiles; tile row m is the right-hand-side tile row
-  const int ntri  = m * (m + 1) / 2, ntile = ntri + m;
-  for (int q = tid; q < ntile; q += nth) {
-    int ti, tj;
-    if (q < ntri) {
-      ti = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
-      while (ti * (ti + 1) / 2 > q) --ti;
-      while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
-      tj = q - ti * (ti + 1) / 2;
-    } else {
-      ti = m, tj = q - ntri;
-    }
-    const int i0 = r1 + 4 * ti, j0 = r1 + 4 * tj;
+// Trailing update: rows [r1, Dp] with r1 = r0 + CB (row Dp = right-hand side), columns [r0, min(row, Dp - 1)].
+// One warp per 16 x 16 tile; lane (rho = lane & 7, gam = lane >> 3) owns the INTERLEAVED elements rows {rho, rho + 8} x
+// columns {gam, gam + 4, gam + 8, gam + 12} of the tile, so that every 16-byte shared load of a warp touches eight
+// consecutive rows (li) or four consecutive rows (lj) — conflict-free with the 16-byte row stride pattern of LD (a
+// contiguous 4 x 4 tile per thread would put the lanes 4 rows apart: 4-way bank conflicts on every load).
+// Row band bi (rows r1 + 16 bi ..) has column bands 0 .. bi + 1.
+__device__ __forceinline__ void chol_trailing_tiles(double* A, int LD, int Dp, int k0, int r0, int wid, int nwarps) {
+  const int lane = threadIdx.x & 31, rho = lane & 7, gam = lane >> 3;
+  const int r1    = r0 + CB;
+  const int nb    = (Dp + 1 - r1 + 15) >> 4;
+  const int ntile = nb * (nb + 3) / 2;
+  for (int q = wid; q < ntile; q += nwarps) {
+    int bi = (int)((sqrtf(9.f + 8.f * (float)q) - 3.f) * 0.5f);
+    while (bi * (bi + 3) / 2 > q) --bi;
+    while ((bi + 1) * (bi + 4) / 2 <= q) ++bi;
+    const int bj = q - bi * (bi + 3) / 2;
+    const int i0 = r1 + 16 * bi + rho, j0 = r0 + 16 * bj + gam;
     double    lj[4][CB], li[CB];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ld8(A + (j0 + c) * LD + k0, lj[c]);
+    for (int c = 0; c < 4; ++c) ld8(A + min(j0 + 4 * c, Dp) * LD + k0, lj[c]);  // clamped rows are masked below
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      ld8(A + (i0 + r) * LD + k0, li);
-      double2* out = reinterpret_cast<double2*>(A + (i0 + r) * LD + j0);
-      double2  o0 = out[0], o1 = out[1];
-      double   s[4];
+    for (int a = 0; a < 2; ++a) {
+      const int i = i0 + 8 * a;
+      if (i > Dp) continue;
+      ld8(A + i * LD + k0, li);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        const int j = j0 + 4 * c;
+        if (j >= Dp || (j > i && i < Dp)) continue;
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int b = 0; b < CB; b += 2) s0 = fma(li[b], lj[c][b], s0), s1 = fma(li[b + 1], lj[c][b + 1], s1);
-        s[c] = s0 + s1;
+        A[i * LD + j] -= s0 + s1;
       }
-      o0.x -= s[0], o0.y -= s[1], o1.x -= s[2], o1.y -= s[3];
-      out[0] = o0, out[1] = o1;
     }
   }
 }
 
+#ifdef WC_LM_TIMING
+#define WC_TICK() c0 = clock64()
+#define WC_TOCK(acc) acc += clock64() - c0
+#else
+#define WC_TICK()
+#define WC_TOCK(acc)
+#endif
+
+// Per block column k, two barriers:
+//   phase 1  panel(k): warp 0 solves the CB rows of the NEXT diagonal block and updates that block; the other warps
+//            solve the panel rows below;
+//   phase 2  warp 0 factorises the next diagonal block (the serial pivot chain)  ||  warps 1..15: the remaining
+//            trailing update, one 16 x 16 tile per warp.
 __device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fail) {
-  const int t = threadIdx.x, warp = t >> 5, LD = chol_ld(Dp);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, LD = chol_ld(Dp);
+#ifdef WC_LM_TIMING
+  long long c_p1 = 0, c_p2 = 0, c0;
+#endif
   if (warp == 0) chol_factor_diag(A, LD, 0, rinv, s_fail);
   __syncthreads();
   for (int k0 = 0; k0 < Dp; k0 += CB) {
     if (*s_fail) return;  // uniform (written before the last barrier)
-    chol_panel(A, LD, Dp, k0, rinv + k0);
-    __syncthreads();
     const int r0 = k0 + CB;
+    WC_TICK();
+    if (warp == 0) {
+      const int i = r0 + lane;
+      if (lane < CB && i <= Dp) chol_panel_row(A, LD, i, k0, rinv + k0);
+      if (r0 < Dp) {
+        __syncwarp();
+        chol_update_next_diag(A, LD, k0, r0);
+      }
+    } else {
+      for (int i = r0 + CB + (t - 32); i <= Dp; i += LMT - 32) chol_panel_row(A, LD, i, k0, rinv + k0);
+    }
+    __syncthreads();
+    WC_TOCK(c_p1);
     if (r0 >= Dp) break;  // last block column: only the right-hand-side row remained
-    chol_update_next_col(A, LD, Dp, k0, r0);
-    __syncthreads();
+    WC_TICK();
     if (warp == 0) chol_factor_diag(A, LD, r0, rinv + r0, s_fail);
-    else chol_trailing_tiles(A, LD, Dp, k0, r0 + CB, t - 32, LMT - 32);
+    else chol_trailing_tiles(A, LD, Dp, k0, r0, warp - 1, LMT / 32 - 1);
     __syncthreads();
+    WC_TOCK(c_p2);
   }
+#ifdef WC_LM_TIMING
+  if (t == 0) printf("chol cycles: phase1 (panel, diag update, factor) %lld phase2 (trailing) %lld\n", c_p1, c_p2);
+#endif
 }
 
 // backward substitution L^T x = z by blocks; z = row Dp of A; result x is written negated into y (length D)
@@ -863,13 +896,26 @@ __device__ void chol_backward_blocked(const double* A, int D, int Dp, const doub
 //   (2) FinalizeIterationAndCheckIfMinimizerCanContinue,
 //   (3) LevenbergMarquardtStrategy::ComputeStep + model cost change + candidate point,
 //   (4) clears the normal-equation buffer the next linearisation accumulates into.
-__global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int a_in_smem, int zero_next) {
+template <bool A_IN_SMEM>
+__global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int zero_next) {
   extern __shared__ __align__(16) double sA[];
   __shared__ double red[LMT / 32];
   __shared__ int    s_fail, s_accept, s_done, s_pending;
   __shared__ double xblk[CB];
-  LMState*  st = B.st;
+  // the LM state block is staged in shared memory (one coalesced read, one coalesced write-back): thread 0's
+  // bookkeeping then costs shared-memory latencies instead of a chain of dependent L2 round trips
+  __shared__ __align__(16) LMState sst;
+  static_assert(sizeof(LMState) % 8 == 0, "LMState is copied as 8-byte words");
   const int t  = threadIdx.x;
+  for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
+    reinterpret_cast<unsigned long long*>(&sst)[k] = reinterpret_cast<const unsigned long long*>(B.st)[k];
+  __syncthreads();
+  LMState* st = &sst;
+  auto write_back = [&]() {
+    __syncthreads();
+    for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
+      reinterpret_cast<unsigned long long*>(B.st)[k] = reinterpret_cast<const unsigned long long*>(&sst)[k];
+  };
   // control flags are broadcast through shared memory: thread 0 rewrites them below while other warps may lag
   if (t == 0) s_done = st->done, s_pending = st->pending;
   __syncthreads();
@@ -879,7 +925,7 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   long long tk[8];
   tk[0] = clock64();
 #endif
-  if (s_pending) lm_decide_dev(B, o, red, &s_accept);
+  if (s_pending) lm_decide_dev(B, st, o, red, &s_accept);
   __syncthreads();
 #ifdef WC_LM_TIMING
   tk[1] = clock64();
@@ -896,11 +942,14 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
     s_done = st->done;
   }
   __syncthreads();
-  if (s_done) return;
+  if (s_done) {
+    write_back();
+    return;
+  }
   const double* H = B.H[st->cur];
   const double* g = B.g[st->cur];
   const int     Dp = (D + CB - 1) / CB * CB, LD = chol_ld(Dp);
-  double*       A    = a_in_smem ? sA : B.A;            // (Dp + 4) x LD
+  double*       A    = A_IN_SMEM ? sA : B.A;            // (Dp + 4) x LD; compile-time choice: shared accesses are LDS/STS
   double*       rinv = A + (size_t)(Dp + 4) * LD;       // reciprocal pivots
   const double  radius = st->radius;
   if (!st->reuse_diagonal)
@@ -910,25 +959,64 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
       B.diag[c]      = fmin(fmax(d, o.min_lm_diagonal), o.max_lm_diagonal);
     }
   __syncthreads();
-  // A = S H S + diag / radius, lower triangle only: one warp per row, lanes over the columns (coalesced rows of H);
-  // padding rows are identity, row Dp is the right-hand side g_s = S g, rows Dp+1..Dp+3 are zero
-  for (int r = t >> 5; r < Dp + 4; r += LMT / 32) {
-    double* Ar = A + (size_t)r * LD;
-    if (r < D) {
-      const double  sr = B.scale[r];
-      const double* Hr = H + (size_t)amb_of(r, ff) * N;
-      for (int c = t & 31; c <= r; c += 32) {
-        double v = Hr[amb_of(c, ff)] * sr * B.scale[c];
-        if (r == c) {
-          const double sq = sqrt(B.diag[r] / radius);
-          v += sq * sq;
+  // A = S H S + diag / radius, lower triangle only; padding rows are identity, row Dp is the right-hand side g_s = S g,
+  // rows Dp+1..Dp+3 are zero.  Warps over rows, lanes over columns (coalesced rows of H); two rows x five column chunks
+  // of loads are issued before the first use so that ~10 L2 round trips are in flight per thread.
+  {
+    const int lane = t & 31, nw = LMT / 32;
+    for (int rb = t >> 5; rb < Dp + 4; rb += 2 * nw) {
+      double v[2][5];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = rb + u * nw;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int c = lane + 32 * q;
+          v[u][q]     = 0.0;
+          if (r < D && c <= r) v[u][q] = H[(size_t)amb_of(r, ff) * N + amb_of(c, ff)];
+          else if (r == Dp && c < D) v[u][q] = g[amb_of(c, ff)];
         }
-        Ar[c] = v;
       }
-    } else if (r < Dp) {
-      for (int c = t & 31; c <= r; c += 32) Ar[c] = c == r ? 1.0 : 0.0;
-    } else {
-      for (int c = t & 31; c < Dp; c += 32) Ar[c] = (r == Dp && c < D) ? g[amb_of(c, ff)] * B.scale[c] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = rb + u * nw;
+        if (r >= Dp + 4) continue;
+        double*      Ar = A + (size_t)r * LD;
+        const double sr = r < D ? B.scale[r] : 1.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int c = lane + 32 * q;
+          if (c >= Dp || (r < Dp && c > r)) continue;
+          double x = v[u][q];
+          if (r < D) {
+            x *= sr * B.scale[c];
+            if (r == c) {
+              const double sq = sqrt(B.diag[r] / radius);
+              x += sq * sq;
+            }
+          } else if (r < Dp) {
+            x = c == r ? 1.0 : 0.0;
+          } else if (r == Dp && c < D) {
+            x *= B.scale[c];
+          }
+          Ar[c] = x;
+        }
+        for (int c = lane + 160; c < Dp && (r >= Dp || c <= r); c += 32) {  // D > 160: remaining columns, plain loop
+          double x = 0.0;
+          if (r < D) {
+            x = H[(size_t)amb_of(r, ff) * N + amb_of(c, ff)] * sr * B.scale[c];
+            if (r == c) {
+              const double sq = sqrt(B.diag[r] / radius);
+              x += sq * sq;
+            }
+          } else if (r < Dp) {
+            x = c == r ? 1.0 : 0.0;
+          } else if (r == Dp && c < D) {
+            x = g[amb_of(c, ff)] * B.scale[c];
+          }
+          Ar[c] = x;
+        }
+      }
     }
   }
   __syncthreads();
@@ -972,7 +1060,8 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 #endif
   if (zero_next) {
     const int nb = 1 - st->cur;
-    for (int i = t; i < N * N; i += LMT) B.H[nb][i] = 0.0;
+    double2* Hz = reinterpret_cast<double2*>(B.H[nb]);  // N = 12 K: N * N is even, cudaMalloc alignment
+    for (int i = t; i < N * N / 2; i += LMT) Hz[i] = make_double2(0.0, 0.0);
     for (int i = t; i < N; i += LMT) B.g[nb][i] = 0.0;
     if (t == 0) *B.cost[nb] = 0.0;
   }
@@ -993,6 +1082,7 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
              tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[6] - tk[0]);
 #endif
   }
+  write_back();
 }
 
 __global__ void extract_ts(const wc_sample_state* __restrict__ s, int K, double* __restrict__ ts, double* __restrict__ x) {
@@ -1067,7 +1157,7 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
   WC_CUDA(c, cudaFuncSetAttribute(window_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
-  WC_CUDA(c, cudaFuncSetAttribute(lm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  WC_CUDA(c, cudaFuncSetAttribute(lm_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return WC_OK;
 }
 
@@ -1254,10 +1344,18 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   if ((s = wc_comm_allreduce(c, 0))) return s;
   { ++c->n_launches; lm_init<<<1, LMT, 0, st>>>(B, o); }
   const int batch = c->lm_batch > 0 ? c->lm_batch : 8;
+  static const int dbg_ev = getenv("WC_LM_EVENTS") != nullptr;  // debug: per-launch stream timeline of the LM loop
+  static cudaEvent_t evs[256];
+  static int evs_init = 0;
+  int n_ev = 0;
+  if (dbg_ev && !evs_init) { for (auto& e : evs) cudaEventCreate(&e); evs_init = 1; }
   for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
     for (int b = 0; b < batch; ++b) {
       // decide(previous candidate) + next trust-region step + clear the candidate buffer, then linearise there
-      { ++c->n_launches; lm_step<<<1, LMT, smem, st>>>(B, o, a_in_smem, c->world == 1); }
+      if (dbg_ev && n_ev + 3 < 256) cudaEventRecord(evs[n_ev++], st);
+      { ++c->n_launches; if (a_in_smem) lm_step<true><<<1, LMT, smem, st>>>(B, o, c->world == 1);
+        else lm_step<false><<<1, LMT, 0, st>>>(B, o, c->world == 1); }
+      if (dbg_ev && n_ev + 3 < 256) cudaEventRecord(evs[n_ev++], st);
       if ((s = enqueue_linearize(c, B, &o, 1, 1))) return s;
       if ((s = wc_comm_allreduce(c, 1))) return s;
     }
@@ -1268,6 +1366,11 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   WC_CUDA(c, cudaMemcpyAsync(m->h_x, c->d_x, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaEventRecord(c->ev[5], st));
   WC_CUDA(c, cudaStreamSynchronize(st));
+  if (dbg_ev) {
+    printf("LM timeline (us between consecutive events: step, linearize, step, ...):");
+    for (int i = 0; i + 1 < n_ev; ++i) { float ms; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); printf(" %.1f", ms * 1e3f); }
+    printf("\n");
+  }
   WC_CUDA(c, cudaGetLastError());
   if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "IMU state outside its sample interval (cost_functor.h:367,390)");
   if ((s = wc_comm_check(c))) return s;
