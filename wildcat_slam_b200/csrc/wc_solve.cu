@@ -858,36 +858,56 @@ __device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fai
 #endif
 }
 
-// backward substitution L^T x = z by blocks; z = row Dp of A; result x is written negated into y (length D)
-__device__ void chol_backward_blocked(const double* A, int D, int Dp, const double* rinv, double* zrow, double* y, double* xblk) {
-  const int t = threadIdx.x, LD = chol_ld(Dp);
-  for (int k0 = Dp - CB; k0 >= 0; k0 -= CB) {
-    if (t < 32) {  // 8 x 8 transposed triangular solve by lanes 0..7 of warp 0
-      const int lane = t;
-      double    v    = lane < CB ? zrow[k0 + lane] : 0.0;
-      double    lcol[CB];  // lcol[r] = L[k0 + r][k0 + lane]
+// Backward substitution L^T x = z by ONE warp, no block barriers: z (row Dp of A) lives in registers, element i in
+// lane i % 32, slot i / 32.  For j = Dp-1 .. 0: x_j = z_j * rinv_j (broadcast by one shuffle), then z_i -= L[j][i] x_j
+// for i < j — row j of L is contiguous, so the loads are conflict-free and independent of the pivot chain.  The slot
+// of the pivot is a compile-time constant of each 32-column sweep, so the loop body is a dozen instructions (a lone
+// warp pays ~4 cycles per dependent instruction: instruction count, not flops, is what matters here).
+// The result is written negated into y (length D).  Systems wider than 32 * BS_SLOTS fall back to a serial sweep.
+constexpr int BS_SLOTS = 8;  // up to 256 unknowns in registers
+template <int SJ>
+__device__ __forceinline__ void backward_sweep(const double* A, int LD, int D, int Dp, const double* rinv, double (&z)[BS_SLOTS],
+                                               double* y) {
+  const int lane = threadIdx.x & 31;
+  if (32 * SJ >= Dp) return;
+  const int jhi = min(31, Dp - 1 - 32 * SJ);
+#pragma unroll 1
+  for (int jj = jhi; jj >= 0; --jj) {
+    const int     j  = 32 * SJ + jj;
+    const double* Lj = A + (size_t)j * LD + lane;
+    double        l[SJ + 1];
 #pragma unroll
-      for (int r = 0; r < CB; ++r) lcol[r] = (lane < CB && r > lane) ? A[(k0 + r) * LD + k0 + lane] : 0.0;
-      const double ri = lane < CB ? rinv[k0 + lane] : 0.0;
+    for (int s = 0; s < SJ; ++s) l[s] = Lj[32 * s];
+    l[SJ] = lane < jj ? Lj[32 * SJ] : 0.0;
+    const double xj = __shfl_sync(0xffffffffu, z[SJ], jj) * rinv[j];
 #pragma unroll
-      for (int r = CB - 1; r >= 0; --r) {
-        if (lane == r) v *= ri;
-        const double xr = __shfl_sync(0xffffffffu, v, r);
-        if (lane < r) v = fma(-lcol[r], xr, v);
-      }
-      if (lane < CB) {
-        xblk[lane] = v;
-        if (k0 + lane < D) y[k0 + lane] = -v;
-      }
+    for (int s = 0; s <= SJ; ++s) z[s] = fma(-l[s], xj, z[s]);
+    if (lane == jj && j < D) y[j] = -xj;
+  }
+}
+__device__ void chol_backward_warp(const double* A, int D, int Dp, const double* rinv, double* y) {
+  const int LD = chol_ld(Dp), lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) return;
+  const double* zrow = A + (size_t)Dp * LD;
+  if (Dp <= 32 * BS_SLOTS) {
+    double z[BS_SLOTS];
+#pragma unroll
+    for (int s = 0; s < BS_SLOTS; ++s) z[s] = (32 * s + lane < Dp) ? zrow[32 * s + lane] : 0.0;
+    backward_sweep<7>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<6>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<5>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<4>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<3>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<2>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<1>(A, LD, D, Dp, rinv, z, y);
+    backward_sweep<0>(A, LD, D, Dp, rinv, z, y);
+  } else if (lane == 0) {
+    double* z = const_cast<double*>(zrow);
+    for (int j = Dp - 1; j >= 0; --j) {
+      const double xj = z[j] * rinv[j];
+      for (int i = 0; i < j; ++i) z[i] = fma(-A[(size_t)j * LD + i], xj, z[i]);
+      if (j < D) y[j] = -xj;
     }
-    __syncthreads();
-    for (int i = t; i < k0; i += LMT) {
-      double v = zrow[i];
-#pragma unroll
-      for (int b = 0; b < CB; ++b) v = fma(-A[(k0 + b) * LD + i], xblk[b], v);
-      zrow[i] = v;
-    }
-    __syncthreads();
   }
 }
 
@@ -901,7 +921,6 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   extern __shared__ __align__(16) double sA[];
   __shared__ double red[LMT / 32];
   __shared__ int    s_fail, s_accept, s_done, s_pending;
-  __shared__ double xblk[CB];
   // the LM state block is staged in shared memory (one coalesced read, one coalesced write-back): thread 0's
   // bookkeeping then costs shared-memory latencies instead of a chain of dependent L2 round trips
   __shared__ __align__(16) LMState sst;
@@ -1030,7 +1049,7 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 #endif
   bool    valid = !s_fail;
   double* y     = B.step;
-  if (valid) chol_backward_blocked(A, D, Dp, rinv, A + (size_t)Dp * LD, y, xblk);  // y = -(S H S + diag/radius)^-1 g_s
+  if (valid) chol_backward_warp(A, D, Dp, rinv, y);  // y = -(S H S + diag/radius)^-1 g_s
   __syncthreads();
 #ifdef WC_LM_TIMING
   tk[4] = clock64();
