@@ -230,10 +230,24 @@ __host__ __device__ inline void SymEig3(double a00, double a01, double a02, doub
     for (int pq = 0; pq < 3; ++pq) {
       const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2, r = 3 - p - q;
       if (a[p][q] == 0.0) continue;
-      double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-      double t     = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-      if (!isfinite(theta)) t = 0.0;
-      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      {  // an off-diagonal entry that cannot change either diagonal entry any more is rounded off (classic cyclic Jacobi)
+        const double g = 100.0 * fabs(a[p][q]);
+        if (fabs(a[p][p]) + g == fabs(a[p][p]) && fabs(a[q][q]) + g == fabs(a[q][q])) {
+          a[p][q] = a[q][p] = 0.0;
+          continue;
+        }
+      }
+      // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = tau / (2 a_pq), written with one division, one square
+      // root and one reciprocal square root: t = sgn * 2|a_pq| / (|tau| + sqrt(tau^2 + 4 a_pq^2)), c = rsqrt(t^2 + 1)
+      const double tau = a[q][q] - a[p][p], b = 2.0 * a[p][q];
+      const double sg  = (tau == 0.0 || ((tau > 0.0) == (b > 0.0))) ? 1.0 : -1.0;
+      double       t   = sg * fabs(b) / (fabs(tau) + sqrt(tau * tau + b * b));
+      if (!isfinite(t)) t = 0.0;
+#ifdef __CUDA_ARCH__
+      const double c = rsqrt(t * t + 1.0), s = t * c;
+#else
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#endif
       double apq = a[p][q];
       a[p][p] -= t * apq;
       a[q][q] += t * apq;

@@ -122,7 +122,8 @@ struct GridBufs {
   int*                hpos;  // table position per cell (cleanup)
   int*                tcell; // per target
   int*                ncells;
-  double*             sfeat; // sorted: 8 doubles per target (f[6], index bits, pad)
+  double*             sfeat; // sorted by cell, structure of arrays: 6 feature columns + the target index column, stride scap
+  size_t              scap;
   double*             cbox;  // per cell: min[6], max[6] of the member features
   unsigned long long* ckey;  // per cell: its key
   int*                err;
@@ -204,11 +205,9 @@ __global__ void grid_scatter(const double* __restrict__ tf, int tstr, int nt, Gr
   if (id < 0) return;
   const int     pos = G.off[id] + atomicAdd(&G.cur[id], 1);
   const double* f   = tf + (size_t)i * tstr;
-  double*       o   = G.sfeat + (size_t)pos * 8;
 #pragma unroll
-  for (int d = 0; d < 6; ++d) o[d] = f[d];
-  o[6] = __longlong_as_double((long long)i);
-  o[7] = 0.0;
+  for (int d = 0; d < 6; ++d) G.sfeat[d * G.scap + pos] = f[d];
+  G.sfeat[6 * G.scap + pos] = __longlong_as_double((long long)i);
 }
 
 // 6-D bounding box of every cell's members (for the pruned scan of the cells the ring search does not reach)
@@ -219,9 +218,11 @@ __global__ void grid_boxes(GridBufs G) {
 #pragma unroll
     for (int d = 0; d < 6; ++d) lo[d] = INFINITY, hi[d] = -INFINITY;
     for (int p = G.off[c]; p < G.off[c + 1]; ++p) {
-      const double* t = G.sfeat + (size_t)p * 8;
 #pragma unroll
-      for (int d = 0; d < 6; ++d) lo[d] = fmin(lo[d], t[d]), hi[d] = fmax(hi[d], t[d]);
+      for (int d = 0; d < 6; ++d) {
+        const double td = G.sfeat[d * G.scap + p];
+        lo[d] = fmin(lo[d], td), hi[d] = fmax(hi[d], td);
+      }
     }
 #pragma unroll
     for (int d = 0; d < 6; ++d) G.cbox[(size_t)c * 12 + d] = lo[d], G.cbox[(size_t)c * 12 + 6 + d] = hi[d];
@@ -241,6 +242,17 @@ __global__ void grid_cleanup(GridBufs G) {
 __global__ void grid_reset_count(GridBufs G) { *G.ncells = 0; }
 
 __device__ __forceinline__ bool cand_less(double d, int id, double dk, int ik) { return d < dk || (d == dk && id < ik); }
+#ifdef WC_KNN_STATS
+__device__ unsigned long long g_knn_stats[8];  // queries, phase-1 queries, members scanned (phase 0 / 1), cells scanned in phase 1, inserts
+__global__ void knn_stats_print() {
+  printf("knn stats: queries %llu phase1 %llu members p0 %llu p1 %llu p1-cells-taken %llu inserts %llu\n", g_knn_stats[0], g_knn_stats[1],
+         g_knn_stats[2], g_knn_stats[3], g_knn_stats[4], g_knn_stats[5]);
+  for (int i = 0; i < 8; ++i) g_knn_stats[i] = 0;
+}
+#define KSTAT(i, v) do { if (lane == 0) atomicAdd(&g_knn_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define KSTAT(i, v)
+#endif
 
 // One warp per query.  The sorted candidate list lives in registers, one entry per lane (lane j = j-th best, k <= 32),
 // so an insertion is a ballot + popc + shfl_up instead of a per-thread array shuffle, and all 32 lanes always work on
@@ -264,38 +276,44 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
     int    my_i = 0x7fffffff, worsti = 0x7fffffff;
 
     // scan the members [p0, p1) of one cell, 32 per step, inserting the ones that beat the current k-th best
-    auto scan_cell = [&](int p0, int p1) {
-#pragma unroll 1
-      for (int base = p0; base < p1; base += 32) {
-        const int p  = base + lane;
-        double    cd = INFINITY;
-        int       ci = 0x7fffffff;
-        if (p < p1) {
-          const double* t = G.sfeat + (size_t)p * 8;
-          double        rr = 0.0;  // flann::L2_Simple accumulation order, no contraction
+    // one step: lane holds sorted-feature row p (or -1); the candidates that beat the current k-th best are inserted
+    auto scan_batch = [&](int p) {
+      double cd = INFINITY;
+      int    ci = 0x7fffffff;
+      if (p >= 0) {
+        double td[7];  // coalesced column loads, all issued before the first use
 #pragma unroll
-          for (int d = 0; d < 6; ++d) {
-            const double diff = __dsub_rn(f[d], t[d]);
-            rr                = __dadd_rn(rr, __dmul_rn(diff, diff));
-          }
-          cd = rr, ci = (int)__double_as_longlong(t[6]);
+        for (int d = 0; d < 7; ++d) td[d] = G.sfeat[d * G.scap + p];
+        double rr = 0.0;  // flann::L2_Simple accumulation order, no contraction
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+          const double diff = __dsub_rn(f[d], td[d]);
+          rr                = __dadd_rn(rr, __dmul_rn(diff, diff));
         }
-        unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, ci, worst, worsti));
-        while (m) {
-          const int    src = __ffs(m) - 1;
-          const double bd  = __shfl_sync(0xffffffffu, cd, src);
-          const int    bi  = __shfl_sync(0xffffffffu, ci, src);
-          m &= m - 1;
-          if (!cand_less(bd, bi, worst, worsti)) continue;  // the list moved on since the ballot
-          const int    pos = __popc(__ballot_sync(0xffffffffu, lane < k && cand_less(my_d, my_i, bd, bi)));
-          const double ud  = __shfl_up_sync(0xffffffffu, my_d, 1);
-          const int    ui  = __shfl_up_sync(0xffffffffu, my_i, 1);
-          if (lane == pos) my_d = bd, my_i = bi;
-          else if (lane > pos) my_d = ud, my_i = ui;
-          worst  = __shfl_sync(0xffffffffu, my_d, k - 1);
-          worsti = __shfl_sync(0xffffffffu, my_i, k - 1);
-        }
+        cd = rr, ci = (int)__double_as_longlong(td[6]);
       }
+      unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, ci, worst, worsti));
+      while (m) {
+        const int    src = __ffs(m) - 1;
+        const double bd  = __shfl_sync(0xffffffffu, cd, src);
+        const int    bi  = __shfl_sync(0xffffffffu, ci, src);
+        m &= m - 1;
+        if (!cand_less(bd, bi, worst, worsti)) continue;  // the list moved on since the ballot
+        KSTAT(5, 1);
+        const int    pos = __popc(__ballot_sync(0xffffffffu, lane < k && cand_less(my_d, my_i, bd, bi)));
+        const double ud  = __shfl_up_sync(0xffffffffu, my_d, 1);
+        const int    ui  = __shfl_up_sync(0xffffffffu, my_i, 1);
+        if (lane == pos) my_d = bd, my_i = bi;
+        else if (lane > pos) my_d = ud, my_i = ui;
+        worst  = __shfl_sync(0xffffffffu, my_d, k - 1);
+        worsti = __shfl_sync(0xffffffffu, my_i, k - 1);
+      }
+    };
+    int  kphase    = 0;
+    auto scan_cell = [&](int p0, int p1) {
+      KSTAT(2 + kphase, p1 - p0);
+#pragma unroll 1
+      for (int base = p0; base < p1; base += 32) scan_batch(base + lane < p1 ? base + lane : -1);
     };
 
     const double    cfx = floor(f[0]), cfy = floor(f[1]), cfz = floor(f[2]);
@@ -303,33 +321,53 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
     const long long ix = rings_ok ? (long long)cfx : 0, iy = rings_ok ? (long long)cfy : 0, iz = rings_ok ? (long long)cfz : 0;
     bool            done = false;
     if (rings_ok) {
-      // phase 0: lane l < 27 probes cell (dx, dy, dz) = (l % 3 - 1, (l / 3) % 3 - 1, l / 9 - 1)
-      int c0 = 0, c1 = 0;
+      // phase 0: lane l < 27 probes one cell of the 3 x 3 x 3 block; lane 0 takes the query's own cell so that its members
+      // come first and tighten the k-th distance early
+      int c0 = 0, cn = 0;
       if (lane < 27) {
-        const unsigned long long key = cell_key(ix + lane % 3 - 1, iy + (lane / 3) % 3 - 1, iz + lane / 9 - 1);
+        const int                cc  = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
+        const unsigned long long key = cell_key(ix + cc % 3 - 1, iy + (cc / 3) % 3 - 1, iz + cc / 9 - 1);
         unsigned long long       h   = mix64(key) & G.mask;
         for (;; h = (h + 1) & G.mask) {
           const unsigned long long kk = G.keys[h];
           if (kk == key) {
             const int id = G.cid[h];
-            c0 = G.off[id], c1 = G.off[id + 1];
+            c0 = G.off[id], cn = G.off[id + 1] - c0;
             break;
           }
           if (kk == WC_CELL_EMPTY) break;
         }
       }
-      // own cell first (lane 13), then the rest
+      // the members of the 27 cells form ONE flat index space (inclusive prefix of the cell sizes over the lanes): every
+      // step scans 32 members regardless of how they are spread over the cells
+      int incl = cn;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const int excl  = incl - cn;
 #pragma unroll 1
-      for (int cc = 0; cc < 27; ++cc) {
-        const int src = cc == 0 ? 13 : (cc <= 13 ? cc - 1 : cc);
-        const int p0 = __shfl_sync(0xffffffffu, c0, src), p1 = __shfl_sync(0xffffffffu, c1, src);
-        if (p1 > p0) scan_cell(p0, p1);
+      for (int base = 0; base < total; base += 32) {
+        const int g  = base + lane;
+        int       lo = 0;  // last cell whose exclusive prefix is <= g
+#pragma unroll
+        for (int stp = 16; stp > 0; stp >>= 1) {
+          const int pv = __shfl_sync(0xffffffffu, excl, lo + stp);  // (lo + stp <= 31)
+          if (pv <= g) lo += stp;
+        }
+        const int ce = __shfl_sync(0xffffffffu, excl, lo), cs = __shfl_sync(0xffffffffu, c0, lo);
+        scan_batch(g < total ? cs + (g - ce) : -1);
       }
       const double b = fmin(fmin(fmin(f[0] - (cfx - 1), (cfx + 2) - f[0]), fmin(f[1] - (cfy - 1), (cfy + 2) - f[1])),
                             fmin(f[2] - (cfz - 1), (cfz + 2) - f[2]));
       done = worst < b * b * (1.0 - 1e-12);
     }
+    KSTAT(0, 1);
     if (!done) {
+      KSTAT(1, 1);
+      kphase = 1;
       // phase 1: box-test the remaining cells 32 at a time, scan the survivors one by one
 #pragma unroll 1
       for (int cb = 0; cb < nc; cb += 32) {
@@ -361,6 +399,7 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
           const int src = __ffs(m) - 1;
           m &= m - 1;
           const int q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
+          KSTAT(4, 1);
           scan_cell(q0, q1);  // (the bound was tested against an older, larger k-th distance: still exact)
         }
       }
@@ -417,52 +456,53 @@ __global__ void resolve_pairs(const int* __restrict__ gated, int nq, int k, int 
   acc_out[i] = take;
 }
 
-// exclusive scan of (acc[i] >= 0) by one CTA (8 items per thread per round), then scatter of the ordered pairs
+// Ordered compaction of the accepted pairs in two launches over all SMs: per-CTA counts, then every CTA sums the counts
+// of the CTAs before it (a few dozen values), scans its own 1024 queries and scatters — output order = query order.
+__global__ void __launch_bounds__(1024) pair_count(const int* __restrict__ acc, int nq, int* __restrict__ blk_cnt) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int n = __syncthreads_count(i < nq && acc[i] >= 0);
+  if (threadIdx.x == 0) blk_cnt[blockIdx.x] = n;
+}
 __global__ void __launch_bounds__(1024)
-compact_pairs(const int* __restrict__ acc, int nq, const double* __restrict__ qf, const double* __restrict__ tf,
-              wc_corr_idx* __restrict__ out, unsigned char* __restrict__ first_is_target, int* __restrict__ n_out) {
-  constexpr int IT = 8;
+pair_scatter(const int* __restrict__ acc, int nq, const int* __restrict__ blk_cnt, const double* __restrict__ qf,
+             const double* __restrict__ tf, wc_corr_idx* __restrict__ out, unsigned char* __restrict__ first_is_target,
+             int* __restrict__ n_out) {
   __shared__ int warp_sums[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nq; base += 1024 * IT) {
-    const int i0 = base + threadIdx.x * IT;
-    int       c[IT], v = 0;
-#pragma unroll
-    for (int u = 0; u < IT; ++u) c[u] = (i0 + u < nq) ? acc[i0 + u] : -1, v += c[u] >= 0;
-    int incl = v;
-    for (int d = 1; d < 32; d <<= 1) {
-      int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if ((threadIdx.x & 31) >= d) incl += o;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int w = warp_sums[threadIdx.x], wi = w;
-      for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, wi, d);
-        if (threadIdx.x >= d) wi += o;
-      }
-      warp_sums[threadIdx.x] = wi - w;
-    }
-    __syncthreads();
-    int pos = carry + warp_sums[threadIdx.x >> 5] + incl - v;
-#pragma unroll
-    for (int u = 0; u < IT; ++u) {
-      if (c[u] < 0) continue;
-      const int  i           = i0 + u;
-      const bool query_first = qf[(size_t)i * FSTR + 12] < tf[(size_t)c[u] * FSTR + 12];  // :41
-      out[pos].s1            = query_first ? i : c[u];
-      out[pos].s2            = query_first ? c[u] : i;
-      first_is_target[pos]   = query_first ? 0 : 1;
-      ++pos;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = pos;
-    __syncthreads();
+  __shared__ int s_base;
+  const int t = threadIdx.x, lane = t & 31, i = blockIdx.x * 1024 + t;
+  if (t < 32) {
+    int s = 0;
+    for (int b = lane; b < (int)blockIdx.x; b += 32) s += blk_cnt[b];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if (lane == 0) s_base = s;
   }
-  if (threadIdx.x == 0) *n_out = carry;
+  const int c = i < nq ? acc[i] : -1;
+  const int v = c >= 0;
+  int       incl = v;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) warp_sums[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    const int w  = warp_sums[t];
+    int       wi = w;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (t >= d) wi += o;
+    }
+    warp_sums[t] = wi - w;
+  }
+  __syncthreads();
+  const int pos = s_base + warp_sums[t >> 5] + incl - v;
+  if (v) {
+    const bool query_first = qf[(size_t)i * FSTR + 12] < tf[(size_t)c * FSTR + 12];  // knn_surfel_matcher.cc:41
+    out[pos].s1            = query_first ? i : c;
+    out[pos].s2            = query_first ? c : i;
+    first_is_target[pos]   = query_first ? 0 : 1;
+  }
+  if (blockIdx.x == gridDim.x - 1 && t == 1023) *n_out = pos + v;
 }
 
 }  // namespace
@@ -480,6 +520,7 @@ static wc_status match_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&c->d_acc, ns * 4));
   WC_CUDA(c, cudaMalloc(&c->d_acc2, ns * 4));
   WC_CUDA(c, cudaMalloc(&c->d_flag, 16));
+  WC_CUDA(c, cudaMalloc(&c->d_scan_tmp, (ns / 1024 + 2) * 4));
   WC_CUDA(c, cudaMalloc(&c->d_corr_out, ns * sizeof(wc_corr_idx)));
   WC_CUDA(c, cudaMalloc(&c->d_fit_out, ns));
   WC_CUDA(c, cudaMallocHost(&c->h_flag, 16));
@@ -497,7 +538,8 @@ static wc_status match_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&G->tcell, ns * 4));
   WC_CUDA(c, cudaMalloc(&G->ncells, 8));
   G->err = c->d_flag + 2;
-  WC_CUDA(c, cudaMalloc(&G->sfeat, ns * 8 * 8));
+  G->scap = ns;
+  WC_CUDA(c, cudaMalloc(&G->sfeat, ns * 7 * 8));
   WC_CUDA(c, cudaMalloc(&G->cbox, (ns + 1) * 12 * 8));
   WC_CUDA(c, cudaMalloc(&G->ckey, (ns + 1) * 8));
   WC_CUDA(c, cudaMemsetAsync(G->keys, 0xff, cap * 8, c->stream));
@@ -510,7 +552,7 @@ static wc_status match_alloc(wc_ctx* c) {
 
 void wc_match_free(wc_ctx* c) {
   void* ptrs[] = {c->d_msurf_q, c->d_msurf_t, c->d_qfeat, c->d_tfeat, c->d_knn_idx, c->d_knn_d2, c->d_gated,
-                  c->d_acc,     c->d_acc2,    c->d_flag,  c->d_corr_out, c->d_fit_out, c->d_part_d, c->d_part_i};
+                  c->d_acc,     c->d_acc2,    c->d_flag,  c->d_scan_tmp, c->d_corr_out, c->d_fit_out, c->d_part_d, c->d_part_i};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -554,6 +596,10 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     { ++c->n_launches; grid_scatter<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB); }
     { ++c->n_launches; grid_boxes<<<c->num_sms, 256, 0, st>>>(GB); }
     { ++c->n_launches; knn6_warp<<<c->num_sms * 8, 256, 0, st>>>(c->d_qfeat, FSTR, (int)nq, k, GB, c->d_knn_idx, c->d_knn_d2); }
+#ifdef WC_KNN_STATS
+    knn_stats_print<<<1, 1, 0, st>>>();
+    { int ncell = 0; cudaMemcpyAsync(&ncell, GB.ncells, 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); printf("grid cells %d targets %zu\n", ncell, nt); }
+#endif
     { ++c->n_launches; grid_cleanup<<<c->num_sms, 256, 0, st>>>(GB); }
     { ++c->n_launches; grid_reset_count<<<1, 1, 0, st>>>(GB); }
   }
@@ -576,7 +622,9 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     if (*c->h_flag == 0) break;
     if (it > (int)nq) WC_FAIL(c, WC_ENUMERIC, "pair de-duplication did not converge");
   }
-  { ++c->n_launches; compact_pairs<<<1, 1024, 0, st>>>(a, (int)nq, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
+  const unsigned gc = (unsigned)((nq + 1023) / 1024);
+  { ++c->n_launches; pair_count<<<gc, 1024, 0, st>>>(a, (int)nq, c->d_scan_tmp); }
+  { ++c->n_launches; pair_scatter<<<gc, 1024, 0, st>>>(a, (int)nq, c->d_scan_tmp, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
   WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 12, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
