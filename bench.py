@@ -45,24 +45,38 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """starts the nvidia-smi loop (call BEFORE the warm-up: the process needs ~100 ms to produce its first line)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300)]
+        note = []
+        if not inside and self.rows:  # timed region shorter than the sampling period: take the samples nearest to it
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0)) if self.t0 is not None else self.rows[-1][0]
+            inside = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            note = ["nearest samples (timed region shorter than the sampling period)"]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])), mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -71,14 +85,8 @@ class ClockSampler:
             except Exception:
                 pass
         if not sm:
-            try:  # the -lms loop produced nothing (very short timed region): take one sample now
-                out = subprocess.check_output(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                              text=True, stderr=subprocess.DEVNULL)
-                r = [c.strip() for c in out.strip().split(",")]
-                return {"sm_mhz": float(r[1]), "sm_max_mhz": float(r[2]), "reasons": ["single post-run sample"]}
-            except Exception:
-                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons) + note, "samples": len(sm)}
 
 
 def oracle_pass(O, w, fix_body, timings=None):
@@ -184,11 +192,12 @@ def main():
         torch.cuda.synchronize()
         return rp.run()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     l0 = ctx.lib.wc_launch_count(ctx.handle)
     dev_ms, iters, stats, summ = 0.0, 0, [], None
     t_wall = time.perf_counter()
@@ -199,6 +208,7 @@ def main():
         stats.append(st)
     barrier()
     t_wall = time.perf_counter() - t_wall
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = ctx.lib.wc_launch_count(ctx.handle) - l0
     tm = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")

@@ -35,11 +35,24 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
 
 struct ExtractParams {
   double voxel;     // (double)(float)voxel_size
+  double inv_voxel; // 1 / voxel (rounded): only proposes the quotient, voxel_floor() makes it exact
   double q0, q1;    // (double)(float)(voxel/4), (double)(float)(voxel/8)
   double t_first;
   int    vox0[3];
   int    n;
 };
+
+// floor(RN(x / v)) without the division, bit-exact for x = (double)float32 and v = (double)float32, |x / v| < 2^21:
+// x and every k * v are multiples of 2^-24 * 2^e grids coarse enough that x / v is either an exact integer or at least
+// 2^-26 away from one, far more than the half-ulp by which the rounded quotient can move — so floor(RN(x / v)) equals
+// the floor of the exact quotient.  The reciprocal multiply proposes q (off by at most one); the products q * v and
+// (q + 1) * v are exact in fp64 (21 + 24 bits), so the two comparisons against x decide the floor exactly.
+__device__ __forceinline__ double voxel_floor(double x, double v, double inv_v) {
+  double q = floor(__dmul_rn(x, inv_v));
+  if (x < __dmul_rn(q, v)) q -= 1.0;
+  else if (x >= __dmul_rn(q + 1.0, v)) q += 1.0;
+  return q;
+}
 
 // ---------------------------------------------------------------------------------------------- K0
 __global__ void repack_points(const wc_point48* __restrict__ raw, int n, float4* __restrict__ xyz,
@@ -102,12 +115,11 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
       if (i > 0 && tt < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
       const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
       // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
-      const int vx = (int)floor(__ddiv_rn(x, P.voxel));
-      const int vy = (int)floor(__ddiv_rn(y, P.voxel));
-      const int vz = (int)floor(__ddiv_rn(z, P.voxel));
+      const double fvx = voxel_floor(x, P.voxel, P.inv_voxel), fvy = voxel_floor(y, P.voxel, P.inv_voxel),
+                   fvz = voxel_floor(z, P.voxel, P.inv_voxel);
+      const int    vx = (int)fvx, vy = (int)fvy, vz = (int)fvz;
       // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
-      double cx = __dmul_rn(0.5 + (double)vx, P.voxel), cy = __dmul_rn(0.5 + (double)vy, P.voxel),
-             cz = __dmul_rn(0.5 + (double)vz, P.voxel);
+      double cx = __dmul_rn(0.5 + fvx, P.voxel), cy = __dmul_rn(0.5 + fvy, P.voxel), cz = __dmul_rn(0.5 + fvz, P.voxel);
       int bx = x > cx, by = y > cy, bz = z > cz;
       const int c1 = 4 * bx + 2 * by + bz;
       cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
@@ -132,7 +144,8 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
       } else {
         const unsigned long long key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) |
                                        ((unsigned long long)rz << 18) | ((unsigned long long)leaf << 12) | (unsigned long long)bin;
-        unsigned h = (unsigned)(mix64(key) >> 40) & (KTAB - 1);
+        unsigned h = ((unsigned)key * 0x9E3779B1u) ^ ((unsigned)(key >> 32) * 0x85EBCA77u);  // tile-local table: a cheap mix
+        h          = ((h ^ (h >> 15)) * 0x2C1B3C6Du) >> 20 & (KTAB - 1);
         for (;;) {  // at most KT distinct keys in KTAB = 2 KT positions: always terminates
           unsigned long long k = skey[h];
           if (k == WC_KEY_EMPTY) k = atomicCAS(&skey[h], WC_KEY_EMPTY, key);
@@ -901,6 +914,7 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   const float  vsf = c->prm.voxel_size;
   ExtractParams P;
   P.voxel = (double)vsf, P.q0 = (double)(float)(vsf / 4), P.q1 = (double)(float)((float)(vsf / 4) / 2);
+  P.inv_voxel = 1.0 / P.voxel;
   P.t_first = c->t_first, P.n = n;
   for (int k = 0; k < 3; ++k) P.vox0[k] = c->vox0[k];
 
