@@ -213,6 +213,34 @@ wc_status wc_build_surfels_resident(wc_ctx* ctx, size_t* n_out, double* gpu_ms_k
 wc_status wc_surfels_fetch(wc_ctx* ctx, wc_surfel* out, size_t cap, size_t* n_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sweep preparation — the per-point steps immediately before BuildSurfels.
+ *
+ * wc_filter_points replaces the loop at the top of LidarOdometry::AddLidarScan (lidar_odometry.cc:489-496):
+ *   p <- (float)(ext_lidar2imu * p); drop if |p| < min_range, |p| > max_range or p inside the blind box;
+ *   the kept points keep their order.  WC_EINVAL_TIME_ORDER replaces the CHECK at :491 and is slightly stricter:
+ *   the reference compares each point with the last KEPT point, this call requires the raw timestamps to be
+ *   non-decreasing (identical on every valid sweep).
+ * wc_undistort_sweep replaces UndistortSweep (lidar_odometry.cc:143-158): every point is moved to the world
+ *   frame with the IMU pose interpolated at its own timestamp; WC_EOUT_OF_SPAN replaces the CHECK at :150.
+ * wc_undistort_upload is the resident variant: raw sweep in, the undistorted sweep is left on the device in
+ *   the layout wc_build_surfels_resident consumes (the undistorted 48-byte sweep is never materialised).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wc_sweep_filter {
+  double ext_q[4];          /* lidar -> IMU rotation, Eigen coeff order (x, y, z, w); lio_config.h:24-30 */
+  double ext_t[3];          /* lidar -> IMU translation                                                 */
+  double min_range;         /* 0.3    lio_config.h:19                                                  */
+  double max_range;         /* 120    lio_config.h:18                                                  */
+  double blind_box_min[3];  /* (-0.8, -0.5, -0.4)  lio_config.h:20-22, in imu_link                      */
+  double blind_box_max[3];  /* ( 0.3,  0.5,  0.4)                                                       */
+} wc_sweep_filter;
+void      wc_default_sweep_filter(wc_sweep_filter* f);
+wc_status wc_filter_points(wc_ctx* ctx, const wc_sweep_filter* f, const wc_point48* in, size_t n, wc_point48* out,
+                           size_t cap, size_t* n_out);
+wc_status wc_undistort_sweep(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu, const wc_point48* in, size_t n,
+                             wc_point48* out);
+wc_status wc_undistort_upload(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu, const wc_point48* in, size_t n);
+
+/* ------------------------------------------------------------------------------------------------
  * Surfel poses — replaces UpdateSurfelPoses (lidar_odometry.cc:160-170) + Surfel::UpdatePose
  * (surfel.h:48-58): interpolate the IMU pose at each surfel time (lerp / Eigen slerp) and move the
  * surfel to the body frame on first call.  In-place on host surfels.

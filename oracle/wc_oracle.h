@@ -83,6 +83,9 @@ int wco_apply_corrections(wc_sample_state* samples, int64_t K, wc_imu_state* imu
 /* UndistortSweep, lidar_odometry.cc:143-158 (a "next" row, used by the synthetic generator's checks) */
 int wco_undistort_sweep(const wc_imu_state* imu, int64_t n_imu, const wc_point48* in, int64_t n, wc_point48* out);
 
+/* AddLidarScan's per-point extrinsic + range / blind-box filter, lidar_odometry.cc:489-496; returns kept count or -status */
+int64_t wco_filter_points(const wc_sweep_filter* f, const wc_point48* in, int64_t n, wc_point48* out);
+
 /* utils.h / Sophus helpers for the known-answer tests: op 0 Exp (out: quat xyzw), 1 Log (in: quat xyzw,
  * out 3), 2 Jl, 3 Jl_inv, 4 Jr, 5 Jr_inv (out 9 row-major), 6 sym-eig (in 9, out 3 evals + 9 evecs) */
 void wco_so3(int op, const double* in, double* out);

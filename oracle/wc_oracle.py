@@ -78,6 +78,16 @@ def undistort_sweep(imu, points):
     return st, out
 
 
+def filter_points(points, flt=None):
+    flt = flt or T.default_sweep_filter()
+    points = np.ascontiguousarray(points, dtype=T.POINT48)
+    out = np.zeros_like(points)
+    f = lib().wco_filter_points
+    f.restype = C.c_int64
+    n = f(C.byref(flt), _p(points), C.c_int64(len(points)), _p(out))
+    return (int(-n), None) if n < 0 else (0, out[:n].copy())
+
+
 def match(query, target, self_match, params=None, use_kdtree=True):
     prm = params or T.default_params()
     query = np.ascontiguousarray(query, dtype=T.SURFEL)

@@ -316,6 +316,29 @@ extern "C" int wco_undistort_sweep(const wc_imu_state* imu, int64_t n_imu, const
   return WC_OK;
 }
 
+// AddLidarScan's per-point loop, lidar_odometry.cc:489-496: extrinsic, time-order CHECK, range / blind-box filter.
+// Returns the number of kept points, or a negative wc_status.
+extern "C" int64_t wco_filter_points(const wc_sweep_filter* f, const wc_point48* in, int64_t n, wc_point48* out) {
+  const Q4 q = Q4::FromCoeffs(f->ext_q);
+  const V3 t(f->ext_t);
+  int64_t  k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    wc_point48 pt = in[i];
+    const V3   p  = q * V3((double)pt.x, (double)pt.y, (double)pt.z) + t;  // Rigid3d * point (rigid_transform.h), :490
+    pt.x = (float)p.x, pt.y = (float)p.y, pt.z = (float)p.z;
+    if (k > 0 && pt.time < out[k - 1].time) return -(int64_t)WC_EINVAL_TIME_ORDER;  // CHECK :491: vs. points_buff_.back()
+    const float  n2 = pt.x * pt.x + pt.y * pt.y + pt.z * pt.z;                         // Vector3f::norm(), :492
+    const double nr = (double)sqrtf(n2);
+    if (nr < f->min_range || nr > f->max_range) continue;
+    const double x = pt.x, y = pt.y, z = pt.z;  // AlignedBox<double,3>::contains
+    if (x >= f->blind_box_min[0] && x <= f->blind_box_max[0] && y >= f->blind_box_min[1] && y <= f->blind_box_max[1] &&
+        z >= f->blind_box_min[2] && z <= f->blind_box_max[2])
+      continue;
+    out[k++] = pt;
+  }
+  return k;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // knn_surfel_matcher.cc
 // ---------------------------------------------------------------------------------------------------

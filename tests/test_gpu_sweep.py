@@ -1,0 +1,129 @@
+"""Parity of the sweep-preparation row (AddLidarScan's extrinsic + range / blind-box filter,
+lidar_odometry.cc:489-496, and UndistortSweep, :143-158) against the CPU oracle.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+from wildcat_slam_b200 import synthetic as S
+from wildcat_slam_b200 import types as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def od():
+    from wildcat_slam_b200 import odometry
+
+    return odometry
+
+
+@pytest.fixture(scope="module")
+def ctx(od):
+    c = od.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import wc_oracle
+
+    wc_oracle.build()
+    return wc_oracle
+
+
+def _same(a, b):
+    """field-wise bit equality (the 48-byte record has padding bytes that carry no meaning)."""
+    return len(a) == len(b) and all(np.array_equal(np.ascontiguousarray(a[f]).view(np.uint8), np.ascontiguousarray(b[f]).view(np.uint8))
+                                  for f in a.dtype.names)
+
+
+def _raw_cloud(name, extra=True):
+    """a lidar-frame cloud with points on both sides of every filter decision."""
+    w = S.make_window(name)
+    pts = w.points.copy()
+    if extra:
+        rng = np.random.default_rng(11)
+        n = len(pts)
+        k = n // 7
+        pts["x"][:k] = rng.uniform(-1.0, 1.0, k).astype(np.float32)        # around the blind box and the 0.3 m sphere
+        pts["y"][:k] = rng.uniform(-1.0, 1.0, k).astype(np.float32)
+        pts["z"][:k] = rng.uniform(-0.6, 0.6, k).astype(np.float32)
+        pts["x"][k:2 * k] = rng.uniform(-130.0, 130.0, k).astype(np.float32)  # around the 120 m sphere
+        pts["y"][k:2 * k] = rng.uniform(-130.0, 130.0, k).astype(np.float32)
+        # exact boundary cases of the box (in imu_link: undo the default extrinsic is not needed, any frame will do)
+    return w, pts
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_filter_points_bit_exact(od, ctx, oracle, name):
+    w, pts = _raw_cloud(name)
+    st, ref = oracle.filter_points(pts)
+    assert st == 0
+    got = od.FilterPoints(pts, ctx=ctx)
+    assert 0 < len(ref) < len(pts)                     # the cloud exercises both outcomes
+    assert len(got) == len(ref)
+    assert _same(got, ref)                             # order, kept set and the float32 coordinates: bit exact
+    # another extrinsic / limits
+    f = T.default_sweep_filter()
+    q = np.array([0.1, -0.2, 0.3, 0.9]); q /= np.linalg.norm(q)
+    f.ext_q[:] = q.tolist()
+    f.ext_t[:] = [0.5, -0.25, 0.125]
+    f.min_range, f.max_range = 1.0, 60.0
+    st, ref = oracle.filter_points(pts, f)
+    got = od.FilterPoints(pts, f, ctx=ctx)
+    assert st == 0 and _same(got, ref)
+
+
+def test_filter_points_edge_cases(od, ctx, oracle):
+    empty = np.zeros(0, dtype=T.POINT48)
+    assert len(od.FilterPoints(empty, ctx=ctx)) == 0
+    one = np.zeros(1, dtype=T.POINT48)
+    one["x"], one["time"] = 5.0, 1.0
+    assert _same(od.FilterPoints(one, ctx=ctx), oracle.filter_points(one)[1])
+    # ragged size (not a multiple of the 1024-point CTA), everything dropped, everything kept
+    w, pts = _raw_cloud("C1", extra=False)
+    pts = pts[:1500]
+    far = pts.copy(); far["x"] = 500.0
+    assert len(od.FilterPoints(far, ctx=ctx)) == 0 == len(oracle.filter_points(far)[1])
+    assert _same(od.FilterPoints(pts, ctx=ctx), oracle.filter_points(pts)[1])
+    # time order violation -> WC_EINVAL_TIME_ORDER (CHECK lidar_odometry.cc:491)
+    bad = pts.copy(); bad["time"][700] = bad["time"][0] - 1.0
+    assert oracle.filter_points(bad)[0] == T.WC_EINVAL_TIME_ORDER
+    from wildcat_slam_b200.abi import WildcatError
+    with pytest.raises(WildcatError) as e:
+        od.FilterPoints(bad, ctx=ctx)
+    assert e.value.status == T.WC_EINVAL_TIME_ORDER
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_undistort_matches_oracle(od, ctx, oracle, name):
+    w = S.make_window(name)
+    pts = w.points  # any IMU-frame coordinates will do: every timestamp lies inside the IMU span
+    st, ref = oracle.undistort_sweep(w.imu, pts)
+    assert st == 0
+    got = od.UndistortSweep(pts, w.imu, ctx=ctx)
+    for fld in ("intensity", "time", "ring"):
+        assert np.array_equal(got[fld], ref[fld])
+    # fp64 slerp (acos / sin from different math libraries) then a float32 store: identical up to one float32 ulp
+    for fld in ("x", "y", "z"):
+        ulp = np.spacing(np.abs(ref[fld]).astype(np.float32))
+        assert (np.abs(got[fld].astype(np.float64) - ref[fld].astype(np.float64)) <= ulp).all()
+        assert np.mean(got[fld] == ref[fld]) > 0.999
+
+
+def test_undistort_error_and_fused_resident_path(od, ctx, oracle):
+    w = S.make_window("C1")
+    from wildcat_slam_b200.abi import WildcatError
+    bad = w.points.copy()
+    bad["time"][-1] = w.imu["timestamp"][-1] + 1.0  # beyond the IMU span: CHECK lidar_odometry.cc:150
+    assert oracle.undistort_sweep(w.imu, bad)[0] == T.WC_EOUT_OF_SPAN
+    with pytest.raises(WildcatError) as e:
+        od.UndistortSweep(bad, w.imu, ctx=ctx)
+    assert e.value.status == T.WC_EOUT_OF_SPAN
+    # fused: raw sweep -> (undistort + repack on the device) -> BuildSurfels == BuildSurfels(UndistortSweep(raw))
+    und = od.UndistortSweep(w.points, w.imu, ctx=ctx)
+    ref = od.BuildSurfels(und, ctx=ctx)
+    rs = od.ResidentSweep(w.points, ctx=ctx, imu_states=w.imu)
+    n, _ = rs.extract()
+    got = rs.fetch()
+    assert n == len(ref) > 0 and got.tobytes() == ref.tobytes()

@@ -55,6 +55,10 @@ def load():
     lib.wc_points_upload.argtypes = [vp, vp, sz]
     lib.wc_build_surfels_resident.argtypes = [vp, P(sz), P(dbl), P(dbl), P(dbl)]
     lib.wc_surfels_fetch.argtypes = [vp, vp, sz, P(sz)]
+    lib.wc_default_sweep_filter.argtypes = [P(T.SweepFilter)]
+    lib.wc_filter_points.argtypes = [vp, P(T.SweepFilter), vp, sz, vp, sz, P(sz)]
+    lib.wc_undistort_sweep.argtypes = [vp, vp, sz, vp, sz, vp]
+    lib.wc_undistort_upload.argtypes = [vp, vp, sz, vp, sz]
     lib.wc_update_surfel_poses.argtypes = [vp, vp, sz, vp, sz]
     lib.wc_match.argtypes = [vp, vp, sz, vp, sz, i32, vp, sz, P(sz), vp, P(dbl)]
     lib.wc_knn6.argtypes = [vp, vp, sz, vp, sz, i32, vp, vp]
@@ -75,7 +79,7 @@ def load():
     for name in declared_symbols():
         f = getattr(lib, name)  # raises AttributeError if the library lacks a declared entry point
         if name not in ("wc_abi_version", "wc_default_params", "wc_default_solve_opts", "wc_destroy", "wc_last_error",
-                        "wc_status_str", "wc_stream", "wc_launch_count", "wc_host_alloc", "wc_host_free"):
+                        "wc_status_str", "wc_stream", "wc_launch_count", "wc_host_alloc", "wc_host_free", "wc_default_sweep_filter"):
             f.restype = i32
     _lib = lib
     return lib

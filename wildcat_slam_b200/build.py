@@ -14,7 +14,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
           *os.environ.get("WC_NVCC_EXTRA", "").split()]  # e.g. WC_NVCC_EXTRA=-DWC_LM_TIMING for the in-kernel phase clocks
 SOURCES = {"wc_api.cu": [], "wc_extract.cu": [], "wc_match.cu": ["-fmad=false"], "wc_solve.cu": [], "wc_spline.cu": [],
-           "wc_comm.cu": [], "wc_pass.cu": []}
+           "wc_comm.cu": [], "wc_pass.cu": [], "wc_sweep.cu": ["-fmad=false"]}
 
 
 def _newer(src, dst):

@@ -9,6 +9,7 @@ void wc_match_free(wc_ctx* c);
 void wc_solve_free(wc_ctx* c);
 void wc_comm_free(wc_ctx* c);
 void wc_spline_free(wc_ctx* c);
+void wc_sweep_free(wc_ctx* c);
 
 extern "C" int wc_abi_version(void) { return WC_ABI_VERSION; }
 
@@ -113,6 +114,7 @@ extern "C" void wc_destroy(wc_ctx* c) {
   wc_match_free(c);
   wc_solve_free(c);
   wc_spline_free(c);
+  wc_sweep_free(c);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   free(c);

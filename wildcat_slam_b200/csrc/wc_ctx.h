@@ -104,6 +104,8 @@ struct wc_ctx {
   int                 want_assign;
   int                 last_slots, last_voxels;
 
+  void*               d_sweep;    // wc_sweep_mem (filter / undistort staging)
+
   // ---- matcher
   double* d_qfeat;  // nq x 8: 6 features + timestamp + pad
   double* d_tfeat;

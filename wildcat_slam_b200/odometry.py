@@ -275,13 +275,45 @@ def ApplyCorrections(samples, imu_states, ctx=None):
     return s, imu
 
 
-class ResidentSweep:
-    """Upload a sweep once, extract repeatedly (the "inputs resident in HBM" leg of the benchmark)."""
+def FilterPoints(cloud, flt=None, ctx=None):
+    """The per-point loop at the top of LidarOdometry::AddLidarScan (lidar_odometry.cc:489-496): lidar -> IMU extrinsic,
+    range and blind-box filter; returns the kept points in order."""
+    ctx = ctx or default_context()
+    flt = flt or T.default_sweep_filter()
+    cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
+    out = np.zeros(max(1, len(cloud)), dtype=T.POINT48)
+    n = C.c_size_t(0)
+    st = ctx.lib.wc_filter_points(ctx.handle, C.byref(flt), T.ptr(cloud), len(cloud), T.ptr(out), len(out), C.byref(n))
+    ctx.check(st, "wc_filter_points")
+    return out[: n.value].copy()
 
-    def __init__(self, cloud, ctx=None):
+
+def UndistortSweep(sweep_in, imu_states, ctx=None):
+    """UndistortSweep (lidar_odometry.cc:143-158): every point to the world frame with the IMU pose interpolated at its
+    own timestamp."""
+    ctx = ctx or default_context()
+    sweep_in = np.ascontiguousarray(sweep_in, dtype=T.POINT48)
+    imu = np.ascontiguousarray(imu_states, dtype=T.IMU)
+    out = np.zeros_like(sweep_in)
+    st = ctx.lib.wc_undistort_sweep(ctx.handle, T.ptr(imu), len(imu), T.ptr(sweep_in), len(sweep_in), T.ptr(out))
+    ctx.check(st, "wc_undistort_sweep")
+    return out
+
+
+class ResidentSweep:
+    """Upload a sweep once, extract repeatedly (the "inputs resident in HBM" leg of the benchmark).  With `imu_states`
+    the cloud is the RAW (distorted, IMU-frame) sweep and the undistortion runs on the device, fused with the repack
+    into the resident layout (wc_undistort_upload)."""
+
+    def __init__(self, cloud, ctx=None, imu_states=None):
         self.ctx = ctx or default_context()
         self.cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
-        self.ctx.check(self.ctx.lib.wc_points_upload(self.ctx.handle, T.ptr(self.cloud), len(self.cloud)), "wc_points_upload")
+        if imu_states is None:
+            self.ctx.check(self.ctx.lib.wc_points_upload(self.ctx.handle, T.ptr(self.cloud), len(self.cloud)), "wc_points_upload")
+        else:
+            imu = np.ascontiguousarray(imu_states, dtype=T.IMU)
+            st = self.ctx.lib.wc_undistort_upload(self.ctx.handle, T.ptr(imu), len(imu), T.ptr(self.cloud), len(self.cloud))
+            self.ctx.check(st, "wc_undistort_upload")
 
     def extract(self):
         n = C.c_size_t(0)

@@ -136,6 +136,28 @@ class PassStats(C.Structure):
                                           "ms_solve")] + [(n, C.c_int64) for n in ("n_surfels", "n_sld_corr", "n_fix_corr", "n_launches")]
 
 
+class SweepFilter(C.Structure):
+    """wc_sweep_filter: lidar -> IMU extrinsic, range limits and blind box (lio_config.h:18-30)."""
+
+    _fields_ = [("ext_q", C.c_double * 4), ("ext_t", C.c_double * 3), ("min_range", C.c_double), ("max_range", C.c_double),
+                ("blind_box_min", C.c_double * 3), ("blind_box_max", C.c_double * 3)]
+
+
+def default_sweep_filter() -> SweepFilter:
+    """Python-side copy of wc_default_sweep_filter (lio_config.h:18-30); the quaternion is Eigen's conversion of the
+    rotation matrix [[-5.32125e-08, -1, 0], [-1, -5.32125e-08, 0], [0, 0, -1]] (trace <= 0 branch, i = 0)."""
+    import math
+
+    f = SweepFilter()
+    t = math.sqrt(-5.32125e-08 - -5.32125e-08 - -1.0 + 1.0)
+    f.ext_q[:] = [0.5 * t, (-1.0 + -1.0) * (0.5 / t), 0.0, 0.0]
+    f.ext_t[:] = [-0.001, -0.00855, 0.055]
+    f.min_range, f.max_range = 0.3, 120.0
+    f.blind_box_min[:] = [-0.8, -0.5, -0.4]
+    f.blind_box_max[:] = [0.3, 0.5, 0.4]
+    return f
+
+
 def default_params() -> Params:
     """Python-side copy of wc_default_params (the library's own is checked against this in tests).
 
