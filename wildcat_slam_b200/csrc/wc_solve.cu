@@ -28,7 +28,7 @@ void      wc_comm_partial_views(wc_ctx* c, double** H, double** g, double** cost
 namespace {
 
 constexpr int REC_COLS = 16;
-constexpr int LT       = 256;       // linearize tile = threads per CTA
+constexpr int LT       = 128;       // linearize tile = threads per CTA (43 KB of shared memory: 4-5 CTAs per SM)
 constexpr int JR       = 28;        // augmented row count: 24 Jacobian columns, residual, 3 pad
 constexpr int JS       = LT + 1;    // padded row stride (doubles)
 constexpr int NGRP     = LT / 32;
@@ -1313,7 +1313,8 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
   a.rec = m->rec, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
   a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
   const int ntiles  = (int)((c->n_rec + LT - 1) / LT);
-  const int n_lidar = ntiles < c->num_sms ? ntiles : c->num_sms;
+  // one tile per CTA while that stays within a few waves (the SMs hold 4-5 tiles each); beyond that, contiguous chunks
+  const int n_lidar = ntiles <= 8 * c->num_sms ? ntiles : 4 * c->num_sms;
   ImuArgs b;
   memset(&b, 0, sizeof(b));
   int n_imu_cta = 0;
