@@ -245,8 +245,8 @@ __device__ __forceinline__ bool cand_less(double d, int id, double dk, int ik) {
 #ifdef WC_KNN_STATS
 __device__ unsigned long long g_knn_stats[8];  // queries, phase-1 queries, members scanned (phase 0 / 1), cells scanned in phase 1, inserts
 __global__ void knn_stats_print() {
-  printf("knn stats: queries %llu phase1 %llu members p0 %llu p1 %llu p1-cells-taken %llu inserts %llu\n", g_knn_stats[0], g_knn_stats[1],
-         g_knn_stats[2], g_knn_stats[3], g_knn_stats[4], g_knn_stats[5]);
+  printf("knn stats: queries %llu ring2 %llu phase1 %llu members p0 %llu p0.5+p1 %llu p1-cells-taken %llu inserts %llu\n", g_knn_stats[0],
+         g_knn_stats[6], g_knn_stats[1], g_knn_stats[2], g_knn_stats[3], g_knn_stats[4], g_knn_stats[5]);
   for (int i = 0; i < 8; ++i) g_knn_stats[i] = 0;
 }
 #define KSTAT(i, v) do { if (lane == 0) atomicAdd(&g_knn_stats[i], (unsigned long long)(v)); } while (0)
@@ -320,55 +320,80 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
     const bool      rings_ok = fabs(cfx) < 1e6 && fabs(cfy) < 1e6 && fabs(cfz) < 1e6;
     const long long ix = rings_ok ? (long long)cfx : 0, iy = rings_ok ? (long long)cfy : 0, iz = rings_ok ? (long long)cfz : 0;
     bool            done = false;
+    int             ring = 1;  // half-width of the cube of cells already scanned
     if (rings_ok) {
-      // phase 0: lane l < 27 probes one cell of the 3 x 3 x 3 block; lane 0 takes the query's own cell so that its members
-      // come first and tighten the k-th distance early
-      int c0 = 0, cn = 0;
-      if (lane < 27) {
-        const int                cc  = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
-        const unsigned long long key = cell_key(ix + cc % 3 - 1, iy + (cc / 3) % 3 - 1, iz + cc / 9 - 1);
-        unsigned long long       h   = mix64(key) & G.mask;
-        for (;; h = (h + 1) & G.mask) {
-          const unsigned long long kk = G.keys[h];
-          if (kk == key) {
-            const int id = G.cid[h];
-            c0 = G.off[id], cn = G.off[id + 1] - c0;
-            break;
+      // probe one cell per lane (cn = 0 for absent cells), then scan the members of all 32 lanes' cells as ONE flat
+      // index space (inclusive prefix of the cell sizes over the lanes): every step scans 32 members regardless of how
+      // they are spread over the cells
+      auto probe_and_scan = [&](bool active, int dx, int dy, int dz) {
+        int c0 = 0, cn = 0;
+        if (active) {
+          const unsigned long long key = cell_key(ix + dx, iy + dy, iz + dz);
+          unsigned long long       h   = mix64(key) & G.mask;
+          for (;; h = (h + 1) & G.mask) {
+            const unsigned long long kk = G.keys[h];
+            if (kk == key) {
+              const int id = G.cid[h];
+              c0 = G.off[id], cn = G.off[id + 1] - c0;
+              break;
+            }
+            if (kk == WC_CELL_EMPTY) break;
           }
-          if (kk == WC_CELL_EMPTY) break;
         }
-      }
-      // the members of the 27 cells form ONE flat index space (inclusive prefix of the cell sizes over the lanes): every
-      // step scans 32 members regardless of how they are spread over the cells
-      int incl = cn;
+        int incl = cn;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      const int excl  = incl - cn;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl  = incl - cn;
+        KSTAT(2 + kphase, total);
 #pragma unroll 1
-      for (int base = 0; base < total; base += 32) {
-        const int g  = base + lane;
-        int       lo = 0;  // last cell whose exclusive prefix is <= g
+        for (int base = 0; base < total; base += 32) {
+          const int g  = base + lane;
+          int       lo = 0;  // last cell whose exclusive prefix is <= g
 #pragma unroll
-        for (int stp = 16; stp > 0; stp >>= 1) {
-          const int pv = __shfl_sync(0xffffffffu, excl, lo + stp);  // (lo + stp <= 31)
-          if (pv <= g) lo += stp;
+          for (int stp = 16; stp > 0; stp >>= 1) {
+            const int pv = __shfl_sync(0xffffffffu, excl, lo + stp);  // (lo + stp <= 31)
+            if (pv <= g) lo += stp;
+          }
+          const int ce = __shfl_sync(0xffffffffu, excl, lo), cs = __shfl_sync(0xffffffffu, c0, lo);
+          scan_batch(g < total ? cs + (g - ce) : -1);
         }
-        const int ce = __shfl_sync(0xffffffffu, excl, lo), cs = __shfl_sync(0xffffffffu, c0, lo);
-        scan_batch(g < total ? cs + (g - ce) : -1);
+      };
+      // phase 0: the 3 x 3 x 3 block; lane 0 takes the query's own cell so that its members come first and tighten the
+      // k-th distance early
+      {
+        const int cc = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
+        probe_and_scan(lane < 27, cc % 3 - 1, (cc / 3) % 3 - 1, cc / 9 - 1);
       }
-      const double b = fmin(fmin(fmin(f[0] - (cfx - 1), (cfx + 2) - f[0]), fmin(f[1] - (cfy - 1), (cfy + 2) - f[1])),
-                            fmin(f[2] - (cfz - 1), (cfz + 2) - f[2]));
+      double b = fmin(fmin(fmin(f[0] - (cfx - 1), (cfx + 2) - f[0]), fmin(f[1] - (cfy - 1), (cfy + 2) - f[1])),
+                      fmin(f[2] - (cfz - 1), (cfz + 2) - f[2]));
       done = worst < b * b * (1.0 - 1e-12);
+      if (!done) {
+        // phase 0.5: the shell of the 5 x 5 x 5 block (98 cells, four rounds of 32 lanes over the 125 offsets) — for a
+        // sparse target set this settles most queries before the global box scan
+        KSTAT(6, 1);
+        kphase = 1;
+#pragma unroll 1
+        for (int rnd = 0; rnd < 4; ++rnd) {
+          const int  o  = rnd * 32 + lane;
+          const int  dx = o % 5 - 2, dy = (o / 5) % 5 - 2, dz = o / 25 - 2;
+          const bool shell = o < 125 && (abs(dx) == 2 || abs(dy) == 2 || abs(dz) == 2);
+          probe_and_scan(shell, dx, dy, dz);
+        }
+        ring = 2;
+        b    = fmin(fmin(fmin(f[0] - (cfx - 2), (cfx + 3) - f[0]), fmin(f[1] - (cfy - 2), (cfy + 3) - f[1])),
+                    fmin(f[2] - (cfz - 2), (cfz + 3) - f[2]));
+        done = worst < b * b * (1.0 - 1e-12);
+      }
     }
     KSTAT(0, 1);
     if (!done) {
       KSTAT(1, 1);
       kphase = 1;
-      // phase 1: box-test the remaining cells 32 at a time, scan the survivors one by one
+      // phase 1: box-test the cells outside the scanned cube 32 at a time, scan the survivors one by one
 #pragma unroll 1
       for (int cb = 0; cb < nc; cb += 32) {
         const int cell = cb + lane;
@@ -380,7 +405,7 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
             const unsigned long long key = G.ckey[cell];
             const long long cx = (long long)(key >> 42) - (1 << 20), cy = (long long)((key >> 21) & 0x1fffff) - (1 << 20),
                             cz = (long long)(key & 0x1fffff) - (1 << 20);
-            visited = llabs(cx - ix) <= 1 && llabs(cy - iy) <= 1 && llabs(cz - iz) <= 1;
+            visited = llabs(cx - ix) <= ring && llabs(cy - iy) <= ring && llabs(cz - iz) <= ring;
           }
           if (!visited) {
             const double* bx = G.cbox + (size_t)cell * 12;
