@@ -68,6 +68,8 @@ struct wc_ctx {
   int          device;
   int          num_sms;
   cudaStream_t stream;
+  cudaStream_t side[2];   // side streams for independent launches inside one call (fork / join by events)
+  cudaEvent_t  ev_fork, ev_join[2];
   cudaEvent_t  ev[8];
   char         err[512];
   long long    n_launches;  // kernels launched so far (bench.py's gpu_launches)
@@ -97,10 +99,14 @@ struct wc_ctx {
   unsigned long long* d_sort_hi;
   unsigned long long* d_sort_lo;
   unsigned int*       d_sort_idx;
+  unsigned int*       d_sort_perm;  // surfel ids grouped by time bucket
+  int*                d_bcnt;       // per time bucket: count / offset / cursor
+  int*                d_boff;
+  int*                d_bcur;
   wc_point_assign*    d_assign;
   size_t              n_surfels;
   int                 vox0[3];
-  double              t_first;
+  double              t_first, t_last;
   int                 want_assign;
   int                 last_slots, last_voxels;
 

@@ -380,7 +380,13 @@ struct EmitParams {
   int    cmin;       // cluster_min_points
   int    max_layer;
   int    surf_cap;
+  double bscale;     // time buckets of the final sort: bucket = (t - t_first) * bscale, clamped to [0, SORT_NB)
 };
+constexpr int SORT_NB = 4096;
+__device__ __forceinline__ int sort_bucket(double t, double t_first, double bscale) {
+  const double b = (t - t_first) * bscale;  // monotone in t: buckets never contradict the exact key order
+  return b >= (double)(SORT_NB - 1) ? SORT_NB - 1 : (b > 0.0 ? (int)b : 0);
+}
 
 // moments about the voxel centre, fp64: n, s[3], ss[6]
 struct Mom {
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(NT)
 cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg, const int* __restrict__ vox_off,
                  const unsigned long long* __restrict__ vox_key, wc_extract_status* __restrict__ st, EmitParams P, int e_lo,
                  wc_surfel* __restrict__ out, unsigned long long* __restrict__ sort_hi,
-                 unsigned long long* __restrict__ sort_lo) {
+                 unsigned long long* __restrict__ sort_lo, int* __restrict__ bcnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned*      skey    = reinterpret_cast<unsigned*>(smem_raw);      // ECAP sort words: levelkey<<14 | entry
   unsigned*      leafbin = skey + ECAP;                                // ECAP
@@ -740,6 +746,7 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
         out[idx]     = s;
         sort_hi[idx] = OrderedBits(tmean);
         sort_lo[idx] = ((unsigned long long)level << 62) | (OrderedBits(cxw) >> 2);
+        atomicAdd(&bcnt[sort_bucket(tmean, P.t_first, P.bscale)], 1);
         (void)lk0;
       }
       __syncthreads();
@@ -764,6 +771,11 @@ __global__ void extract_cleanup(const wc_extract_status* __restrict__ st, unsign
 }
 
 // ---------------------------------------------------------------------------------------------- final sort
+// std::sort(surfels by timestamp) (surfel_extraction.cc:334) as a bucket sort: the emit kernels count the surfels per
+// time bucket (SORT_NB uniform buckets over the sweep; the bucket map is monotone in the timestamp), one CTA scans the
+// counts, the surfel ids are scattered into their buckets, and one warp per bucket orders its handful of entries by the
+// exact key (timestamp bits, then level / centre.x bits, then emission id) by rank counting.  Four launches instead of
+// a 20-launch global bitonic network.
 struct SortRec {
   unsigned long long hi, lo;
   unsigned           idx;
@@ -774,54 +786,76 @@ __device__ __forceinline__ bool rec_less(const SortRec& a, const SortRec& b) {
   return a.idx < b.idx;
 }
 
-// sorts tiles of 2048 in shared memory: all (k, j) steps with k <= 2048 when first != 0, otherwise the tail
-// j < 2048 of the merge step k_global
-__global__ void __launch_bounds__(1024)
-sort_tile(unsigned long long* hi, unsigned long long* lo, unsigned* idx, int n_pad, int k_global) {
-  __shared__ unsigned long long shi[2048], slo[2048];
-  __shared__ unsigned           sidx[2048];
-  const int base = blockIdx.x * 2048;
-  for (int i = threadIdx.x; i < 2048; i += 1024) shi[i] = hi[base + i], slo[i] = lo[base + i], sidx[i] = idx[base + i];
+__global__ void __launch_bounds__(1024) bsort_scan(const int* __restrict__ bcnt, int* __restrict__ boff, int* __restrict__ bcur) {
+  __shared__ int warp_sums[32];
+  const int t = threadIdx.x, lane = t & 31;
+  int       v[SORT_NB / 1024], tot = 0;
+#pragma unroll
+  for (int k = 0; k < SORT_NB / 1024; ++k) v[k] = bcnt[t * (SORT_NB / 1024) + k], tot += v[k];
+  int incl = tot;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) warp_sums[t >> 5] = incl;
   __syncthreads();
-  const int k_begin = k_global ? k_global : 2, k_end = k_global ? k_global : 2048;
-  for (int k = k_begin; k <= k_end; k <<= 1) {
-    for (int j = min(k >> 1, 1024); j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < 1024; t += 1024) {
-        const int i   = 2 * t - (t & (j - 1));  // index with bit j clear
-        const int ixj = i + j;
-        const bool up = ((base + i) & k) == 0;
-        SortRec a{shi[i], slo[i], sidx[i]}, b{shi[ixj], slo[ixj], sidx[ixj]};
-        if (rec_less(b, a) == up) {
-          shi[i] = b.hi, slo[i] = b.lo, sidx[i] = b.idx;
-          shi[ixj] = a.hi, slo[ixj] = a.lo, sidx[ixj] = a.idx;
-        }
-      }
-      __syncthreads();
+  if (t < 32) {
+    const int w  = warp_sums[t];
+    int       wi = w;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (t >= d) wi += o;
     }
-    if (k_global) break;
+    warp_sums[t] = wi - w;
   }
-  for (int i = threadIdx.x; i < 2048; i += 1024) hi[base + i] = shi[i], lo[base + i] = slo[i], idx[base + i] = sidx[i];
-  (void)n_pad;
-}
-// one global compare-exchange step (j >= 2048)
-__global__ void sort_global_step(unsigned long long* hi, unsigned long long* lo, unsigned* idx, int n_pad, int k, int j) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_pad / 2) return;
-  const int  i   = 2 * t - (t & (j - 1));
-  const int  ixj = i + j;
-  const bool up  = (i & k) == 0;
-  SortRec    a{hi[i], lo[i], idx[i]}, b{hi[ixj], lo[ixj], idx[ixj]};
-  if (rec_less(b, a) == up) {
-    hi[i] = b.hi, lo[i] = b.lo, idx[i] = b.idx;
-    hi[ixj] = a.hi, lo[ixj] = a.lo, idx[ixj] = a.idx;
+  __syncthreads();
+  int run = warp_sums[t >> 5] + incl - tot;
+#pragma unroll
+  for (int k = 0; k < SORT_NB / 1024; ++k) {
+    boff[t * (SORT_NB / 1024) + k] = run, bcur[t * (SORT_NB / 1024) + k] = 0;
+    run += v[k];
   }
+  if (t == 1023) boff[SORT_NB] = run;
 }
-__global__ void sort_pad(unsigned long long* hi, unsigned long long* lo, unsigned* idx, int n, int n_pad) {
+
+__global__ void bsort_scatter(const unsigned long long* __restrict__ hi, int n, double t_first, double bscale,
+                              const int* __restrict__ boff, int* __restrict__ bcur, unsigned* __restrict__ perm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  if (i >= n) hi[i] = ~0ull, lo[i] = ~0ull;
-  idx[i] = (unsigned)i;
+  if (i >= n) return;
+  const int b = sort_bucket(FromOrderedBits(hi[i]), t_first, bscale);
+  perm[boff[b] + atomicAdd(&bcur[b], 1)] = (unsigned)i;
 }
+
+// one warp per bucket: out_idx[boff[b] + rank] = id, rank = number of bucket entries with a smaller exact key
+__global__ void __launch_bounds__(256)
+bsort_rank(const unsigned long long* __restrict__ hi, const unsigned long long* __restrict__ lo, const int* __restrict__ boff,
+           const unsigned* __restrict__ perm, int* __restrict__ bcnt, unsigned* __restrict__ out_idx) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= SORT_NB) return;
+  const int p0 = boff[b], m = boff[b + 1] - p0;
+  if (lane == 0) bcnt[b] = 0;  // leave the counters clean for the next call
+  for (int base = 0; base < m; base += 32) {
+    const int e = base + lane;
+    SortRec   me{~0ull, ~0ull, ~0u};
+    if (e < m) me.idx = perm[p0 + e], me.hi = hi[me.idx], me.lo = lo[me.idx];
+    int rank = 0;
+    for (int cb = 0; cb < m; cb += 32) {  // all entries of the bucket, 32 at a time through the lanes
+      const int c = cb + lane;
+      SortRec   ot{~0ull, ~0ull, ~0u};
+      if (c < m) ot.idx = perm[p0 + c], ot.hi = hi[ot.idx], ot.lo = lo[ot.idx];
+      const int lim = min(32, m - cb);
+      for (int j = 0; j < lim; ++j) {
+        SortRec o;
+        o.hi  = __shfl_sync(0xffffffffu, ot.hi, j);
+        o.lo  = __shfl_sync(0xffffffffu, ot.lo, j);
+        o.idx = __shfl_sync(0xffffffffu, ot.idx, j);
+        rank += rec_less(o, me);
+      }
+    }
+    if (e < m) out_idx[p0 + rank] = me.idx;
+  }
+}
+
 __global__ void gather_surfels(const wc_surfel* __restrict__ in, const unsigned* __restrict__ idx, int n,
                                wc_surfel* __restrict__ out) {
   // 13 x 16-byte chunks per surfel; consecutive threads move consecutive chunks
@@ -861,6 +895,11 @@ static wc_status extract_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&c->d_sort_hi, sc * 8));
   WC_CUDA(c, cudaMalloc(&c->d_sort_lo, sc * 8));
   WC_CUDA(c, cudaMalloc(&c->d_sort_idx, sc * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_sort_perm, sc * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_bcnt, SORT_NB * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_boff, (SORT_NB + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_bcur, SORT_NB * 4));
+  WC_CUDA(c, cudaMemsetAsync(c->d_bcnt, 0, SORT_NB * 4, c->stream));
   WC_CUDA(c, cudaMalloc(&c->d_assign, np * sizeof(wc_point_assign)));
   WC_CUDA(c, cudaMemsetAsync(c->d_vkeys, 0xff, c->vcap * 8, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vslot, 0xff, c->vcap * 4, c->stream));
@@ -875,7 +914,7 @@ static wc_status extract_alloc(wc_ctx* c) {
 void wc_extract_free(wc_ctx* c) {
   void* ptrs[] = {c->d_raw,     c->d_xyz,      c->d_time,    c->d_htab,   c->d_slots,    c->d_vkeys,
                   c->d_vslot,   c->d_vox_count, c->d_vox_off, c->d_vox_cursor, c->d_vox_key, c->d_vox_hpos, c->d_seg,   c->d_xstat,
-                  c->d_surf_raw, c->d_surf,    c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, c->d_assign};
+                  c->d_surf_raw, c->d_surf,    c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, c->d_assign, c->d_sort_perm, c->d_bcnt, c->d_boff, c->d_bcur};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_xstat) cudaFreeHost(c->h_xstat);
@@ -894,7 +933,7 @@ extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n
   // voxel of the first point / first timestamp anchor the relative keys (host copy of element 0 is at hand)
   const double vs = (double)c->prm.voxel_size;
   c->vox0[0] = (int)floor((double)pts[0].x / vs), c->vox0[1] = (int)floor((double)pts[0].y / vs), c->vox0[2] = (int)floor((double)pts[0].z / vs);
-  c->t_first = pts[0].time;
+  c->t_first = pts[0].time, c->t_last = pts[n - 1].time;
   WC_CUDA(c, cudaStreamSynchronize(c->stream));
   return WC_OK;
 }
@@ -938,13 +977,23 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   for (int k = 0; k < 3; ++k) E.view[k] = c->prm.view_point[k], E.vox0[k] = c->vox0[k], E.lps[k] = c->prm.layer_point_size[k];
   E.cmin = c->prm.cluster_min_points, E.max_layer = c->prm.max_layer;
   E.surf_cap = (int)c->prm.max_surfels;
+  E.bscale   = c->t_last > c->t_first ? (double)SORT_NB / (c->t_last - c->t_first) : 0.0;
+  // the three entry-count tiers are independent (surfel slots are claimed by an atomic counter): they run concurrently
+  // on the main stream and two side streams, so the small tiers fill the SMs the large tier's tail leaves idle
   c->n_launches += 3;
-  cluster_eig_emit<128, 64, true><<<c->num_sms * 12, 64, 128 * (16 + 8 * REC), st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 0,
-                                                                                     c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+  WC_CUDA(c, cudaEventRecord(c->ev_fork, st));
+  WC_CUDA(c, cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
+  WC_CUDA(c, cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
   cluster_eig_emit<512, 128, true><<<c->num_sms * 3, 128, 512 * (16 + 8 * REC), st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat,
-                                                                                        E, 128, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
-  cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E, 512,
-                                                                         c->d_surf_raw, c->d_sort_hi, c->d_sort_lo);
+                                                                                        E, 128, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
+  cluster_eig_emit<128, 64, true><<<c->num_sms * 12, 64, 128 * (16 + 8 * REC), c->side[0]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key,
+                                                                                              c->d_xstat, E, 0, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
+  cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, c->side[1]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
+                                                                                 512, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
+  WC_CUDA(c, cudaEventRecord(c->ev_join[0], c->side[0]));
+  WC_CUDA(c, cudaEventRecord(c->ev_join[1], c->side[1]));
+  WC_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
+  WC_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
   WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
   { ++c->n_launches; extract_cleanup<<<c->num_sms, 256, 0, st>>>(c->d_xstat, c->d_vkeys, c->d_vslot, c->d_vox_hpos, c->d_vox_count,
                                               c->d_vox_cursor); }
@@ -958,16 +1007,11 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   c->n_surfels = (size_t)S;
   c->last_slots = hs.n_slots, c->last_voxels = hs.n_voxels;
   if (S > 0) {
-    int n_pad = 2048;
-    while (n_pad < S) n_pad <<= 1;
-    { ++c->n_launches; sort_pad<<<(n_pad + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, S, n_pad); }
-    { ++c->n_launches; sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, 0); }
-    for (int k = 4096; k <= n_pad; k <<= 1) {
-      for (int j = k >> 1; j >= 2048; j >>= 1)
-        { ++c->n_launches; sort_global_step<<<(n_pad / 2 + 255) / 256, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k, j); }
-      { ++c->n_launches; sort_tile<<<n_pad / 2048, 1024, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, n_pad, k); }
-    }
-    { ++c->n_launches; gather_surfels<<<(S * 13 + 255) / 256, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, S, c->d_surf); }
+    c->n_launches += 4;
+    bsort_scan<<<1, 1024, 0, st>>>(c->d_bcnt, c->d_boff, c->d_bcur);
+    bsort_scatter<<<(S + 255) / 256, 256, 0, st>>>(c->d_sort_hi, S, E.t_first, E.bscale, c->d_boff, c->d_bcur, c->d_sort_perm);
+    bsort_rank<<<SORT_NB / 8, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_boff, c->d_sort_perm, c->d_bcnt, c->d_sort_idx);
+    gather_surfels<<<(S * 13 + 255) / 256, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, S, c->d_surf);
   }
   WC_CUDA(c, cudaEventRecord(c->ev[3], st));
   WC_CUDA(c, cudaStreamSynchronize(st));

@@ -281,6 +281,6 @@ extern "C" wc_status wc_undistort_upload(wc_ctx* c, const wc_imu_state* imu, siz
   const double vs = (double)c->prm.voxel_size;
   c->vox0[0] = (int)floor((double)m->h_first->x / vs), c->vox0[1] = (int)floor((double)m->h_first->y / vs),
   c->vox0[2] = (int)floor((double)m->h_first->z / vs);
-  c->t_first = in[0].time;
+  c->t_first = in[0].time, c->t_last = in[n - 1].time;
   return WC_OK;
 }
