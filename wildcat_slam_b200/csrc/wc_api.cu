@@ -94,7 +94,7 @@ extern "C" wc_status wc_create(const wc_params* p, int device, wc_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(c); return WC_ECUDA; }
   c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : WC_NUM_SMS_FALLBACK;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { free(c); return WC_ECUDA; }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 3; ++i)
     if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { free(c); return WC_ECUDA; }
   if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { free(c); return WC_ECUDA; }
@@ -120,7 +120,7 @@ extern "C" void wc_destroy(wc_ctx* c) {
   wc_spline_free(c);
   wc_sweep_free(c);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
-  for (int i = 0; i < 2; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]);
+  for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]);
   cudaEventDestroy(c->ev_fork);
   cudaStreamDestroy(c->stream);
   free(c);

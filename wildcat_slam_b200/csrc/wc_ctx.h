@@ -68,8 +68,8 @@ struct wc_ctx {
   int          device;
   int          num_sms;
   cudaStream_t stream;
-  cudaStream_t side[2];   // side streams for independent launches inside one call (fork / join by events)
-  cudaEvent_t  ev_fork, ev_join[2];
+  cudaStream_t side[3];   // side streams for independent launches inside one call (fork / join by events)
+  cudaEvent_t  ev_fork, ev_join[3];
   cudaEvent_t  ev[8];
   char         err[512];
   long long    n_launches;  // kernels launched so far (bench.py's gpu_launches)

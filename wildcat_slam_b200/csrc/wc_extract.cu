@@ -982,18 +982,20 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   // on the main stream and two side streams, so the small tiers fill the SMs the large tier's tail leaves idle
   c->n_launches += 3;
   WC_CUDA(c, cudaEventRecord(c->ev_fork, st));
-  WC_CUDA(c, cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
-  WC_CUDA(c, cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
+  for (int i = 0; i < 3; ++i) WC_CUDA(c, cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+  c->n_launches += 1;
   cluster_eig_emit<512, 128, true><<<c->num_sms * 3, 128, 512 * (16 + 8 * REC), st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat,
-                                                                                        E, 128, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
+                                                                                        E, 256, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
+  cluster_eig_emit<256, 128, true><<<c->num_sms * 6, 128, 256 * (16 + 8 * REC), c->side[2]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key,
+                                                                                                c->d_xstat, E, 128, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
   cluster_eig_emit<128, 64, true><<<c->num_sms * 12, 64, 128 * (16 + 8 * REC), c->side[0]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key,
-                                                                                              c->d_xstat, E, 0, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
+                                                                                               c->d_xstat, E, 0, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
   cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, c->side[1]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
                                                                                  512, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
-  WC_CUDA(c, cudaEventRecord(c->ev_join[0], c->side[0]));
-  WC_CUDA(c, cudaEventRecord(c->ev_join[1], c->side[1]));
-  WC_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
-  WC_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
+  for (int i = 0; i < 3; ++i) {
+    WC_CUDA(c, cudaEventRecord(c->ev_join[i], c->side[i]));
+    WC_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[i], 0));
+  }
   WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
   { ++c->n_launches; extract_cleanup<<<c->num_sms, 256, 0, st>>>(c->d_xstat, c->d_vkeys, c->d_vslot, c->d_vox_hpos, c->d_vox_count,
                                               c->d_vox_cursor); }
