@@ -263,15 +263,36 @@ def main():
             d2h = ns * 208 * 2 + (len(cs) + len(cf)) * 9 + K * 96 + 2400
             return dt, sg.num_iterations, h2d, d2h
 
-        for _ in range(2):
-            e2e_step()
-        tot, its, h2d, d2h = 0.0, 0, 0, 0
-        for _ in range(args.steps):
-            dt, it, h2d, d2h = e2e_step()
-            tot += dt
-            its += it
-        e2e = {"value": its / tot, "unit": "LM iterations/s (whole window pass)", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * tot / args.steps}
+        def e2e_chain_step():
+            """the integration INTEGRATION.md section 3 recommends: host buffers in, corrections out, one chain of C-ABI
+            calls (wc_points_upload + wc_pass_upload + wc_window_pass_resident) — every step uploads the sweep again."""
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rp2 = od.ResidentPass(pts, w.imu, w.samples, fix_p, ctx=ctx2)   # H2D: 48-byte points, IMU / sample states, fixed window
+            x2, sg2, st2 = rp2.run()                                        # D2H: corrections + summary
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            h2d = N * 48 + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + len(fix) * 208
+            d2h = K * 96 + 2400
+            return dt, sg2.num_iterations, h2d, d2h
+
+        def measure(step_fn):
+            for _ in range(2):
+                step_fn()
+            tot, its, h2d, d2h = 0.0, 0, 0, 0
+            for _ in range(args.steps):
+                dt, it, h2d, d2h = step_fn()
+                tot += dt
+                its += it
+            return {"value": its / tot, "unit": "LM iterations/s (whole window pass)", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * tot / args.steps}
+
+        e2e = measure(e2e_chain_step)
+        e2e["api"] = "wc_points_upload + wc_pass_upload + wc_window_pass_resident (host buffers in, corrections out)"
+        e2e["per_call_api"] = measure(e2e_step)
+        e2e["per_call_api"]["api"] = ("wc_build_surfels, wc_update_surfel_poses, wc_match x2, wc_window_solve: the reference's five entry points "
+                                      "one by one, surfels and correspondences cross PCIe between the calls")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
