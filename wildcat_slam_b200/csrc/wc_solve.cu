@@ -546,11 +546,13 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
   }
 }
 
-// lidar tiles on the first n_lidar CTAs, IMU triplets on the rest: one launch per linearisation
-__global__ void __launch_bounds__(LT) window_linearize(LinArgs a, ImuArgs b, int n_lidar) {
+// IMU triplets on the first n_imu CTAs, lidar tiles on the rest: one launch per linearisation.  The IMU warps run long
+// serial chains (Log / Exp / 12 x 36 Jacobians per triplet); scheduled first, they overlap with the lidar tiles
+// instead of forming the kernel's tail.
+__global__ void __launch_bounds__(LT) window_linearize(LinArgs a, ImuArgs b, int n_lidar, int n_imu) {
   extern __shared__ __align__(16) double sm[];
-  if ((int)blockIdx.x < n_lidar) lidar_linearize_body(a, sm, blockIdx.x, n_lidar);
-  else imu_linearize_body(b, sm, blockIdx.x - n_lidar);
+  if ((int)blockIdx.x < n_imu) imu_linearize_body(b, sm, blockIdx.x);
+  else lidar_linearize_body(a, sm, blockIdx.x - n_imu, n_lidar);
 }
 
 // ------------------------------------------------------------------------------------------------ K7
@@ -1318,14 +1320,15 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
   ImuArgs b;
   memset(&b, 0, sizeof(b));
   int n_imu_cta = 0;
-  if (o->use_imu_factors && c->n_imu >= 3 && c->rank == 0) {
+  static const int dbg_no_imu = getenv("WC_DBG_NO_IMU") != nullptr;  // timing experiment only
+  if (o->use_imu_factors && c->n_imu >= 3 && c->rank == 0 && !dbg_no_imu) {
     b.imu = c->d_imu, b.n_imu = (int)c->n_imu, b.ts = m->ts, b.K = (int)c->K, b.B = B, b.at_candidate = at_candidate;
     b.wg = c->prm.weight_gyr, b.wa = c->prm.weight_acc, b.wbg = c->prm.weight_bg, b.wba = c->prm.weight_ba;
     b.dt = 1.0 / c->prm.imu_rate;
     for (int k = 0; k < 3; ++k) b.grav[k] = m->grav[k];
     n_imu_cta = (int)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS);
   }
-  if (n_lidar + n_imu_cta > 0) { ++c->n_launches; window_linearize<<<n_lidar + n_imu_cta, LT, LIN_SMEM, st>>>(a, b, n_lidar); }
+  if (n_lidar + n_imu_cta > 0) { ++c->n_launches; window_linearize<<<n_lidar + n_imu_cta, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }
