@@ -346,3 +346,22 @@ def test_c3_full_size_properties(od, ctx):
     err0 = np.linalg.norm(w.samples["pos"][-1] - w.truth_sample_pos[-1])
     err1 = np.linalg.norm(w.samples["pos"][-1] + smp["data_cor"][-1, 3:6] - w.truth_sample_pos[-1])
     assert err1 < 0.1 * err0
+
+
+def test_solve_wide_system_64_control_poses(od, ctx, oracle):
+    """BASELINE config 5 shape in small: 64 control poses (12 * 64 - 3 = 765 unknowns).  The LM system no longer fits
+    shared memory, so the Cholesky runs out of global memory (lm_step<false>) with the CTA-wide backward sweep."""
+    import dataclasses
+
+    w = S.make_window(dataclasses.replace(S.CONFIGS["C2"], name="C2K64", K=64))
+    g = od.BuildSurfels(w.points, ctx=ctx)
+    sld = od.UpdateSurfelPoses(w.imu, g, ctx=ctx)
+    fix = od.UpdateSurfelPoses(w.fix_imu, od.BuildSurfels(w.fix_points, ctx=ctx), ctx=ctx)
+    m = od.KnnSurfelMatcher(ctx); m.BuildIndex(sld); cs, _ = m.Match(sld)
+    m2 = od.KnnSurfelMatcher(ctx); m2.BuildIndex(fix); cf, _ = m2.Match(sld)
+    smp, sg = od.SolveWindow(sld, fix, cs, cf, w.imu, w.samples, ctx=ctx)
+    st, smp_o, so = oracle.window_solve(sld, fix, cs, cf, w.imu, w.samples)
+    assert st == 0 and len(w.samples) == 64
+    assert sg.num_iterations == so.num_iterations and sg.termination == so.termination
+    assert abs(sg.final_cost / so.final_cost - 1) < TOL_COST_REL
+    np.testing.assert_allclose(smp["data_cor"], smp_o["data_cor"], rtol=0, atol=TOL_X)

@@ -828,7 +828,7 @@ __device__ __forceinline__ void chol_trailing_tiles(double* A, int LD, int Dp, i
 __device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fail) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, LD = chol_ld(Dp);
 #ifdef WC_LM_TIMING
-  long long c_p1 = 0, c_p2 = 0, c0;
+  long long c_p1 = 0, c_p2 = 0, c_fact = 0, c0;
 #endif
   if (warp == 0) chol_factor_diag(A, LD, 0, rinv, s_fail);
   __syncthreads();
@@ -850,13 +850,17 @@ __device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fai
     WC_TOCK(c_p1);
     if (r0 >= Dp) break;  // last block column: only the right-hand-side row remained
     WC_TICK();
-    if (warp == 0) chol_factor_diag(A, LD, r0, rinv + r0, s_fail);
-    else chol_trailing_tiles(A, LD, Dp, k0, r0, warp - 1, LMT / 32 - 1);
+    if (warp == 0) {
+      chol_factor_diag(A, LD, r0, rinv + r0, s_fail);
+#ifdef WC_LM_TIMING
+      c_fact += clock64() - c0;
+#endif
+    } else chol_trailing_tiles(A, LD, Dp, k0, r0, warp - 1, LMT / 32 - 1);
     __syncthreads();
     WC_TOCK(c_p2);
   }
 #ifdef WC_LM_TIMING
-  if (t == 0) printf("chol cycles: phase1 (panel, diag update, factor) %lld phase2 (trailing) %lld\n", c_p1, c_p2);
+  if (t == 0) printf("chol cycles: phase1 (panel, diag update) %lld phase2 %lld of which warp 0's factor %lld\n", c_p1, c_p2, c_fact);
 #endif
 }
 
@@ -887,11 +891,11 @@ __device__ __forceinline__ void backward_sweep(const double* A, int LD, int D, i
     if (lane == jj && j < D) y[j] = -xj;
   }
 }
-__device__ void chol_backward_warp(const double* A, int D, int Dp, const double* rinv, double* y) {
+__device__ void chol_backward_warp(double* A, int D, int Dp, const double* rinv, double* y) {
   const int LD = chol_ld(Dp), lane = threadIdx.x & 31;
-  if (threadIdx.x >= 32) return;
-  const double* zrow = A + (size_t)Dp * LD;
+  double*   zrow = A + (size_t)Dp * LD;
   if (Dp <= 32 * BS_SLOTS) {
+    if (threadIdx.x >= 32) return;
     double z[BS_SLOTS];
 #pragma unroll
     for (int s = 0; s < BS_SLOTS; ++s) z[s] = (32 * s + lane < Dp) ? zrow[32 * s + lane] : 0.0;
@@ -903,12 +907,14 @@ __device__ void chol_backward_warp(const double* A, int D, int Dp, const double*
     backward_sweep<2>(A, LD, D, Dp, rinv, z, y);
     backward_sweep<1>(A, LD, D, Dp, rinv, z, y);
     backward_sweep<0>(A, LD, D, Dp, rinv, z, y);
-  } else if (lane == 0) {
-    double* z = const_cast<double*>(zrow);
+  } else {
+    // wide systems (K > 21 control poses): column sweep by the whole CTA, one barrier per column
     for (int j = Dp - 1; j >= 0; --j) {
-      const double xj = z[j] * rinv[j];
-      for (int i = 0; i < j; ++i) z[i] = fma(-A[(size_t)j * LD + i], xj, z[i]);
-      if (j < D) y[j] = -xj;
+      const double  xj = zrow[j] * rinv[j];
+      const double* Lj = A + (size_t)j * LD;
+      for (int i = threadIdx.x; i < j; i += LMT) zrow[i] = fma(-Lj[i], xj, zrow[i]);
+      if (threadIdx.x == 0 && j < D) y[j] = -xj;
+      __syncthreads();
     }
   }
 }
