@@ -210,14 +210,16 @@ __global__ void grid_scatter(const double* __restrict__ tf, int tstr, int nt, Gr
   G.sfeat[6 * G.scap + pos] = __longlong_as_double((long long)i);
 }
 
-// 6-D bounding box of every cell's members (for the pruned scan of the cells the ring search does not reach)
-__global__ void grid_boxes(GridBufs G) {
-  const int n = *G.ncells;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-    double lo[6], hi[6];
+// 6-D bounding box of every cell's members (for the pruned scan of the cells the ring search does not reach): eight
+// lanes per cell stride over its members, then a 3-step shuffle reduction
+__global__ void __launch_bounds__(256) grid_boxes(GridBufs G) {
+  const int n = *G.ncells, sub = threadIdx.x & 7;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  double    lo[6], hi[6];
 #pragma unroll
-    for (int d = 0; d < 6; ++d) lo[d] = INFINITY, hi[d] = -INFINITY;
-    for (int p = G.off[c]; p < G.off[c + 1]; ++p) {
+  for (int d = 0; d < 6; ++d) lo[d] = INFINITY, hi[d] = -INFINITY;
+  if (c < n)
+    for (int p = G.off[c] + sub; p < G.off[c + 1]; p += 8) {
 #pragma unroll
       for (int d = 0; d < 6; ++d) {
         const double td = G.sfeat[d * G.scap + p];
@@ -225,8 +227,15 @@ __global__ void grid_boxes(GridBufs G) {
       }
     }
 #pragma unroll
+  for (int s = 4; s > 0; s >>= 1)
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+    }
+  if (c < n && sub == 0)
+#pragma unroll
     for (int d = 0; d < 6; ++d) G.cbox[(size_t)c * 12 + d] = lo[d], G.cbox[(size_t)c * 12 + 6 + d] = hi[d];
-  }
 }
 
 __global__ void grid_cleanup(GridBufs G) {
@@ -619,7 +628,7 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     { ++c->n_launches; grid_count<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB, (int)c->prm.max_surfels); }
     { ++c->n_launches; grid_scan<<<1, 1024, 0, st>>>(GB); }
     { ++c->n_launches; grid_scatter<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB); }
-    { ++c->n_launches; grid_boxes<<<c->num_sms, 256, 0, st>>>(GB); }
+    { ++c->n_launches; grid_boxes<<<(unsigned)((nt * 8 + 255) / 256), 256, 0, st>>>(GB); }  // cells <= targets
     { ++c->n_launches; knn6_warp<<<c->num_sms * 8, 256, 0, st>>>(c->d_qfeat, FSTR, (int)nq, k, GB, c->d_knn_idx, c->d_knn_d2); }
 #ifdef WC_KNN_STATS
     knn_stats_print<<<1, 1, 0, st>>>();
@@ -634,14 +643,16 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
   int* a = c->d_acc;
   int* b = c->d_acc2;
   for (int it = 0;; ++it) {
-    WC_CUDA(c, cudaMemsetAsync(c->d_flag, 0, 4, st));
-    const int sweeps = self_match ? 3 : 1;
+    // acc <- F(acc) is a deterministic sweep; it has converged when a sweep reproduces its input.  Eight sweeps are
+    // enqueued before the first host check (the recurrence settles in a handful), the flag is cleared right before
+    // the last sweep of a batch so that it reports that sweep alone.
+    const int sweeps = self_match ? 8 : 1;
     for (int s = 0; s < sweeps; ++s) {
+      if (s == sweeps - 1) WC_CUDA(c, cudaMemsetAsync(c->d_flag, 0, 4, st));
       { ++c->n_launches; resolve_pairs<<<gq, 256, 0, st>>>(c->d_gated, (int)nq, k, self_match, a, b, c->d_flag); }
       int* tmp = a; a = b; b = tmp;
     }
     if (!self_match) break;
-    // the last sweep of the batch wrote `changed` relative to its input; converged iff the whole batch was quiet
     WC_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));
     if (*c->h_flag == 0) break;
