@@ -348,6 +348,32 @@ def test_c3_full_size_properties(od, ctx):
     assert err1 < 0.1 * err0
 
 
+def test_c3_matcher_grid_is_exact(od, ctx, monkeypatch):
+    """Full-size matcher (46 k surfels): the uniform-grid search with every cell size (and its ring / box-scan phases) must
+    return exactly the correspondences of the exhaustive scan — the grid is an index, never an approximation."""
+    w = S.make_window("C3")
+    sld = od.UpdateSurfelPoses(w.imu, od.BuildSurfels(w.points, ctx=ctx), ctx=ctx)
+    fix = od.UpdateSurfelPoses(w.fix_imu, od.BuildSurfels(w.fix_points, ctx=ctx), ctx=ctx)
+
+    def both(c):
+        m = od.KnnSurfelMatcher(c); m.BuildIndex(sld); a, _ = m.Match(sld)
+        m2 = od.KnnSurfelMatcher(c); m2.BuildIndex(fix); b, _ = m2.Match(sld)
+        return a.tobytes(), b.tobytes()
+
+    monkeypatch.setenv("WC_KNN_GRID_MIN", str(1 << 40))  # read at context creation: always the exhaustive scan
+    brute_ctx = od.Context(0)
+    monkeypatch.delenv("WC_KNN_GRID_MIN")
+    try:
+        ref = both(brute_ctx)
+    finally:
+        brute_ctx.close()
+    assert both(ctx) == ref                                # default: unit cells
+    for cells in ("1", "2", "4"):
+        monkeypatch.setenv("WC_KNN_CELLS_PER_UNIT", cells)  # read at every match call
+        assert both(ctx) == ref, cells
+    monkeypatch.delenv("WC_KNN_CELLS_PER_UNIT")
+
+
 def test_solve_wide_system_64_control_poses(od, ctx, oracle):
     """BASELINE config 5 shape in small: 64 control poses (12 * 64 - 3 = 765 unknowns).  The LM system no longer fits
     shared memory, so the Cholesky runs out of global memory (lm_step<false>) with the CTA-wide backward sweep."""

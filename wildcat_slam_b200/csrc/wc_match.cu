@@ -124,6 +124,7 @@ struct GridBufs {
   int*                ncells;
   double*             sfeat; // sorted by cell, structure of arrays: 6 feature columns + the target index column, stride scap
   size_t              scap;
+  double              cs;    // grid cells per feature unit along the three centre axes (a power of two: f * cs is exact)
   double*             cbox;  // per cell: min[6], max[6] of the member features
   unsigned long long* ckey;  // per cell: its key
   int*                err;
@@ -133,7 +134,7 @@ __global__ void grid_count(const double* __restrict__ tf, int tstr, int nt, Grid
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nt) return;
   const double* f  = tf + (size_t)i * tstr;
-  const double  fx = floor(f[0]), fy = floor(f[1]), fz = floor(f[2]);
+  const double  fx = floor(f[0] * G.cs), fy = floor(f[1] * G.cs), fz = floor(f[2] * G.cs);
   if (!(fabs(fx) < 1e6 && fabs(fy) < 1e6 && fabs(fz) < 1e6)) {
     *G.err = 1;  // outside the 2^20-cell key range (or non-finite)
     G.tcell[i] = -1;
@@ -325,7 +326,8 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
       for (int base = p0; base < p1; base += 32) scan_batch(base + lane < p1 ? base + lane : -1);
     };
 
-    const double    cfx = floor(f[0]), cfy = floor(f[1]), cfz = floor(f[2]);
+    const double    gx = f[0] * G.cs, gy = f[1] * G.cs, gz = f[2] * G.cs;  // grid coordinates of the query centre
+    const double    cfx = floor(gx), cfy = floor(gy), cfz = floor(gz);
     const bool      rings_ok = fabs(cfx) < 1e6 && fabs(cfy) < 1e6 && fabs(cfz) < 1e6;
     const long long ix = rings_ok ? (long long)cfx : 0, iy = rings_ok ? (long long)cfy : 0, iz = rings_ok ? (long long)cfz : 0;
     bool            done = false;
@@ -377,8 +379,9 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
         const int cc = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
         probe_and_scan(lane < 27, cc % 3 - 1, (cc / 3) % 3 - 1, cc / 9 - 1);
       }
-      double b = fmin(fmin(fmin(f[0] - (cfx - 1), (cfx + 2) - f[0]), fmin(f[1] - (cfy - 1), (cfy + 2) - f[1])),
-                      fmin(f[2] - (cfz - 1), (cfz + 2) - f[2]));
+      // distance from the query to the nearest face of the scanned cube, in feature units
+      double b = fmin(fmin(fmin(gx - (cfx - 1), (cfx + 2) - gx), fmin(gy - (cfy - 1), (cfy + 2) - gy)),
+                      fmin(gz - (cfz - 1), (cfz + 2) - gz)) / G.cs;
       done = worst < b * b * (1.0 - 1e-12);
       if (!done) {
         // phase 0.5: the shell of the 5 x 5 x 5 block (98 cells, four rounds of 32 lanes over the 125 offsets) — for a
@@ -393,8 +396,8 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
           probe_and_scan(shell, dx, dy, dz);
         }
         ring = 2;
-        b    = fmin(fmin(fmin(f[0] - (cfx - 2), (cfx + 3) - f[0]), fmin(f[1] - (cfy - 2), (cfy + 3) - f[1])),
-                    fmin(f[2] - (cfz - 2), (cfz + 3) - f[2]));
+        b    = fmin(fmin(fmin(gx - (cfx - 2), (cfx + 3) - gx), fmin(gy - (cfy - 2), (cfy + 3) - gy)),
+                    fmin(gz - (cfz - 2), (cfz + 3) - gz)) / G.cs;
         done = worst < b * b * (1.0 - 1e-12);
       }
     }
@@ -625,6 +628,10 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
                                                                          c->d_knn_idx, c->d_knn_d2); }
   } else {
     GridBufs GB = *(GridBufs*)c->d_grid;
+    // unit cells (1 m / 5 deg feature units): measured at C3, half-size cells scan fewer candidates in the 3 x 3 x 3 block
+    // but escalate to the ring-2 / box-scan phases more often and end up slower (930 vs 890 us); exact either way
+    GB.cs = 1.0;
+    if (const char* e = getenv("WC_KNN_CELLS_PER_UNIT")) GB.cs = atof(e);  // test hook (1, 2, 4)
     { ++c->n_launches; grid_count<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB, (int)c->prm.max_surfels); }
     { ++c->n_launches; grid_scan<<<1, 1024, 0, st>>>(GB); }
     { ++c->n_launches; grid_scatter<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB); }
