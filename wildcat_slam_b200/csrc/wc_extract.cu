@@ -103,12 +103,13 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
   for (int k = t; k < KTAB / 2; k += KNT) cnt2[k] = 0u;
   __syncthreads();
 
-  // ---- keys, exact fixed-point payload, shared-memory insert + rank of the point inside its key group
-  int hpos[KPT], rank[KPT];
+  // ---- keys and exact fixed-point payload: straight-line code over the thread's KPT points, so the loads and the
+  //      dependent fp64 chains of the points interleave (the shared-memory inserts, with their CAS loops, come after)
+  unsigned long long key[KPT];
 #pragma unroll
   for (int u = 0; u < KPT; ++u) {
     const int l = t + KNT * u, i = base + l;
-    hpos[u] = -1, rank[u] = 0;
+    key[u] = WC_KEY_EMPTY;
     if (i < P.n) {
       const float4 p  = xyz[i];
       const double tt = time[i];
@@ -139,24 +140,30 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
       pay[l]              = q;
       const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
       if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
-          Q < 0 || bin >= WC_MAX_BINS) {
+          Q < 0 || bin >= WC_MAX_BINS)
         st->err_range = 1;
-      } else {
-        const unsigned long long key = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) |
-                                       ((unsigned long long)rz << 18) | ((unsigned long long)leaf << 12) | (unsigned long long)bin;
-        unsigned h = ((unsigned)key * 0x9E3779B1u) ^ ((unsigned)(key >> 32) * 0x85EBCA77u);  // tile-local table: a cheap mix
-        h          = ((h ^ (h >> 15)) * 0x2C1B3C6Du) >> 20 & (KTAB - 1);
-        for (;;) {  // at most KT distinct keys in KTAB = 2 KT positions: always terminates
-          unsigned long long k = skey[h];
-          if (k == WC_KEY_EMPTY) k = atomicCAS(&skey[h], WC_KEY_EMPTY, key);
-          if (k == WC_KEY_EMPTY || k == key) break;
-          h = (h + 1) & (KTAB - 1);
-        }
-        hpos[u]          = (int)h;
-        const unsigned sh = (h & 1u) * 16u;
-        rank[u]          = (int)((atomicAdd(&cnt2[h >> 1], 1u << sh) >> sh) & 0xffffu);
-      }
+      else
+        key[u] = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) | ((unsigned long long)rz << 18) |
+                 ((unsigned long long)leaf << 12) | (unsigned long long)bin;
     }
+  }
+  // ---- shared-memory insert + rank of the point inside its key group
+  int hpos[KPT], rank[KPT];
+#pragma unroll
+  for (int u = 0; u < KPT; ++u) {
+    hpos[u] = -1, rank[u] = 0;
+    if (key[u] == WC_KEY_EMPTY) continue;
+    unsigned h = ((unsigned)key[u] * 0x9E3779B1u) ^ ((unsigned)(key[u] >> 32) * 0x85EBCA77u);  // tile-local table: a cheap mix
+    h          = ((h ^ (h >> 15)) * 0x2C1B3C6Du) >> 20 & (KTAB - 1);
+    for (;;) {  // at most KT distinct keys in KTAB = 2 KT positions: always terminates
+      unsigned long long k = skey[h];
+      if (k == WC_KEY_EMPTY) k = atomicCAS(&skey[h], WC_KEY_EMPTY, key[u]);
+      if (k == WC_KEY_EMPTY || k == key[u]) break;
+      h = (h + 1) & (KTAB - 1);
+    }
+    hpos[u]           = (int)h;
+    const unsigned sh = (h & 1u) * 16u;
+    rank[u]           = (int)((atomicAdd(&cnt2[h >> 1], 1u << sh) >> sh) & 0xffffu);
   }
   __syncthreads();
   // ---- exclusive scan of the per-position counts (8 positions per thread) -> offsets and the compact run list
@@ -215,7 +222,19 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
     const int                np  = (int)((cnt2[h >> 1] >> ((h & 1) * 16)) & 0xffffu);
     long long a_t = 0, a_x = 0, a_y = 0, a_z = 0, a_xx = 0, a_xy = 0, a_xz = 0, a_yy = 0, a_yz = 0, a_zz = 0;
     int       lmin = KT, lmax = -1;
-    for (int j = 0; j < np; ++j) {
+    int j = 0;
+    for (; j + 1 < np; j += 2) {  // two points per step: the two dependent perm -> payload load chains overlap
+      const int  l0 = perm[p0 + j], l1 = perm[p0 + j + 1];
+      const int4 e = pay[l0], f = pay[l1];
+      lmin = min(lmin, min(l0, l1)), lmax = max(lmax, max(l0, l1));
+      a_t += e.w, a_x += e.x, a_y += e.y, a_z += e.z;
+      a_xx += (long long)e.x * e.x, a_xy += (long long)e.x * e.y, a_xz += (long long)e.x * e.z;
+      a_yy += (long long)e.y * e.y, a_yz += (long long)e.y * e.z, a_zz += (long long)e.z * e.z;
+      a_t += f.w, a_x += f.x, a_y += f.y, a_z += f.z;
+      a_xx += (long long)f.x * f.x, a_xy += (long long)f.x * f.y, a_xz += (long long)f.x * f.z;
+      a_yy += (long long)f.y * f.y, a_yz += (long long)f.y * f.z, a_zz += (long long)f.z * f.z;
+    }
+    if (j < np) {
       const int  l = perm[p0 + j];
       const int4 e = pay[l];
       lmin = min(lmin, l), lmax = max(lmax, l);
