@@ -23,6 +23,10 @@ m2 = od.KnnSurfelMatcher(ctx); m2.BuildIndex(fix); cf, _ = m2.Match(sld)
 x1, s1 = od.ResidentWindow(sld, fix, cs, cf, w.imu, w.samples, ctx).solve()      # single GPU (world == 1 in the ctx)
 handles = sharding.exchange_handles(ctx.comm_export(), dist, device="cuda")
 ctx.comm_connect(rank, world, handles)
+# sharded matcher: k-NN queries split over the ranks, index lists all-gathered over NVLink -> identical pair lists
+m = od.KnnSurfelMatcher(ctx); m.BuildIndex(sld); cs2, _ = m.Match(sld)
+m2 = od.KnnSurfelMatcher(ctx); m2.BuildIndex(fix); cf2, _ = m2.Match(sld)
+assert cs2.tobytes() == cs.tobytes() and cf2.tobytes() == cf.tobytes(), "sharded matcher differs from the single-GPU matcher"
 rw = od.ResidentWindow(sld, fix, cs, cf, w.imu, w.samples, ctx)                  # sharded: this rank packs its block only
 for rep in range(3):
     xs, ss = rw.solve()
@@ -31,6 +35,7 @@ allx = [torch.empty_like(t) for _ in range(world)]
 dist.all_gather(allx, t)
 same = all(torch.equal(allx[0], a) for a in allx)
 d = float(np.abs(xs - x1).max())
+print(f"[rank {rank}] sharded matcher identical: {len(cs2)}+{len(cf2)} pairs", flush=True)
 print(f"[rank {rank}] iters single={s1.num_iterations} sharded={ss.num_iterations} cost single={s1.final_cost:.12g} sharded={ss.final_cost:.12g} "
       f"|x_sharded - x_single|max={d:.3e} bitwise_identical_across_ranks={same} solve_ms single={s1.gpu_ms_total:.3f} sharded={ss.gpu_ms_total:.3f}", flush=True)
 assert same and d < 1e-9 and ss.num_iterations == s1.num_iterations

@@ -62,6 +62,45 @@ __global__ void __launch_bounds__(256) comm_allreduce(CommArgs a) {
   }
 }
 
+// All-gather of per-query rows (the k-NN index lists of the sharded matcher): rank r computed rows [row0[r], row0[r+1])
+// into ITS exported gather region; after one flag round every rank copies all slices into its local array.
+struct GatherArgs {
+  unsigned long long* my_flags;       // local: gather flags[rank of writer]
+  unsigned long long* peer_flags[8];
+  const int*          region[8];      // gather regions of this epoch's parity, by rank
+  int*                dst;            // local full array
+  int*                err;
+  unsigned long long  epoch;
+  int                 rank, world, width;  // ints per row
+  int                 row0[9];
+  long long           timeout_cycles;
+};
+
+__global__ void __launch_bounds__(256) comm_allgather_rows(GatherArgs a) {
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    *((volatile unsigned long long*)&a.peer_flags[threadIdx.x][a.rank]) = a.epoch;
+  }
+  if (threadIdx.x < a.world) {
+    const long long t0 = clock64();
+    while (*((volatile unsigned long long*)&a.my_flags[threadIdx.x]) < a.epoch) {
+      if (clock64() - t0 > a.timeout_cycles) {
+        *a.err = WC_ECOMM;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const size_t total = (size_t)a.row0[a.world] * a.width;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / a.width);
+    int       r   = 0;
+    while (row >= a.row0[r + 1]) ++r;
+    a.dst[i] = *((const volatile int*)&a.region[r][i]);  // regions are indexed like the full array
+  }
+}
+
 }  // namespace
 
 static size_t part_doubles(const wc_ctx* c) {
@@ -69,9 +108,13 @@ static size_t part_doubles(const wc_ctx* c) {
   return N * N + N + 2;
 }
 
+static size_t gather_ints(const wc_ctx* c) { return (size_t)c->prm.max_surfels * 16; }
+static size_t gather_off(const wc_ctx* c) { return 256 + 2 * part_doubles(c) * 8; }  // byte offset of the gather flags
+
 static wc_status comm_alloc(wc_ctx* c) {
   if (c->d_xchg) return WC_OK;
-  c->xchg_bytes = 256 + 2 * part_doubles(c) * 8;
+  // [256 B reduce flags][2 x partial normal equations][256 B gather flags][2 x gather region of max_surfels x 16 ints]
+  c->xchg_bytes = 256 + 2 * part_doubles(c) * 8 + 256 + 2 * gather_ints(c) * 4;
   WC_CUDA(c, cudaMalloc(&c->d_xchg, c->xchg_bytes));
   WC_CUDA(c, cudaMemset(c->d_xchg, 0, c->xchg_bytes));
   WC_CUDA(c, cudaMalloc(&c->d_comm_err, 4));
@@ -116,7 +159,7 @@ extern "C" wc_status wc_comm_connect(wc_ctx* c, int rank, int world, const uint8
     if (e != cudaSuccess) WC_FAIL(c, WC_ECOMM, "cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
     c->peer_xchg[r] = (double*)p;
   }
-  c->rank = rank, c->world = world, c->comm_ready = 1, c->comm_epoch = 0;
+  c->rank = rank, c->world = world, c->comm_ready = 1, c->comm_epoch = 0, c->gather_epoch = 0;
   return WC_OK;
 }
 
@@ -156,6 +199,34 @@ wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate) {
   int          grid  = (int)((total + 255) / 256);
   if (grid > 64) grid = 64;
   { ++c->n_launches; comm_allreduce<<<grid, 256, 0, c->stream>>>(a); }
+  WC_CUDA(c, cudaGetLastError());
+  return WC_OK;
+}
+
+// where this rank writes its rows for the next all-gather (indexed like the full array), world > 1
+int* wc_comm_gather_region(wc_ctx* c) {
+  const int par = (int)((c->gather_epoch + 1) & 1);
+  return (int*)((char*)c->d_xchg + gather_off(c) + 256) + (size_t)par * gather_ints(c);
+}
+
+// rows [row0[r], row0[r+1]) of `width` ints were written by rank r into its gather region; fills dst on every rank
+wc_status wc_comm_allgather_rows(wc_ctx* c, int* dst, const int* row0, int width) {
+  if (c->world <= 1) return WC_OK;
+  if (!c->comm_ready) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
+  if ((size_t)row0[c->world] * width > gather_ints(c)) WC_FAIL(c, WC_ECAPACITY, "gather region too small");
+  c->gather_epoch += 1;
+  GatherArgs a;
+  memset(&a, 0, sizeof(a));
+  const int par = (int)(c->gather_epoch & 1);
+  a.my_flags    = (unsigned long long*)((char*)c->d_xchg + gather_off(c));
+  for (int r = 0; r < c->world; ++r) {
+    a.peer_flags[r] = (unsigned long long*)((char*)c->peer_xchg[r] + gather_off(c));
+    a.region[r]     = (const int*)((char*)c->peer_xchg[r] + gather_off(c) + 256) + (size_t)par * gather_ints(c);
+  }
+  for (int r = 0; r <= c->world; ++r) a.row0[r] = row0[r];
+  a.dst = dst, a.err = c->d_comm_err, a.epoch = c->gather_epoch, a.rank = c->rank, a.world = c->world, a.width = width;
+  a.timeout_cycles = 4000000000ll;
+  { ++c->n_launches; comm_allgather_rows<<<64, 256, 0, c->stream>>>(a); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }

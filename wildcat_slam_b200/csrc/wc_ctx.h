@@ -164,6 +164,7 @@ struct wc_ctx {
   double* peer_xchg[8];   // peer exchange buffers (own entry = d_xchg)
   int     comm_ready;
   unsigned long long comm_epoch;
+  unsigned long long gather_epoch;
   int*    d_comm_err;
 };
 

@@ -603,7 +603,14 @@ void wc_match_free(wc_ctx* c) {
   }
 }
 
+int*      wc_comm_gather_region(wc_ctx* c);  // wc_comm.cu
+wc_status wc_comm_check(wc_ctx* c);
+wc_status wc_comm_allgather_rows(wc_ctx* c, int* dst, const int* row0, int width);
+
 // Device-resident matcher core: query/target surfels already at d_q / d_t.  Leaves the pairs in d_corr_out.
+// With world > 1 the exact k-NN search (the bulk of the matcher) is sharded over the ranks by query blocks and the index
+// lists are all-gathered through NVLink peer memory; index build, gating and pair resolution are replicated (they are
+// order-dependent across queries and cheap), so every rank ends with the identical correspondence list.
 wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_surfel* d_t, size_t nt, int self_match,
                           size_t* n_out) {
   *n_out = 0;
@@ -621,11 +628,21 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     { ++c->n_launches; surfel_features<<<gt, 256, 0, st>>>(d_t, (int)nt, c->prm.center_dist_threshold, c->prm.angular_dist_threshold, c->d_tfeat); }
     tfeat = c->d_tfeat;
   }
+  // query shard of this rank
+  const bool sharded = c->world > 1 && c->comm_ready && nq >= 1024;
+  int        row0[9] = {0};
+  for (int r = 0; r <= c->world && r <= 8; ++r) row0[r] = sharded ? (int)((nq * (size_t)r) / (size_t)c->world) : (r ? (int)nq : 0);
+  const int     q0 = sharded ? row0[c->rank] : 0, nq_my = (sharded ? row0[c->rank + 1] : (int)nq) - q0;
+  const double* qf_my   = c->d_qfeat + (size_t)q0 * FSTR;
+  int*          knn_out = (sharded ? wc_comm_gather_region(c) : c->d_knn_idx) + (size_t)q0 * k;
+  double*       d2_out  = c->d_knn_d2 + (size_t)q0 * k;
   if (nt < (size_t)c->knn_grid_min) {
-    if (k <= 10) { ++c->n_launches; knn6_bruteforce<10><<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
-                                                                         c->d_knn_idx, c->d_knn_d2); }
-    else { ++c->n_launches; knn6_bruteforce<KMAX><<<(unsigned)((nq + TILE - 1) / TILE), TILE, 0, st>>>(c->d_qfeat, FSTR, (int)nq, tfeat, FSTR, (int)nt, k,
-                                                                         c->d_knn_idx, c->d_knn_d2); }
+    if (nq_my > 0) {
+      if (k <= 10) { ++c->n_launches; knn6_bruteforce<10><<<(unsigned)((nq_my + TILE - 1) / TILE), TILE, 0, st>>>(qf_my, FSTR, nq_my, tfeat, FSTR, (int)nt, k,
+                                                                           knn_out, d2_out); }
+      else { ++c->n_launches; knn6_bruteforce<KMAX><<<(unsigned)((nq_my + TILE - 1) / TILE), TILE, 0, st>>>(qf_my, FSTR, nq_my, tfeat, FSTR, (int)nt, k,
+                                                                           knn_out, d2_out); }
+    }
   } else {
     GridBufs GB = *(GridBufs*)c->d_grid;
     // unit cells (1 m / 5 deg feature units): measured at C3, half-size cells scan fewer candidates in the 3 x 3 x 3 block
@@ -636,13 +653,17 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     { ++c->n_launches; grid_scan<<<1, 1024, 0, st>>>(GB); }
     { ++c->n_launches; grid_scatter<<<gt, 256, 0, st>>>(tfeat, FSTR, (int)nt, GB); }
     { ++c->n_launches; grid_boxes<<<(unsigned)((nt * 8 + 255) / 256), 256, 0, st>>>(GB); }  // cells <= targets
-    { ++c->n_launches; knn6_warp<<<c->num_sms * 8, 256, 0, st>>>(c->d_qfeat, FSTR, (int)nq, k, GB, c->d_knn_idx, c->d_knn_d2); }
+    if (nq_my > 0) { ++c->n_launches; knn6_warp<<<c->num_sms * 8, 256, 0, st>>>(qf_my, FSTR, nq_my, k, GB, knn_out, d2_out); }
 #ifdef WC_KNN_STATS
     knn_stats_print<<<1, 1, 0, st>>>();
     { int ncell = 0; cudaMemcpyAsync(&ncell, GB.ncells, 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); printf("grid cells %d targets %zu\n", ncell, nt); }
 #endif
     { ++c->n_launches; grid_cleanup<<<c->num_sms, 256, 0, st>>>(GB); }
     { ++c->n_launches; grid_reset_count<<<1, 1, 0, st>>>(GB); }
+  }
+  if (sharded) {
+    wc_status gs = wc_comm_allgather_rows(c, c->d_knn_idx, row0, k);
+    if (gs) return gs;
   }
   GateParams GP{c->prm.time_diff_threshold, c->prm.angular_dist_threshold, c->prm.surfel_dist_threshold, k};
   { ++c->n_launches; gate_candidates<<<gq, 256, 0, st>>>(c->d_qfeat, (int)nq, tfeat, c->d_knn_idx, GP, c->d_gated); }
@@ -672,6 +693,10 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
   if (c->h_flag[2]) WC_FAIL(c, WC_EINVAL, "surfel centres outside the matcher grid range (+-1e6 cells) or non-finite");
+  if (sharded) {
+    wc_status cs = wc_comm_check(c);
+    if (cs) return cs;
+  }
   *n_out = (size_t)c->h_flag[1];
   if (getenv("WC_DEBUG")) fprintf(stderr, "[wc_match] nq=%zu nt=%zu self=%d pairs=%d\n", nq, nt, self_match, c->h_flag[1]);
   return WC_OK;

@@ -447,8 +447,14 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
   if (i1.timestamp < a.ts[0] || i3.timestamp > a.ts[a.K - 1]) return;  // :324-329 (timestamps increase)
   double* jac = sj[wid];
   for (int k = lane; k < 12 * IMU_LD; k += 32) jac[k] = 0.0;
+  __shared__ double smat[IMU_WARPS][4][9];  // F0, F1, A30, A39 of this warp's triplet
   __syncwarp();
-  if (lane == 0) {
+  // The factor's independent pieces run on four lanes side by side (each repeats the cheap common part): lane 0 the
+  // residuals, lane 1 F0, lane 2 F1, lane 3 A30 / A39 — the serial chain of one lane doing everything was the tail of the
+  // whole linearisation launch.
+  int    l[3] = {0, 0, 0};
+  double f[3] = {0.0, 0.0, 0.0};
+  if (lane < 4) {
     const int sp2  = upper_bound_ts(a.ts, a.K, i1.timestamp);
     const int mode = (sp2 == a.K - 1) ? 1 : 0;
     const int nblk = mode == 0 ? 3 : 2;
@@ -456,8 +462,6 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
     const double* xs[3] = {x + 12 * (sp2 - 1), x + 12 * sp2, x + 12 * (mode == 0 ? sp2 + 1 : sp2)};
     // ComputeStateCorr for the three IMU states (cost_functor.h:358-400)
     StateCorr c[3];
-    int       l[3];
-    double    f[3];
     const double tt[3] = {i1.timestamp, i2.timestamp, i3.timestamp};
     bool         ok    = true;
     for (int s = 0; s < 3; ++s) {
@@ -473,26 +477,40 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
       f[s] = (t - tsv[l[s]]) / (tsv[l[s] + 1] - tsv[l[s]]);
       state_corr(xs[l[s]], xs[l[s] + 1], f[s], c[s]);
     }
-    if (!ok) st->err = WC_EOUT_OF_SPAN;
     const Q4 R1 = ldq(i1.rot), R2 = ldq(i2.rot);
     const Q4 E1R1 = Exp(c[0].r) * R1;
-    const V3 gyr_est = Log((conj(E1R1) * Exp(c[1].r)) * R2) / a.dt;
-    const V3 acc_est = ((c[2].t + ld3(i3.pos)) + (c[0].t + ld3(i1.pos)) - 2.0 * (c[1].t + ld3(i2.pos))) / (a.dt * a.dt);
-    const V3 rg  = a.wg * ((ld3(i1.gyr) + ld3(i2.gyr)) / 2.0 - gyr_est - c[0].bg);
-    const V3 ra  = a.wa * (E1R1 * (ld3(i1.acc) - c[0].ba) - acc_est + ld3(a.grav));
-    const V3 rbg = a.wbg * (c[0].bg - c[1].bg);
-    const V3 rba = a.wba * (c[0].ba - c[1].ba);
-    const double res[12] = {rg.x, rg.y, rg.z, ra.x, ra.y, ra.z, rbg.x, rbg.y, rbg.z, rba.x, rba.y, rba.z};
-    for (int k = 0; k < 12; ++k) jac[k * IMU_LD + 36] = res[k];
+    if (lane == 0) {
+      if (!ok) st->err = WC_EOUT_OF_SPAN;
+      const V3 gyr_est = Log((conj(E1R1) * Exp(c[1].r)) * R2) / a.dt;
+      const V3 acc_est = ((c[2].t + ld3(i3.pos)) + (c[0].t + ld3(i1.pos)) - 2.0 * (c[1].t + ld3(i2.pos))) / (a.dt * a.dt);
+      const V3 rg  = a.wg * ((ld3(i1.gyr) + ld3(i2.gyr)) / 2.0 - gyr_est - c[0].bg);
+      const V3 ra  = a.wa * (E1R1 * (ld3(i1.acc) - c[0].ba) - acc_est + ld3(a.grav));
+      const V3 rbg = a.wbg * (c[0].bg - c[1].bg);
+      const V3 rba = a.wba * (c[0].ba - c[1].ba);
+      const double res[12] = {rg.x, rg.y, rg.z, ra.x, ra.y, ra.z, rbg.x, rbg.y, rbg.z, rba.x, rba.y, rba.z};
+      for (int k = 0; k < 12; ++k) jac[k * IMU_LD + 36] = res[k];
+      sblk[wid][0] = sp2 - 1, sblk[wid][1] = sp2, sblk[wid][2] = mode == 0 ? sp2 + 1 : -1, sblk[wid][3] = nblk;
+      double cst = 0.0;
+      for (int k = 0; k < 12; ++k) cst += 0.5 * res[k] * res[k];  // TrivialLoss
+      atomicAdd(a.B.cost[buf], cst);
+    } else if (lane == 1) {
+      st33(smat[wid][0], imu_F(conj(R1), Exp(c[1].r) * R2, c[0].r));
+    } else if (lane == 2) {
+      st33(smat[wid][1], imu_F(conj(E1R1), R2, c[1].r));
+    } else {
+      st33(smat[wid][2], (ToMatrix(Exp(c[0].r)) * Hat(R1 * (ld3(i1.acc) - c[0].ba))) * Jr(c[0].r));
+      st33(smat[wid][3], ToMatrix(E1R1));
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
     // jacobian_tau, tau1, tau2 (:301-321) dispatched to the bracketing blocks (:402-444)
     const M3     I   = eye3();
     const double idt = 1 / a.dt, idt2 = 1 / a.dt / a.dt;
     {
       const int    cl = 12 * l[0], cr = cl + 12;
       const double wl = 1 - f[0], wr = f[0];
-      const M3     F0  = imu_F(conj(R1), Exp(c[1].r) * R2, c[0].r);
-      const M3     A30 = (ToMatrix(Exp(c[0].r)) * Hat(R1 * (ld3(i1.acc) - c[0].ba))) * Jr(c[0].r);
-      const M3     A39 = ToMatrix(E1R1);
+      const M3     F0 = ld33(smat[wid][0]), A30 = ld33(smat[wid][2]), A39 = ld33(smat[wid][3]);
       for (int side = 0; side < 2; ++side) {
         const int    c0 = side ? cr : cl;
         const double w  = side ? wr : wl;
@@ -508,7 +526,7 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
     {
       const int    cl = 12 * l[1], cr = cl + 12;
       const double wl = 1 - f[1], wr = f[1];
-      const M3     F1 = imu_F(conj(E1R1), R2, c[1].r);
+      const M3     F1 = ld33(smat[wid][1]);
       for (int side = 0; side < 2; ++side) {
         const int    c0 = side ? cr : cl;
         const double w  = side ? wr : wl;
@@ -525,10 +543,6 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
       add_block(jac, IMU_LD, 3, cl + 3, I, -wl * a.wa * idt2);
       add_block(jac, IMU_LD, 3, cr + 3, I, -wr * a.wa * idt2);
     }
-    sblk[wid][0] = sp2 - 1, sblk[wid][1] = sp2, sblk[wid][2] = mode == 0 ? sp2 + 1 : -1, sblk[wid][3] = nblk;
-    double cst = 0.0;
-    for (int k = 0; k < 12; ++k) cst += 0.5 * res[k] * res[k];  // TrivialLoss
-    atomicAdd(a.B.cost[buf], cst);
   }
   __syncwarp();
   const int nc = 12 * sblk[wid][3];
