@@ -22,6 +22,7 @@ struct CommArgs {
   unsigned long long* my_flags;        // local: flags[rank of writer]
   unsigned long long* peer_flags[8];   // remote flag arrays
   const double*       part[8];         // partial buffers of this epoch's parity, by rank (own entry local)
+  double*             my_other;        // own partial of the other parity: zeroed here for the linearisation after next
   double*             H[2];
   double*             g[2];
   double*             cost[2];
@@ -33,8 +34,9 @@ struct CommArgs {
 };
 
 __global__ void __launch_bounds__(256) comm_allreduce(CommArgs a) {
-  const int cur = a.state[0], done = a.state[1], step_valid = a.state[4];
-  if (done || (a.at_candidate && !step_valid)) return;  // replicated state: every rank takes the same branch
+  const int cur = a.state[0], done = a.state[1];
+  if (done) return;  // replicated state: every rank takes the same branch.  (After an invalid step the linearisation wrote
+                     // nothing: the reduction then sums zeros, which keeps the flag / parity protocol in step.)
   if (blockIdx.x == 0 && threadIdx.x < a.world) {
     __threadfence_system();
     *((volatile unsigned long long*)&a.peer_flags[threadIdx.x][a.rank]) = a.epoch;
@@ -59,7 +61,29 @@ __global__ void __launch_bounds__(256) comm_allreduce(CommArgs a) {
     if (i < nH) a.H[buf][i] = s;
     else if (i < nH + a.N) a.g[buf][i - nH] = s;
     else *a.cost[buf] = s;
+    // every peer has signalled this epoch, i.e. finished reading the previous one: the other-parity partial is free and
+    // is cleared here for the next linearisation (no separate zeroing launch on the iteration path)
+    a.my_other[i] = 0.0;
   }
+}
+
+// start of a sharded solve: one flag round, then both own partials are cleared (nobody can still be reading them)
+__global__ void __launch_bounds__(256) comm_barrier_zero(CommArgs a, double* p0, double* p1, size_t n) {
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    *((volatile unsigned long long*)&a.peer_flags[threadIdx.x][a.rank]) = a.epoch;
+  }
+  if (threadIdx.x < a.world) {
+    const long long t0 = clock64();
+    while (*((volatile unsigned long long*)&a.my_flags[threadIdx.x]) < a.epoch) {
+      if (clock64() - t0 > a.timeout_cycles) {
+        *a.err = WC_ECOMM;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p0[i] = 0.0, p1[i] = 0.0;
 }
 
 // All-gather of per-query rows (the k-NN index lists of the sharded matcher): rank r computed rows [row0[r], row0[r+1])
@@ -190,6 +214,7 @@ wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate) {
     a.peer_flags[r] = (unsigned long long*)c->peer_xchg[r];
     a.part[r]       = (const double*)((char*)c->peer_xchg[r] + 256) + (size_t)par * part_doubles(c);
   }
+  a.my_other = (double*)((char*)c->d_xchg + 256) + (size_t)(1 - par) * part_doubles(c);
   void* state = nullptr;
   wc_solve_exchange_views(c, 0, a.H, a.g, a.cost, &a.N, &state);
   a.state = (const int*)state, a.err = c->d_comm_err;
@@ -199,6 +224,23 @@ wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate) {
   int          grid  = (int)((total + 255) / 256);
   if (grid > 64) grid = 64;
   { ++c->n_launches; comm_allreduce<<<grid, 256, 0, c->stream>>>(a); }
+  WC_CUDA(c, cudaGetLastError());
+  return WC_OK;
+}
+
+// start of a sharded solve: barrier over the ranks + clear both partial buffers of this rank
+wc_status wc_comm_begin_solve(wc_ctx* c) {
+  if (c->world <= 1) return WC_OK;
+  if (!c->comm_ready) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
+  c->comm_epoch += 1;
+  CommArgs a;
+  memset(&a, 0, sizeof(a));
+  a.my_flags = (unsigned long long*)c->d_xchg;
+  for (int r = 0; r < c->world; ++r) a.peer_flags[r] = (unsigned long long*)c->peer_xchg[r];
+  a.err = c->d_comm_err, a.epoch = c->comm_epoch, a.rank = c->rank, a.world = c->world;
+  a.timeout_cycles = 4000000000ll;
+  double* p0 = (double*)((char*)c->d_xchg + 256);
+  { ++c->n_launches; comm_barrier_zero<<<64, 256, 0, c->stream>>>(a, p0, p0 + part_doubles(c), (size_t)(12 * c->K) * (12 * c->K) + 12 * c->K + 1); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }

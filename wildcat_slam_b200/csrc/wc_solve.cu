@@ -23,6 +23,7 @@ using namespace wcd;
 
 wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate);  // wc_comm.cu; no-op when world == 1
 wc_status wc_comm_check(wc_ctx* c);
+wc_status wc_comm_begin_solve(wc_ctx* c);
 void      wc_comm_partial_views(wc_ctx* c, double** H, double** g, double** cost);
 
 namespace {
@@ -1328,7 +1329,7 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     double *pH, *pg, *pc;
     wc_comm_partial_views(c, &pH, &pg, &pc);
     B.H[0] = B.H[1] = pH, B.g[0] = B.g[1] = pg, B.cost[0] = B.cost[1] = pc;
-    zeroed = 0;
+    zeroed = 1;  // cleared by wc_comm_begin_solve / by the reduction two epochs back
   }
   if (!zeroed) { ++c->n_launches; zero_buffers<<<64, 256, 0, st>>>(B, at_candidate); }
   LinArgs a;
@@ -1382,8 +1383,9 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   WC_CUDA(c, cudaEventRecord(c->ev[4], st));
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
-  wc_status s = enqueue_linearize(c, B, &o, 0, 0);
+  wc_status s = wc_comm_begin_solve(c);
   if (s) return s;
+  if ((s = enqueue_linearize(c, B, &o, 0, 0))) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;
   { ++c->n_launches; lm_init<<<1, LMT, 0, st>>>(B, o); }
   const int batch = c->lm_batch > 0 ? c->lm_batch : 8;
@@ -1457,6 +1459,7 @@ extern "C" wc_status wc_window_evaluate(wc_ctx* c, const wc_surfel* sld, size_t 
   SolveBufs     B  = make_bufs(c, 0);
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, N * 8, cudaMemcpyDeviceToDevice, st));
+  if ((s = wc_comm_begin_solve(c))) return s;
   if ((s = enqueue_linearize(c, B, &o, 0, 0))) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;
   if (cost) WC_CUDA(c, cudaMemcpyAsync(cost, m->cost, 8, cudaMemcpyDeviceToHost, st));
