@@ -117,11 +117,32 @@ __global__ void __launch_bounds__(256) comm_allgather_rows(GatherArgs a) {
   __syncthreads();
   __threadfence_system();
   const size_t total = (size_t)a.row0[a.world] * a.width;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  auto rank_of = [&](size_t i) {
     const int row = (int)(i / a.width);
     int       r   = 0;
     while (row >= a.row0[r + 1]) ++r;
-    a.dst[i] = *((const volatile int*)&a.region[r][i]);  // regions are indexed like the full array
+    return r;
+  };
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if ((a.width & 1) == 0) {
+    // even row width: every slice starts on an 8-byte boundary; 8-byte peer loads, four in flight per thread
+    const size_t n2 = total >> 1;
+    int2*        d2 = reinterpret_cast<int2*>(a.dst);
+    for (size_t i0 = tid; i0 < n2; i0 += 4 * nth) {
+      unsigned long long v[4];  // (the flag round and the fences above order these loads after the peers' writes)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t i = i0 + u * nth;
+        if (i < n2) v[u] = *((const volatile unsigned long long*)(reinterpret_cast<const unsigned long long*>(a.region[rank_of(2 * i)]) + i));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t i = i0 + u * nth;
+        if (i < n2) reinterpret_cast<unsigned long long*>(d2)[i] = v[u];
+      }
+    }
+  } else {
+    for (size_t i = tid; i < total; i += nth) a.dst[i] = *((const volatile int*)&a.region[rank_of(i)][i]);
   }
 }
 
@@ -268,7 +289,7 @@ wc_status wc_comm_allgather_rows(wc_ctx* c, int* dst, const int* row0, int width
   for (int r = 0; r <= c->world; ++r) a.row0[r] = row0[r];
   a.dst = dst, a.err = c->d_comm_err, a.epoch = c->gather_epoch, a.rank = c->rank, a.world = c->world, a.width = width;
   a.timeout_cycles = 4000000000ll;
-  { ++c->n_launches; comm_allgather_rows<<<64, 256, 0, c->stream>>>(a); }
+  { ++c->n_launches; comm_allgather_rows<<<c->num_sms, 256, 0, c->stream>>>(a); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }
