@@ -701,7 +701,9 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
       }
       const int node_base = level == 2 ? 9 : (level == 1 ? 1 : 0);
       // cluster boundaries: at each group head compare with the previous group of the same node
-      for (int i = threadIdx.x; i < E; i += NT) {
+      unsigned long long my_starts = 0;  // bit per loop trip: written to flag[] only after every thread has read it
+      int                trip      = 0;
+      for (int i = threadIdx.x; i < E; i += NT, ++trip) {
         const unsigned char f = flag[i];
         if (!(f & 1)) continue;
         const unsigned lk = skey[i] >> 14;
@@ -721,8 +723,12 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
           // points[i].timestamp - cluster.back().timestamp > 0.05  (surfel_extraction.cc:24)
           start = __dsub_rn(FromOrderedBits(~gmin_inv), FromOrderedBits(pmax)) > P.gap;
         }
-        if (start) flag[i] = f | 4;
+        if (start) my_starts |= 1ull << trip;
       }
+      __syncthreads();
+      trip = 0;
+      for (int i = threadIdx.x; i < E; i += NT, ++trip)
+        if ((my_starts >> trip) & 1ull) flag[i] |= 4;
       __syncthreads();
       // one thread per cluster: accumulate, fit, test, emit
       for (int i = threadIdx.x; i < E; i += NT) {
