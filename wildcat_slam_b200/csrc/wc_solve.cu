@@ -745,6 +745,41 @@ __device__ __forceinline__ void chol_factor_diag(double* A, int LD, int k0, doub
   if (c0 + 4 <= r) A[(k0 + r) * LD + k0 + c0 + 4] = e1;
 }
 
+#ifndef WC_FACTOR_ROLLED
+// default (measured in the kernel, 17 block factors: 44.7 k cycles vs 51.0 k for the rolled lane-grid variant above and
+// 43.6 k for an all-in-registers variant that needs 196 registers): lanes 0..CB-1 hold one row each (CB registers),
+// fully unrolled pivot loop, shuffles for the pivot row
+__device__ __forceinline__ void chol_factor_diag_rows(double* A, int LD, int k0, double* rinv_out, int* s_fail) {
+  const int lane = threadIdx.x & 31;
+  double    a[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) a[c] = (lane < CB && c <= lane) ? A[(k0 + lane) * LD + k0 + c] : (c == lane ? 1.0 : 0.0);
+  bool   bad  = false;
+  double rinv = 1.0;
+#pragma unroll
+  for (int j = 0; j < CB; ++j) {
+    const double djj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
+    const double rs = rsqrt(djj);
+    if (lane == j) rinv = rs;
+    if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
+#pragma unroll
+    for (int k = j + 1; k < CB; ++k) {
+      const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+      if (lane >= k) a[k] -= a[j] * lkj;
+    }
+  }
+  if (bad && lane == 0) *s_fail = 1;
+  if (lane < CB) {
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c <= lane) A[(k0 + lane) * LD + k0 + c] = a[c];
+    rinv_out[lane] = rinv;
+  }
+}
+#define chol_factor_diag chol_factor_diag_rows
+#endif
+
 // load 8 consecutive doubles (16-byte aligned) as four 128-bit accesses
 __device__ __forceinline__ void ld8(const double* p, double* v) {
   const double2* q = reinterpret_cast<const double2*>(p);
@@ -843,7 +878,7 @@ __device__ __forceinline__ void chol_trailing_tiles(double* A, int LD, int Dp, i
 __device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fail) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, LD = chol_ld(Dp);
 #ifdef WC_LM_TIMING
-  long long c_p1 = 0, c_p2 = 0, c_fact = 0, c0;
+  long long c_p1 = 0, c_p2 = 0, c_fact = 0, c_trail = 0, c0;
 #endif
   if (warp == 0) chol_factor_diag(A, LD, 0, rinv, s_fail);
   __syncthreads();
@@ -870,12 +905,18 @@ __device__ void cholesky_blocked_rhs(double* A, int Dp, double* rinv, int* s_fai
 #ifdef WC_LM_TIMING
       c_fact += clock64() - c0;
 #endif
-    } else chol_trailing_tiles(A, LD, Dp, k0, r0, warp - 1, LMT / 32 - 1);
+    } else {
+      chol_trailing_tiles(A, LD, Dp, k0, r0, warp - 1, LMT / 32 - 1);
+#ifdef WC_LM_TIMING
+      if (t == LMT - 1) c_trail += clock64() - c0;
+#endif
+    }
     __syncthreads();
     WC_TOCK(c_p2);
   }
 #ifdef WC_LM_TIMING
   if (t == 0) printf("chol cycles: phase1 (panel, diag update) %lld phase2 %lld of which warp 0's factor %lld\n", c_p1, c_p2, c_fact);
+  if (t == LMT - 1) printf("chol cycles: last warp's trailing %lld\n", c_trail);
 #endif
 }
 
