@@ -286,6 +286,7 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
     int    my_i = 0x7fffffff, worsti = 0x7fffffff;
 
     // scan the members [p0, p1) of one cell, 32 per step, inserting the ones that beat the current k-th best
+    bool fresh = true;  // warp-uniform: the list is still empty
     // one step: lane holds sorted-feature row p (or -1); the candidates that beat the current k-th best are inserted
     auto scan_batch = [&](int p) {
       double cd = INFINITY;
@@ -301,6 +302,27 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
           rr                = __dadd_rn(rr, __dmul_rn(diff, diff));
         }
         cd = rr, ci = (int)__double_as_longlong(td[6]);
+      }
+      if (fresh) {
+        // empty list (first batch of the query): a 32-lane bitonic sort of the batch IS the list — 15 compare-exchange
+        // steps instead of ~20 serial insertions; lanes >= k keep larger candidates, which the insert path ignores
+        if (__any_sync(0xffffffffu, ci != 0x7fffffff)) {
+#pragma unroll
+          for (int kk = 2; kk <= 32; kk <<= 1)
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+              const double od = __shfl_xor_sync(0xffffffffu, cd, j);
+              const int    oi = __shfl_xor_sync(0xffffffffu, ci, j);
+              const bool   up = (lane & kk) == 0, lower = (lane & j) == 0;
+              const bool   o_less = cand_less(od, oi, cd, ci);
+              if ((lower == up) ? o_less : !o_less && !(od == cd && oi == ci)) cd = od, ci = oi;
+            }
+          my_d = cd, my_i = ci;
+          worst  = __shfl_sync(0xffffffffu, my_d, k - 1);
+          worsti = __shfl_sync(0xffffffffu, my_i, k - 1);
+          fresh  = false;
+        }
+        return;
       }
       unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, ci, worst, worsti));
       while (m) {
