@@ -56,6 +56,34 @@ def c1():
     print("c1_oracle.npz", len(r["surfels"]), len(cs), len(cf), n)
 
 
+def sweep():
+    """3. c1_sweep_oracle.npz — the sweep-preparation row (AddLidarScan's extrinsic + range / blind-box filter and
+    UndistortSweep) of the oracle on a seeded C1-sized cloud that exercises every filter outcome: a regression pin of the
+    restatement (untested upstream: parity unpinned)."""
+    from oracle import wc_oracle as O
+    from wildcat_slam_b200 import synthetic as S
+
+    w = S.make_window("C1")
+    n = 3000  # a prefix keeps the fixture small
+    pts = w.points[:n].copy()
+    rng = np.random.default_rng(11)
+    k = len(pts) // 7
+    pts["x"][:k] = rng.uniform(-1.0, 1.0, k).astype(np.float32)
+    pts["y"][:k] = rng.uniform(-1.0, 1.0, k).astype(np.float32)
+    pts["z"][:k] = rng.uniform(-0.6, 0.6, k).astype(np.float32)
+    pts["x"][k:2 * k] = rng.uniform(-130.0, 130.0, k).astype(np.float32)
+    pts["y"][k:2 * k] = rng.uniform(-130.0, 130.0, k).astype(np.float32)
+    st, kept = O.filter_points(pts)
+    assert st == 0
+    st, und = O.undistort_sweep(w.imu, w.points[:n])
+    assert st == 0
+    xyz = lambda a: np.stack([a["x"], a["y"], a["z"]], 1)
+    np.savez_compressed(os.path.join(HERE, "c1_sweep_oracle.npz"), raw_xyz=xyz(pts), raw_t=pts["time"], kept_xyz=xyz(kept),
+                        kept_t=kept["time"], undistorted_xyz=xyz(und))
+    print("c1_sweep_oracle.npz", len(pts), len(kept))
+
+
 if __name__ == "__main__":
     notebook()
     c1()
+    sweep()

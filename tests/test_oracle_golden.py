@@ -271,3 +271,33 @@ def test_solve_reduces_cost_and_recovers_bias(oracle, c2_window):
     err1 = np.linalg.norm(w.samples["pos"] + smp["data_cor"][:, 3:6] - w.truth_sample_pos, axis=1)
     assert err1[-1] < 0.5 * err0[-1]
     np.testing.assert_allclose(smp["data_cor"][-1, 6:9], w.cfg.bg_true, atol=1.5e-3)
+
+
+def test_sweep_row_golden_regression(oracle):
+    """the oracle's sweep-preparation row (lidar_odometry.cc:489-496, 143-158) against the committed fixture
+    (tests/golden/make_golden.py: sweep) — a regression pin of the restatement; upstream has no test for it."""
+    import os
+
+    from wildcat_slam_b200 import synthetic as S
+    from wildcat_slam_b200 import types as T
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_sweep_oracle.npz"))
+    w = S.make_window("C1")
+    n = len(g["raw_t"])
+    pts = np.zeros(n, dtype=T.POINT48)
+    pts["x"], pts["y"], pts["z"], pts["time"] = g["raw_xyz"][:, 0], g["raw_xyz"][:, 1], g["raw_xyz"][:, 2], g["raw_t"]
+    st, kept = oracle.filter_points(pts)
+    assert st == 0 and len(kept) == len(g["kept_t"]) and 0 < len(kept) < n
+    assert np.array_equal(np.stack([kept["x"], kept["y"], kept["z"]], 1), g["kept_xyz"]) and np.array_equal(kept["time"], g["kept_t"])
+    # the default extrinsic maps (x, y, z) -> (-y - 0.001, -x - 0.00855, -z + 0.055) up to the 5e-8 off-diagonal terms
+    raw = g["raw_xyz"].astype(np.float64)
+    approx = np.stack([-raw[:, 1] - 0.001, -raw[:, 0] - 0.00855, -raw[:, 2] + 0.055], 1)
+    keep = (np.linalg.norm(approx, axis=1) >= 0.3) & (np.linalg.norm(approx, axis=1) <= 120.0) & ~(
+        (approx[:, 0] >= -0.8) & (approx[:, 0] <= 0.3) & (np.abs(approx[:, 1]) <= 0.5) & (np.abs(approx[:, 2]) <= 0.4))
+    assert abs(int(keep.sum()) - len(kept)) <= 2  # independent numpy restatement (boundary ties aside)
+    st, und = oracle.undistort_sweep(w.imu, w.points[:n])
+    assert st == 0 and np.array_equal(np.stack([und["x"], und["y"], und["z"]], 1), g["undistorted_xyz"])
+    # time-order violation against the last KEPT point aborts (CHECK lidar_odometry.cc:491)
+    bad = pts.copy()
+    bad["time"][n // 2] = bad["time"][0] - 1.0
+    assert oracle.filter_points(bad)[0] == T.WC_EINVAL_TIME_ORDER
