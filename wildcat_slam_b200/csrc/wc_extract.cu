@@ -22,8 +22,6 @@ using namespace wcd;
 
 namespace {
 
-constexpr int kWarp = 32;
-
 __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33;
   k *= 0xff51afd7ed558ccdull;
@@ -495,9 +493,6 @@ __device__ __forceinline__ unsigned level_key(unsigned leafbin, int level) {
 }
 __device__ __forceinline__ unsigned group_of(unsigned lk, int level) { return level == 2 ? lk : (level == 1 ? lk >> 3 : lk >> 6); }
 __device__ __forceinline__ unsigned node_of(unsigned lk, int level) { return level == 2 ? lk >> 12 : (level == 1 ? lk >> 15 : 0u); }
-__device__ __forceinline__ unsigned bin_of(unsigned lk, int level) {
-  return level == 2 ? (lk & 4095u) : (level == 1 ? ((lk >> 3) & 4095u) : (lk >> 6));
-}
 
 template <int NT>
 __device__ void bitonic_sort_smem(unsigned* keys, int npad) {
