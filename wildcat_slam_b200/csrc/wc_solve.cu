@@ -1113,6 +1113,16 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 #endif
   bool    valid = !s_fail;
   double* y     = B.step;
+  // the backward substitution of a system this size occupies one warp: the other warps clear the normal-equation buffer
+  // the next linearisation accumulates into, instead of doing that after the solve with everybody waiting
+  const bool zero_early = zero_next && Dp <= 32 * BS_SLOTS && t >= 32;
+  if (zero_early) {
+    const int nb = 1 - st->cur;
+    double2*  Hz = reinterpret_cast<double2*>(B.H[nb]);  // N = 12 K: N * N is even, cudaMalloc alignment
+    for (int i = t - 32; i < N * N / 2; i += LMT - 32) Hz[i] = make_double2(0.0, 0.0);
+    for (int i = t - 32; i < N; i += LMT - 32) B.g[nb][i] = 0.0;
+    if (t == 32) *B.cost[nb] = 0.0;
+  }
   if (valid) chol_backward_warp(A, D, Dp, rinv, y);  // y = -(S H S + diag/radius)^-1 g_s
   __syncthreads();
 #ifdef WC_LM_TIMING
@@ -1141,7 +1151,7 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 #ifdef WC_LM_TIMING
   tk[5] = clock64();
 #endif
-  if (zero_next) {
+  if (zero_next && Dp > 32 * BS_SLOTS) {  // wide systems: every thread took part in the backward sweep
     const int nb = 1 - st->cur;
     double2* Hz = reinterpret_cast<double2*>(B.H[nb]);  // N = 12 K: N * N is even, cudaMalloc alignment
     for (int i = t; i < N * N / 2; i += LMT) Hz[i] = make_double2(0.0, 0.0);
