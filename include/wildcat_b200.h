@@ -323,6 +323,18 @@ int64_t   wc_launch_count(const wc_ctx* ctx);
 wc_status wc_spline_fit_eval(wc_ctx* ctx, const double* ts, const double* pts3, size_t K, const double* query_t,
                              size_t nq, double* out3, uint8_t* valid);
 
+/* IMU forward prediction + new sample states — replaces steps 2-3 of
+ * LidarOdometry::PredictImuStatesAndSampleStates (lidar_odometry.cc:403-453) with PredictPoseOfNewImuState (:112-123).
+ * imu: n_imu states in/out; [0] and [1] carry poses (the tail of the window), [2..n) carry timestamp / acc / gyr and
+ * receive rot = rot_prev * Exp(((gyr_prev + gyr) / 2 - bg) dt) and pos = (R_pp (acc_pp - ba) + grav) dt^2 + 2 pos_prev - pos_pp.
+ * ba, bg, grav: those of the last sample state (:404-406).  samples_out: n_new sample states at
+ * t_last_sample + i * sample_dt, i = 1..n_new: lerp / slerp pose of the bracketing IMU states (:439-449), biases and
+ * gravity copied, pose corrections zero.  WC_EINVAL_TIME_ORDER replaces CHECK_NEAR :119 (uniform IMU spacing within
+ * 1e-6 s), WC_EOUT_OF_SPAN the CHECK_NE at :441-442. */
+wc_status wc_predict_states(wc_ctx* ctx, wc_imu_state* imu, size_t n_imu, const double* ba3, const double* bg3,
+                            const double* grav3, double t_last_sample, double sample_dt, size_t n_new,
+                            wc_sample_state* samples_out);
+
 /* Post-solve updates — replaces UpdateImuPoses + UpdateSamplePoses (lidar_odometry.cc:172-215):
  * spreads the sample corrections over the IMU states with the cubic B-spline, re-predicts the last IMU
  * state, folds the corrections into the sample poses and zeroes them.  In place. */

@@ -80,6 +80,10 @@ double wco_cubic_spline_interpolate(double s_1, double p_1, double s0, double p0
 /* UpdateImuPoses + UpdateSamplePoses, lidar_odometry.cc:172-215 */
 int wco_apply_corrections(wc_sample_state* samples, int64_t K, wc_imu_state* imu, int64_t n_imu);
 
+/* PredictImuStatesAndSampleStates steps 2-3 (lidar_odometry.cc:403-453) with PredictPoseOfNewImuState (:112-123) */
+int wco_predict_states(wc_imu_state* imu, int64_t n_imu, const double* ba3, const double* bg3, const double* grav3,
+                       double t_last_sample, double sample_dt, int64_t n_new, wc_sample_state* samples_out);
+
 /* UndistortSweep, lidar_odometry.cc:143-158 (a "next" row, used by the synthetic generator's checks) */
 int wco_undistort_sweep(const wc_imu_state* imu, int64_t n_imu, const wc_point48* in, int64_t n, wc_point48* out);
 

@@ -78,6 +78,15 @@ def undistort_sweep(imu, points):
     return st, out
 
 
+def predict_states(imu, ba, bg, grav, t_last_sample, sample_dt, n_new):
+    imu = np.ascontiguousarray(imu, dtype=T.IMU).copy()
+    out = np.zeros(max(1, n_new), dtype=T.SAMPLE)
+    v = [np.ascontiguousarray(a, dtype=np.float64) for a in (ba, bg, grav)]
+    st = lib().wco_predict_states(_p(imu), C.c_int64(len(imu)), _p(v[0]), _p(v[1]), _p(v[2]), C.c_double(t_last_sample),
+                                  C.c_double(sample_dt), C.c_int64(n_new), _p(out))
+    return st, imu, out[:n_new].copy()
+
+
 def filter_points(points, flt=None):
     flt = flt or T.default_sweep_filter()
     points = np.ascontiguousarray(points, dtype=T.POINT48)

@@ -6,6 +6,9 @@
 #include <vector>
 
 #include "wc_math.h"
+#include <cmath>
+#include <cstring>
+
 #include "wc_oracle.h"
 
 using namespace wco;
@@ -175,6 +178,38 @@ extern "C" int wco_apply_corrections(wc_sample_state* samples, int64_t K, wc_imu
     V3 t = V3(samples[k].data_cor + 3) + V3(samples[k].pos);
     q.storeCoeffs(samples[k].rot), t.store(samples[k].pos);
     for (int c = 0; c < 6; ++c) samples[k].data_cor[c] = 0;
+  }
+  return WC_OK;
+}
+
+// PredictImuStatesAndSampleStates steps 2-3, lidar_odometry.cc:403-453: forward-predict imu[2..n) from the two states in
+// front of them (PredictPoseOfNewImuState, :112-123, CHECK_NEAR on the spacing :119), then append n_new sample states at
+// t_last_sample + i * sample_dt with the lerp / slerp pose of the bracketing IMU states and the given biases / gravity.
+extern "C" int wco_predict_states(wc_imu_state* imu, int64_t n_imu, const double* ba3, const double* bg3, const double* grav3,
+                                  double t_last_sample, double sample_dt, int64_t n_new, wc_sample_state* samples_out) {
+  if (n_imu < 2) return WC_EINVAL;
+  const V3 ba(ba3), bg(bg3), grav(grav3);
+  for (int64_t k = 2; k < n_imu; ++k) {
+    const double d3 = imu[k].timestamp - imu[k - 1].timestamp, d2 = imu[k - 1].timestamp - imu[k - 2].timestamp;
+    if (!(std::fabs(d3 - d2) <= 1e-6)) return WC_EINVAL_TIME_ORDER;  // CHECK_NEAR :119
+    PredictPoseOfNewImuState(imu[k - 2], imu[k - 1], ba, bg, grav, imu[k]);
+  }
+  for (int64_t i = 1; i <= n_new; ++i) {
+    const double     t = t_last_sample + (double)i * sample_dt;  // :431
+    wc_sample_state& ss = samples_out[i - 1];
+    std::memset(&ss, 0, sizeof(ss));
+    ss.timestamp = t;
+    for (int c = 0; c < 3; ++c) ss.data_cor[6 + c] = bg3[c], ss.data_cor[9 + c] = ba3[c], ss.grav[c] = grav3[c];
+    int64_t lo = 0, hi = n_imu;  // std::lower_bound :439
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (imu[mid].timestamp < t) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0 || lo == n_imu) return WC_EOUT_OF_SPAN;  // CHECK_NE :441-442
+    const double f   = (t - imu[lo - 1].timestamp) / (imu[lo].timestamp - imu[lo - 1].timestamp);
+    const Q4     rot = Slerp(Q4::FromCoeffs(imu[lo - 1].rot), f, Q4::FromCoeffs(imu[lo].rot));
+    const V3     pos = (1 - f) * V3(imu[lo - 1].pos) + f * V3(imu[lo].pos);
+    rot.storeCoeffs(ss.rot), pos.store(ss.pos);
   }
   return WC_OK;
 }

@@ -127,3 +127,44 @@ def test_undistort_error_and_fused_resident_path(od, ctx, oracle):
     n, _ = rs.extract()
     got = rs.fetch()
     assert n == len(ref) > 0 and got.tobytes() == ref.tobytes()
+
+
+def test_predict_states_matches_oracle(od, ctx, oracle):
+    """SURVEY section 8(f) rank 2, first part: IMU forward prediction (PredictPoseOfNewImuState, lidar_odometry.cc:112-123)
+    and the new sample states (:430-453).  fp64 with a different sincos library and FMA contraction on the device:
+    stated tolerances, 400-step recurrences included."""
+    from wildcat_slam_b200.abi import WildcatError
+
+    w = S.make_window("C2")
+    imu = w.imu.copy()
+    imu["pos"][2:] = 0
+    imu["rot"][2:] = 0
+    ba, bg = np.array([0.01, -0.02, 0.03]), np.array([0.001, 0.002, -0.003])
+    t_last, sdt = float(w.samples["timestamp"][0]), 0.08
+    n_new = int((imu["timestamp"][-1] - t_last) / sdt)
+    st, imu_o, smp_o = oracle.predict_states(imu, ba, bg, S.GRAV, t_last, sdt, n_new)
+    assert st == 0 and n_new >= 20
+    imu_g, smp_g = od.PredictStates(imu, ba, bg, S.GRAV, t_last, sdt, n_new, ctx=ctx)
+    for f in ("timestamp", "acc", "gyr"):
+        assert np.array_equal(imu_g[f], imu_o[f])
+    np.testing.assert_allclose(imu_g["rot"], imu_o["rot"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(imu_g["pos"], imu_o["pos"], rtol=0, atol=1e-10)
+    assert np.array_equal(smp_g["timestamp"], smp_o["timestamp"]) and np.array_equal(smp_g["data_cor"], smp_o["data_cor"])
+    assert np.array_equal(smp_g["grav"], smp_o["grav"])
+    np.testing.assert_allclose(smp_g["rot"], smp_o["rot"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(smp_g["pos"], smp_o["pos"], rtol=0, atol=1e-10)
+    # with zero biases the prediction reproduces the generator's own (independent, numpy) forward prediction
+    imu0, _ = od.PredictStates(imu, np.zeros(3), np.zeros(3), S.GRAV, t_last, sdt, 0, ctx=ctx)
+    np.testing.assert_allclose(imu0["rot"], w.imu["rot"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(imu0["pos"], w.imu["pos"], rtol=0, atol=1e-10)
+    # CHECK_NEAR on the IMU spacing (:119) and CHECK_NE on the sample bracket (:441-442)
+    bad = imu.copy()
+    bad["timestamp"][10] += 1e-3
+    assert oracle.predict_states(bad, ba, bg, S.GRAV, t_last, sdt, 0)[0] == T.WC_EINVAL_TIME_ORDER
+    with pytest.raises(WildcatError) as e:
+        od.PredictStates(bad, ba, bg, S.GRAV, t_last, sdt, 0, ctx=ctx)
+    assert e.value.status == T.WC_EINVAL_TIME_ORDER
+    assert oracle.predict_states(imu, ba, bg, S.GRAV, float(imu["timestamp"][-1]), sdt, 1)[0] == T.WC_EOUT_OF_SPAN
+    with pytest.raises(WildcatError) as e:
+        od.PredictStates(imu, ba, bg, S.GRAV, float(imu["timestamp"][-1]), sdt, 1, ctx=ctx)
+    assert e.value.status == T.WC_EOUT_OF_SPAN

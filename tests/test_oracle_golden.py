@@ -301,3 +301,40 @@ def test_sweep_row_golden_regression(oracle):
     bad = pts.copy()
     bad["time"][n // 2] = bad["time"][0] - 1.0
     assert oracle.filter_points(bad)[0] == T.WC_EINVAL_TIME_ORDER
+
+
+def test_predict_states_against_numpy_restatement(oracle):
+    """the oracle's IMU forward prediction + sample-state creation (lidar_odometry.cc:112-123, 403-453) against an
+    independent numpy restatement (wildcat_slam_b200.synthetic: _predict / _pose_at, written for the generator)."""
+    from wildcat_slam_b200 import synthetic as S
+    from wildcat_slam_b200 import types as T
+
+    w = S.make_window("C1")
+    imu = w.imu.copy()
+    imu["pos"][2:] = 0
+    imu["rot"][2:] = 0
+    t_last, sdt = float(w.samples["timestamp"][0]), 0.08
+    n_new = int((imu["timestamp"][-1] - t_last) / sdt)
+    st, out, smp = oracle.predict_states(imu, np.zeros(3), np.zeros(3), S.GRAV, t_last, sdt, n_new)
+    assert st == 0 and n_new >= 3
+    np.testing.assert_allclose(out["rot"], w.imu["rot"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["pos"], w.imu["pos"], rtol=0, atol=1e-12)
+    pos, rot = S._pose_at(w.imu, smp["timestamp"])
+    np.testing.assert_allclose(smp["pos"], pos, rtol=0, atol=1e-12)
+    assert np.minimum(np.abs(smp["rot"] - rot).max(1), np.abs(smp["rot"] + rot).max(1)).max() < 1e-12
+    assert np.array_equal(smp["timestamp"], t_last + sdt * np.arange(1, n_new + 1)) and not smp["data_cor"].any()
+    ba, bg = np.array([0.01, -0.02, 0.03]), np.array([0.001, 0.002, -0.003])
+    st, out2, smp2 = oracle.predict_states(imu, ba, bg, S.GRAV, t_last, sdt, 1)
+    chk = imu.copy()
+    for i in range(2, len(chk)):
+        i1, i2, i3 = chk[i - 2], chk[i - 1], chk[i]
+        dt = i3["timestamp"] - i2["timestamp"]
+        chk["rot"][i] = S.quat_mul(i2["rot"], S.so3_exp((((i2["gyr"] + i3["gyr"]) / 2 - bg) * dt)[None])[0])
+        chk["pos"][i] = (S.quat_rotate(i1["rot"], i1["acc"] - ba) + S.GRAV) * dt * dt + 2 * i2["pos"] - i1["pos"]
+    np.testing.assert_allclose(out2["rot"], chk["rot"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out2["pos"], chk["pos"], rtol=0, atol=1e-12)
+    assert np.array_equal(smp2["data_cor"][0, 6:9], bg) and np.array_equal(smp2["data_cor"][0, 9:12], ba)
+    bad = imu.copy()
+    bad["timestamp"][5] += 1e-3
+    assert oracle.predict_states(bad, ba, bg, S.GRAV, t_last, sdt, 0)[0] == T.WC_EINVAL_TIME_ORDER
+    assert oracle.predict_states(imu, ba, bg, S.GRAV, float(imu["timestamp"][-1]), sdt, 1)[0] == T.WC_EOUT_OF_SPAN

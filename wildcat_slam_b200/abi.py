@@ -69,6 +69,7 @@ def load():
     lib.wc_window_evaluate.argtypes = [vp, *win, P(T.SolveOpts), P(dbl), vp, vp]
     lib.wc_spline_fit_eval.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp]
     lib.wc_apply_corrections.argtypes = [vp, vp, sz, vp, sz]
+    lib.wc_predict_states.argtypes = [vp, vp, sz, vp, vp, vp, dbl, dbl, sz, vp]
     lib.wc_pass_upload.argtypes = [vp, vp, sz, vp, sz, vp, sz]
     lib.wc_window_pass_resident.argtypes = [vp, P(T.SolveOpts), P(T.SolveSummary), vp, P(T.PassStats)]
     lib.wc_launch_count.argtypes = [vp]

@@ -195,6 +195,55 @@ __global__ void gather_corrections(const wc_sample_state* __restrict__ s, int K,
   ts[k] = s[k].timestamp;
 }
 
+// PredictImuStatesAndSampleStates steps 2-3 (lidar_odometry.cc:403-453) in one CTA:
+//   A (parallel)   dq_k = Exp(((g_{k-1} + g_k) / 2 - bg) dt_k), parked in imu[k].rot; spacing check (CHECK_NEAR :119)
+//   B (one thread) rot_k = rot_{k-1} * dq_k                      — the chain itself is sequential in the reference too
+//   C (parallel)   a_k = (R_{k-2} (acc_{k-2} - ba) + grav) dt dt, parked in imu[k].pos
+//   D (one thread) pos_k = a_k + 2 pos_{k-1} - pos_{k-2}
+//   E (parallel)   new sample states: lerp / slerp of the bracketing IMU states (:439-449)
+// The expensive parts (Exp: sincos; the rotations; slerp) run in parallel, the two recurrences cost a few FMAs per step.
+__global__ void __launch_bounds__(256)
+predict_states(wc_imu_state* __restrict__ imu, int n, V3 ba, V3 bg, V3 grav, double t_last, double sample_dt, int n_new,
+               wc_sample_state* __restrict__ out, int* __restrict__ err) {
+  const int t = threadIdx.x;
+  for (int k = 2 + t; k < n; k += 256) {
+    const double d3 = imu[k].timestamp - imu[k - 1].timestamp, d2 = imu[k - 1].timestamp - imu[k - 2].timestamp;
+    if (!(fabs(d3 - d2) <= 1e-6)) err[0] = WC_EINVAL_TIME_ORDER;
+    stq(imu[k].rot, Exp(((ld3(imu[k - 1].gyr) + ld3(imu[k].gyr)) / 2.0 - bg) * d3));
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int k = 2; k < n; ++k) stq(imu[k].rot, ldq(imu[k - 1].rot) * ldq(imu[k].rot));
+  __syncthreads();
+  for (int k = 2 + t; k < n; k += 256) {
+    const double dt = imu[k].timestamp - imu[k - 1].timestamp;
+    st3(imu[k].pos, (ldq(imu[k - 2].rot) * (ld3(imu[k - 2].acc) - ba) + grav) * dt * dt);
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int k = 2; k < n; ++k) st3(imu[k].pos, ld3(imu[k].pos) + 2.0 * ld3(imu[k - 1].pos) - ld3(imu[k - 2].pos));
+  __syncthreads();
+  for (int i = 1 + t; i <= n_new; i += 256) {
+    const double     ts = t_last + (double)i * sample_dt;
+    wc_sample_state& ss = out[i - 1];
+    ss.timestamp = ts;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ss.data_cor[c] = 0.0;
+    ss.data_cor[6] = bg.x, ss.data_cor[7] = bg.y, ss.data_cor[8] = bg.z;
+    ss.data_cor[9] = ba.x, ss.data_cor[10] = ba.y, ss.data_cor[11] = ba.z;
+    st3(ss.grav, grav);
+    const int idx = imu_lower_bound(imu, n, ts);
+    if (idx == 0 || idx == n) {  // CHECK_NE :441-442
+      err[0] = WC_EOUT_OF_SPAN;
+      continue;
+    }
+    const wc_imu_state &a = imu[idx - 1], &b = imu[idx];
+    const double        f = (ts - a.timestamp) / (b.timestamp - a.timestamp);
+    stq(ss.rot, Slerp(ldq(a.rot), f, ldq(b.rot)));
+    st3(ss.pos, (1 - f) * ld3(a.pos) + f * ld3(b.pos));
+  }
+}
+
 }  // namespace
 
 struct wc_spline_mem {
@@ -301,6 +350,30 @@ wc_status wc_update_surfel_poses_device(wc_ctx* c, const wc_imu_state* d_imu, si
   WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, c->stream));
   WC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (m->h_flags[2]) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the IMU state span (lidar_odometry.cc:164)");
+  return WC_OK;
+}
+
+extern "C" wc_status wc_predict_states(wc_ctx* c, wc_imu_state* imu, size_t n_imu, const double* ba3, const double* bg3,
+                                       const double* grav3, double t_last_sample, double sample_dt, size_t n_new,
+                                       wc_sample_state* samples_out) {
+  if (!c || !imu || n_imu < 2 || !ba3 || !bg3 || !grav3 || (n_new && !samples_out)) return WC_EINVAL;
+  if (n_new > (size_t)c->prm.max_samples || n_imu > (size_t)c->prm.max_imu_states) WC_FAIL(c, WC_ECAPACITY, "capacity exceeded");
+  wc_status s = spline_alloc(c, 0);
+  if (s) return s;
+  wc_spline_mem* m  = (wc_spline_mem*)c->d_spline;
+  cudaStream_t   st = c->stream;
+  WC_CUDA(c, cudaMemcpyAsync(m->imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
+  WC_CUDA(c, cudaMemsetAsync(m->flags, 0, 16, st));
+  { ++c->n_launches; predict_states<<<1, 256, 0, st>>>(m->imu, (int)n_imu, mk(ba3[0], ba3[1], ba3[2]), mk(bg3[0], bg3[1], bg3[2]),
+                                                        mk(grav3[0], grav3[1], grav3[2]), t_last_sample, sample_dt, (int)n_new, m->samples,
+                                                        m->flags); }
+  WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaMemcpyAsync(imu, m->imu, n_imu * sizeof(wc_imu_state), cudaMemcpyDeviceToHost, st));
+  if (n_new) WC_CUDA(c, cudaMemcpyAsync(samples_out, m->samples, n_new * sizeof(wc_sample_state), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (m->h_flags[0] == WC_EINVAL_TIME_ORDER) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "IMU samples are not uniformly spaced within 1e-6 s (lidar_odometry.cc:119)");
+  if (m->h_flags[0] == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "new sample time outside the predicted IMU states (lidar_odometry.cc:441-442)");
   return WC_OK;
 }
 

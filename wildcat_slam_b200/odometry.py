@@ -275,6 +275,19 @@ def ApplyCorrections(samples, imu_states, ctx=None):
     return s, imu
 
 
+def PredictStates(imu_states, ba, bg, grav, t_last_sample, sample_dt, n_new, ctx=None):
+    """Steps 2-3 of LidarOdometry::PredictImuStatesAndSampleStates (lidar_odometry.cc:403-453): forward-predict the poses
+    of imu_states[2:] (PredictPoseOfNewImuState) and create n_new sample states at t_last_sample + i * sample_dt."""
+    ctx = ctx or default_context()
+    imu = np.ascontiguousarray(imu_states, dtype=T.IMU).copy()
+    out = np.zeros(max(1, n_new), dtype=T.SAMPLE)
+    v = [np.ascontiguousarray(a, dtype=np.float64) for a in (ba, bg, grav)]
+    st = ctx.lib.wc_predict_states(ctx.handle, T.ptr(imu), len(imu), T.ptr(v[0]), T.ptr(v[1]), T.ptr(v[2]),
+                                   C.c_double(t_last_sample), C.c_double(sample_dt), n_new, T.ptr(out))
+    ctx.check(st, "wc_predict_states")
+    return imu, out[:n_new].copy()
+
+
 def FilterPoints(cloud, flt=None, ctx=None):
     """The per-point loop at the top of LidarOdometry::AddLidarScan (lidar_odometry.cc:489-496): lidar -> IMU extrinsic,
     range and blind-box filter; returns the kept points in order."""
