@@ -17,6 +17,8 @@
 //   Build*Residuals + ceres::Solve         lidar_odometry.cc:254-363,541-561  SolveWindow(...)
 //   CubicBSplineInterpolator               spline_interpolation.h:44-51     CubicBSplineInterpolator
 //   UpdateImuPoses + UpdateSamplePoses     lidar_odometry.cc:172-215        ApplyCorrections(samples, imu_states)
+//   AddLidarScan's extrinsic + filter      lidar_odometry.cc:489-496        FilterPoints(msg, points_buff)
+//   PredictImuStatesAndSampleStates 2-3    lidar_odometry.cc:403-453        PredictStates(imu_states, n_predicted, samples, dt, n_new)
 #pragma once
 #include <array>
 #include <cstring>
@@ -134,6 +136,39 @@ inline void BuildSurfels(const std::vector<Point>& cloud, std::deque<Surfel::Ptr
     auto s = std::make_shared<Surfel>();
     std::memcpy(static_cast<void*>(s.get()), &out[i], sizeof(wc_surfel));
     surfels.push_back(std::move(s));
+  }
+}
+
+// ---- the per-point loop at the top of AddLidarScan, lidar_odometry.cc:489-496: extrinsic + range / blind-box filter -----
+inline void FilterPoints(const std::vector<Point>& msg, std::deque<Point>& points_buff, const wc_sweep_filter* filter = nullptr,
+                         Context& ctx = Context::Default()) {
+  wc_sweep_filter f;
+  if (filter) f = *filter; else wc_default_sweep_filter(&f);
+  std::vector<Point> kept(msg.size());
+  size_t             n = 0;
+  ctx.Check(wc_filter_points(ctx.get(), &f, msg.data(), msg.size(), kept.data(), kept.size(), &n), "FilterPoints");
+  points_buff.insert(points_buff.end(), kept.begin(), kept.begin() + (std::ptrdiff_t)n);
+}
+
+// ---- steps 2-3 of PredictImuStatesAndSampleStates, lidar_odometry.cc:403-453 -------------------------------------------
+// imu_states: the last two states carry poses, the ones appended after them (timestamp / acc / gyr set) receive theirs;
+// n_new sample states are appended at sample_states.back()->timestamp + i * sample_dt with its biases and gravity.
+inline void PredictStates(std::deque<ImuState>& imu_states, size_t n_already_predicted, std::deque<SampleState::Ptr>& sample_states,
+                          double sample_dt, size_t n_new, Context& ctx = Context::Default()) {
+  if (n_already_predicted < 2 || n_already_predicted > imu_states.size() || sample_states.empty())
+    throw Error(WC_EINVAL, "PredictStates: need two predicted IMU states and one sample state");
+  std::vector<wc_imu_state> imu(imu_states.size() - n_already_predicted + 2);
+  for (size_t i = 0; i < imu.size(); ++i) std::memcpy(&imu[i], &imu_states[n_already_predicted - 2 + i], sizeof(wc_imu_state));
+  SampleState&                 last = *sample_states.back();
+  std::vector<wc_sample_state> added(n_new ? n_new : 1);
+  ctx.Check(wc_predict_states(ctx.get(), imu.data(), imu.size(), last.ba(), last.bg(), last.grav.data(), last.timestamp, sample_dt, n_new,
+                              added.data()),
+            "PredictStates");
+  for (size_t i = 2; i < imu.size(); ++i) std::memcpy(static_cast<void*>(&imu_states[n_already_predicted - 2 + i]), &imu[i], sizeof(wc_imu_state));
+  for (size_t i = 0; i < n_new; ++i) {
+    auto s = std::make_shared<SampleState>();
+    std::memcpy(static_cast<void*>(s.get()), &added[i], sizeof(wc_sample_state));
+    sample_states.push_back(std::move(s));
   }
 }
 

@@ -90,6 +90,25 @@ int main(int argc, char** argv) {
     }
     const bool outside_null = interp.Interp(0.2) == nullptr && interp.Interp(1.1) == nullptr;
 
+    // the rows around the path: FilterPoints (lidar_odometry.cc:489-496), UndistortSweep (:143-158), PredictStates (:403-453)
+    std::deque<wb::Point> points_buff;
+    wb::FilterPoints(points, points_buff);
+    std::vector<wb::Point> undistorted;
+    wb::UndistortSweep(points, ToDeque(ReadAll<wb::ImuState>(dir + "/imu.bin")), undistorted);
+    double und_sum = 0;
+    for (const auto& p : undistorted) und_sum += (double)p.x + (double)p.y + (double)p.z;
+    auto imu_pred = ToDeque(ReadAll<wb::ImuState>(dir + "/imu.bin"));  // poses of [2..) wiped, then re-predicted with zero biases
+    const auto imu_ref = imu_pred;
+    for (size_t i = 2; i < imu_pred.size(); ++i) imu_pred[i].pos = {0, 0, 0}, imu_pred[i].rot = {0, 0, 0, 0};
+    std::deque<wb::SampleState::Ptr> smp_pred;
+    smp_pred.push_back(std::make_shared<wb::SampleState>());
+    smp_pred[0]->timestamp = imu_ref[0].timestamp;
+    smp_pred[0]->grav      = {0.0, 0.0, -9.81};
+    wb::PredictStates(imu_pred, 2, smp_pred, 0.08, 2);
+    double pred_err = 0;
+    for (size_t i = 0; i < imu_pred.size(); ++i)
+      for (int k = 0; k < 3; ++k) pred_err = std::max(pred_err, std::abs(imu_pred[i].pos[k] - imu_ref[i].pos[k]));
+
     // error path: CHECK(pt.time >= back().time) (lidar_odometry.cc:491) -> Error{WC_EINVAL_TIME_ORDER}
     int  thrown = 0;
     auto bad    = points;
@@ -102,9 +121,10 @@ int main(int argc, char** argv) {
     }
 
     std::printf("surfels %zu fix %zu corr_sld %zu corr_fix %zu iterations %d termination %d initial_cost %.17g final_cost %.17g "
-                "residual_cor %.3g spline_err %.3g outside_null %d thrown %d\n",
+                "residual_cor %.3g spline_err %.3g outside_null %d thrown %d kept %zu und_sum %.17g pred_err %.3g new_samples %zu\n",
                 surfels_sld_win.size(), surfels_fix_win.size(), surfel_corrs_sld.size(), surfel_corrs_fix.size(), summary.num_iterations,
-                summary.termination, summary.initial_cost, summary.final_cost, residual_cor, spline_err, (int)outside_null, thrown);
+                summary.termination, summary.initial_cost, summary.final_cost, residual_cor, spline_err, (int)outside_null, thrown,
+                points_buff.size(), und_sum, pred_err, smp_pred.size() - 1);
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "mirror_test failed: %s\n", e.what());

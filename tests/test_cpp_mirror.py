@@ -56,6 +56,8 @@ def test_mirror_pipeline_equals_python_mirror(tmp_path):
         m = od.KnnSurfelMatcher(ctx); m.BuildIndex(sld); cs, _ = m.Match(sld)
         m2 = od.KnnSurfelMatcher(ctx); m2.BuildIndex(fix); cf, _ = m2.Match(sld)
         smp, sg = od.SolveWindow(sld, fix, cs, cf, w.imu, w.samples, ctx=ctx)
+        kept = od.FilterPoints(w.points, ctx=ctx)
+        und = od.UndistortSweep(w.points, w.imu, ctx=ctx)
     finally:
         ctx.close()
     assert int(out["surfels"]) == len(sld) > 0 and int(out["fix"]) == len(fix)
@@ -72,3 +74,7 @@ def test_mirror_pipeline_equals_python_mirror(tmp_path):
     assert float(out["residual_cor"]) == 0.0                                     # UpdateSamplePoses zeroes the corrections
     assert float(out["spline_err"]) < 1e-6 and out["outside_null"] == "1"        # spline_interpolation_test.cc:79-96, :52-54
     assert int(out["thrown"]) == T.WC_EINVAL_TIME_ORDER                           # CHECK lidar_odometry.cc:491
+    assert int(out["kept"]) == len(kept)                                          # FilterPoints
+    und_sum = float(und["x"].astype(np.float64).sum() + und["y"].astype(np.float64).sum() + und["z"].astype(np.float64).sum())
+    assert float(out["und_sum"]) == pytest.approx(und_sum, rel=1e-9)              # UndistortSweep (same kernel; summation order only)
+    assert float(out["pred_err"]) < 1e-10 and int(out["new_samples"]) == 2        # PredictStates reproduces the generator's prediction
