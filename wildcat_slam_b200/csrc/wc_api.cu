@@ -89,17 +89,21 @@ extern "C" wc_status wc_create(const wc_params* p, int device, wc_ctx** out) {
   if (!c) return WC_EINVAL;
   if (p) c->prm = *p; else wc_default_params(&c->prm);
   c->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) { free(c); return WC_ECUDA; }
+  // every failure below goes through wc_destroy, which tolerates the still-zeroed fields
+  bool ok = cudaSetDevice(device) == cudaSuccess;
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(c); return WC_ECUDA; }
-  c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : WC_NUM_SMS_FALLBACK;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { free(c); return WC_ECUDA; }
-  for (int i = 0; i < 3; ++i)
-    if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { free(c); return WC_ECUDA; }
-  if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { free(c); return WC_ECUDA; }
-  for (int i = 0; i < 8; ++i)
-    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { free(c); return WC_ECUDA; }
+  ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+  if (ok) c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : WC_NUM_SMS_FALLBACK;
+  ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i < 3; ++i)
+    ok = cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  if (!ok) {
+    wc_destroy(c);
+    return WC_ECUDA;
+  }
   c->rank = 0, c->world = 1;
   c->knn_grid_min = 512;
   c->lm_batch = 8;
@@ -112,17 +116,23 @@ extern "C" wc_status wc_create(const wc_params* p, int device, wc_ctx** out) {
 extern "C" void wc_destroy(wc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 3; ++i)
+    if (c->side[i]) cudaStreamSynchronize(c->side[i]);
   wc_comm_free(c);
   wc_extract_free(c);
   wc_match_free(c);
   wc_solve_free(c);
   wc_spline_free(c);
   wc_sweep_free(c);
-  for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
-  for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->side[i]), cudaEventDestroy(c->ev_join[i]);
-  cudaEventDestroy(c->ev_fork);
-  cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 8; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 3; ++i) {
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->stream) cudaStreamDestroy(c->stream);
   free(c);
 }
 

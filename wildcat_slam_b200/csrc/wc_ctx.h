@@ -130,6 +130,7 @@ struct wc_ctx {
   void*   d_grid;      // GridBufs (host copy of the device pointers)
   double* d_part_d;    // partial top-k lists of the tiled exhaustive kNN stage
   int*    d_part_i;
+  int     match_query_first;  // last match produced at least one pair whose FIRST surfel is the query
   long long knn_grid_min;  // target count from which the uniform-grid kNN replaces the brute-force scan
 
   // ---- window solve

@@ -979,6 +979,9 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
 
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
   WC_CUDA(c, cudaMemsetAsync(c->d_xstat, 0, sizeof(wc_extract_status), st));
+  // the emit kernels add to the time-bucket counters before any error is known: clear them on every call, so that a
+  // call that returned early (time order / range / capacity) cannot leave stale counts behind
+  WC_CUDA(c, cudaMemsetAsync(c->d_bcnt, 0, SORT_NB * 4, st));
   // cell table sized to this sweep (worst case one cell per point still fits; typical load is ~0.2)
   const size_t hcap = wc_next_pow2(n < 1024 ? 1024 : (size_t)n);
   WC_CUDA(c, cudaMemsetAsync(c->d_htab, 0xff, hcap * sizeof(HEnt), st));

@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(1024) pair_count(const int* __restrict__ acc, 
 __global__ void __launch_bounds__(1024)
 pair_scatter(const int* __restrict__ acc, int nq, const int* __restrict__ blk_cnt, const double* __restrict__ qf,
              const double* __restrict__ tf, wc_corr_idx* __restrict__ out, unsigned char* __restrict__ first_is_target,
-             int* __restrict__ n_out) {
+             int* __restrict__ n_out /* [0] pair count, [2] set when a pair has the QUERY first */) {
   __shared__ int warp_sums[32];
   __shared__ int s_base;
   const int t = threadIdx.x, lane = t & 31, i = blockIdx.x * 1024 + t;
@@ -560,6 +560,7 @@ pair_scatter(const int* __restrict__ acc, int nq, const int* __restrict__ blk_cn
     out[pos].s1            = query_first ? i : c;
     out[pos].s2            = query_first ? c : i;
     first_is_target[pos]   = query_first ? 0 : 1;
+    if (query_first) n_out[2] = 1;
   }
   if (blockIdx.x == gridDim.x - 1 && t == 1023) *n_out = pos + v;
 }
@@ -720,6 +721,7 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
     if (cs) return cs;
   }
   *n_out = (size_t)c->h_flag[1];
+  c->match_query_first = c->h_flag[3];
   if (getenv("WC_DEBUG")) fprintf(stderr, "[wc_match] nq=%zu nt=%zu self=%d pairs=%d\n", nq, nt, self_match, c->h_flag[1]);
   return WC_OK;
 }
@@ -762,6 +764,8 @@ extern "C" wc_status wc_knn6(wc_ctx* c, const double* query6, size_t nq, const d
   if (!c || !query6 || !target6 || !out_idx || !out_dist2) return WC_EINVAL;
   if (k < 1 || k > KMAX) WC_FAIL(c, WC_EINVAL, "k must be 1..%d", KMAX);
   if (nq > (size_t)c->prm.max_surfels || nt > (size_t)c->prm.max_surfels) WC_FAIL(c, WC_ECAPACITY, "too many vectors");
+  // the reference reads k_indices[0..k) whatever the target count (undefined behaviour, knn_surfel_matcher.cc:60-62)
+  if (nq && nt < (size_t)k) WC_FAIL(c, WC_ETOO_FEW_TARGETS, "%zu targets for a %d-nearest-neighbour search", nt, k);
   wc_status s = match_alloc(c);
   if (s) return s;
   cudaStream_t st = c->stream;

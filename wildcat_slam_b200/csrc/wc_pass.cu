@@ -44,6 +44,9 @@ extern "C" wc_status wc_window_pass_resident(wc_ctx* c, const wc_solve_opts* opt
   if (n_sc) WC_CUDA(c, cudaMemcpyAsync(c->d_sld_corr, c->d_corr_out, n_sc * sizeof(wc_corr_idx), cudaMemcpyDeviceToDevice, st));
   if ((s = wc_match_device(c, c->d_sld, S, c->d_fix, c->n_fix, 0, &n_fc))) return s;
   if (n_sc + n_fc > (size_t)c->prm.max_corrs) WC_FAIL(c, WC_ECAPACITY, "too many correspondences");
+  // the fixed-window residuals read a pair as (fixed, sliding): CHECK_LT(s1.t, s2.t), lidar_odometry.cc:301
+  if (n_fc && c->match_query_first)
+    WC_FAIL(c, WC_EINVAL_TIME_ORDER, "a fixed-window surfel is not older than the sliding-window surfel it was matched to");
   if (n_fc) WC_CUDA(c, cudaMemcpyAsync(c->d_fix_corr, c->d_corr_out, n_fc * sizeof(wc_corr_idx), cudaMemcpyDeviceToDevice, st));
   c->n_sld_corr = n_sc, c->n_fix_corr = n_fc;
   ps.n_sld_corr = (int64_t)n_sc, ps.n_fix_corr = (int64_t)n_fc;

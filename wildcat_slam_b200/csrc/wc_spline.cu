@@ -174,6 +174,7 @@ __global__ void repredict_and_update_samples(wc_imu_state* __restrict__ imu, int
       const wc_sample_state& b = s[K - 1];
       const V3 ba = ld3(b.data_cor + 9), bg = ld3(b.data_cor + 6), grav = ld3(b.grav);
       const double dt = i3.timestamp - i2.timestamp;
+      if (!(fabs(dt - (i2.timestamp - i1.timestamp)) <= 1e-6)) *err = WC_EINVAL_TIME_ORDER;  // CHECK_NEAR :119
       stq(i3.rot, ldq(i2.rot) * Exp(((ld3(i2.gyr) + ld3(i3.gyr)) / 2.0 - bg) * dt));
       st3(i3.pos, (ldq(i1.rot) * (ld3(i1.acc) - ba) + grav) * dt * dt + 2.0 * ld3(i2.pos) - ld3(i1.pos));
     }
@@ -396,11 +397,15 @@ extern "C" wc_status wc_apply_corrections(wc_ctx* c, wc_sample_state* samples, s
                                                                            samples[K - 1].timestamp, m->imu, (int)n_imu, m->flags); }
   { ++c->n_launches; repredict_and_update_samples<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(m->imu, (int)n_imu, m->samples, (int)K, m->flags,
                                                                             m->flags + 2); }
+  // the flags come back first: on an error the caller's arrays stay untouched (the reference would have aborted)
   WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (m->h_flags[2] == WC_EINVAL_TIME_ORDER)
+    WC_FAIL(c, WC_EINVAL_TIME_ORDER, "trailing IMU samples are not uniformly spaced within 1e-6 s (lidar_odometry.cc:119)");
+  if (m->h_flags[2]) WC_FAIL(c, WC_EOUT_OF_SPAN, "IMU states are not exactly covered by the sample span (lidar_odometry.cc:209-210)");
   WC_CUDA(c, cudaMemcpyAsync(samples, m->samples, K * sizeof(wc_sample_state), cudaMemcpyDeviceToHost, st));
   if (n_imu) WC_CUDA(c, cudaMemcpyAsync(imu, m->imu, n_imu * sizeof(wc_imu_state), cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
-  WC_CUDA(c, cudaGetLastError());
-  if (m->h_flags[2]) WC_FAIL(c, WC_EOUT_OF_SPAN, "IMU states are not exactly covered by the sample span (lidar_odometry.cc:209-210)");
   return WC_OK;
 }
