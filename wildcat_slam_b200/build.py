@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or not os.path.exists(OUT):
+    if force or procs or not os.path.exists(OUT) or any(_newer(o, OUT) for o in objs):
         subprocess.check_call([nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart"])
     return OUT
 

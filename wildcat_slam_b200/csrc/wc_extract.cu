@@ -15,6 +15,8 @@
 // boundary between consecutive non-empty bins exists iff t_min(next) - t_max(prev) > gap — the same fp64
 // subtraction on the same two operands the reference performs, because those two points are consecutive in the
 // node's time-ordered list.
+#include <math.h>
+
 #include "wc_ctx.h"
 #include "wc_device_math.cuh"
 
@@ -32,24 +34,38 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
 }
 
 struct ExtractParams {
-  double voxel;     // (double)(float)voxel_size
-  double inv_voxel; // 1 / voxel (rounded): only proposes the quotient, voxel_floor() makes it exact
-  double q0, q1;    // (double)(float)(voxel/4), (double)(float)(voxel/8)
   double t_first;
+  float  v4, inv_v4, v8;  // leaf-cell width voxel/4 (exact in float32), its rounded reciprocal, half width voxel/8
   int    vox0[3];
   int    n;
 };
 
-// floor(RN(x / v)) without the division, bit-exact for x = (double)float32 and v = (double)float32, |x / v| < 2^21:
-// x and every k * v are multiples of 2^-24 * 2^e grids coarse enough that x / v is either an exact integer or at least
-// 2^-26 away from one, far more than the half-ulp by which the rounded quotient can move — so floor(RN(x / v)) equals
-// the floor of the exact quotient.  The reciprocal multiply proposes q (off by at most one); the products q * v and
-// (q + 1) * v are exact in fp64 (21 + 24 bits), so the two comparisons against x decide the floor exactly.
-__device__ __forceinline__ double voxel_floor(double x, double v, double inv_v) {
-  double q = floor(__dmul_rn(x, inv_v));
-  if (x < __dmul_rn(q, v)) q -= 1.0;
-  else if (x >= __dmul_rn(q + 1.0, v)) q += 1.0;
-  return q;
+// axis_cell: x float32, v4 = voxel/4 (exact in float32).  y = RN(x * RN(1/v4)) is within 2^-6 of x / v4 (|x / v4| < 2^22),
+// so g0 = round-to-nearest(y) (magic-number add) is floor(x / v4) or floor + 1.  r0 = fma(-g0, v4, x) is the CORRECTLY
+// ROUNDED value of x - g0 v4: its sign is exact, hence g = g0 - [r0 < 0] is exactly floor(x / v4), and r = fma(-g, v4, x)
+// is zero iff x lies exactly on a cell face.  The reference (surfel_extraction.h:59-64, .cc:148-166,209-211) evaluates
+// floor(x / v), (0.5 + k) v, c +- v/4, c +- v/8 in double; all of these are exact there (products of a <= 22-bit integer
+// and the 24-bit v), so its cell decisions are the exact ones too: voxel = g >> 2, child index along the axis
+// f = g & 3 — except ON a face (r == 0), where the strict '>' sends the point to the lower cell unless that would leave
+// the voxel.  The fixed-point offset from the leaf centre (2 g' + 1) v8 is one more fused multiply-add: exact whenever
+// |x| >= 2^-4 m (the offset is then a multiple of 2^-27 below 2^-3), rounded by at most 0.75 * 2^-27 m closer to the axis.
+// tests/test_voxel_floor.py checks all of this against the reference's double-precision formulas.
+__device__ __forceinline__ bool axis_cell(float x, const ExtractParams& P, int& q, int& f, int& rel) {
+  const float MAGIC = 12582912.f;  // 1.5 * 2^23
+  const float y     = __fmul_rn(x, P.inv_v4);
+  const float gm    = __fadd_rn(y, MAGIC);
+  int         g     = __float_as_int(gm) - 0x4B400000;
+  float       gf    = __fadd_rn(gm, -MAGIC);
+  const float r0    = __fmaf_rn(-gf, P.v4, x);
+  if (r0 < 0.f) g -= 1, gf = __fadd_rn(gf, -1.f);
+  const float r    = __fmaf_rn(-gf, P.v4, x);
+  const int   gl   = g & 3;
+  const bool  face = (r == 0.f) && gl != 0;
+  q                = g >> 2;
+  f                = gl - (face ? 1 : 0);
+  const float gc   = __fmaf_rn(face ? __fadd_rn(gf, -1.f) : gf, 2.f, 1.f);  // 2 g' + 1: exact
+  rel              = __float2int_rn(__fmul_rn(__fmaf_rn(-gc, P.v8, x), (float)WC_COORD_SCALE));
+  return fabsf(y) < 4.0e6f;  // also false for NaN / Inf
 }
 
 // ---------------------------------------------------------------------------------------------- K0
@@ -112,32 +128,21 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
       const float4 p  = xyz[i];
       const double tt = time[i];
       if (i > 0 && tt < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
-      const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-      // VoxelLoc, surfel_extraction.h:59-64: floor(pos / resolution), resolution = (double)0.8f  (Q2)
-      const double fvx = voxel_floor(x, P.voxel, P.inv_voxel), fvy = voxel_floor(y, P.voxel, P.inv_voxel),
-                   fvz = voxel_floor(z, P.voxel, P.inv_voxel);
-      const int    vx = (int)fvx, vy = (int)fvy, vz = (int)fvz;
-      // root centre (surfel_extraction.cc:209-211) and the two child descents (:148-166)
-      double cx = __dmul_rn(0.5 + fvx, P.voxel), cy = __dmul_rn(0.5 + fvy, P.voxel), cz = __dmul_rn(0.5 + fvz, P.voxel);
-      int bx = x > cx, by = y > cy, bz = z > cz;
-      const int c1 = 4 * bx + 2 * by + bz;
-      cx += bx ? P.q0 : -P.q0, cy += by ? P.q0 : -P.q0, cz += bz ? P.q0 : -P.q0;
-      bx = x > cx, by = y > cy, bz = z > cz;
-      const int c2 = 4 * bx + 2 * by + bz;
-      cx += bx ? P.q1 : -P.q1, cy += by ? P.q1 : -P.q1, cz += bz ? P.q1 : -P.q1;
-      const int leaf = 8 * c1 + c2;
-      if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
-      // exact fixed-point coordinates relative to the leaf-cell centre, exact fixed-point time
+      // VoxelLoc (surfel_extraction.h:59-64), the two child descents (.cc:148-166) and the exact fixed-point offset
+      // from the leaf-cell centre, in float32 / integer arithmetic (axis_cell)
+      int  vx, vy, vz, fx, fy, fz;
       int4 q;
-      q.x = (int)__double2ll_rn((x - cx) * WC_COORD_SCALE);
-      q.y = (int)__double2ll_rn((y - cy) * WC_COORD_SCALE);
-      q.z = (int)__double2ll_rn((z - cz) * WC_COORD_SCALE);
+      bool ok = axis_cell(p.x, P, vx, fx, q.x);
+      ok      = axis_cell(p.y, P, vy, fy, q.y) && ok;
+      ok      = axis_cell(p.z, P, vz, fz, q.z) && ok;
+      const int leaf = ((fx >> 1) << 5) | ((fy >> 1) << 4) | ((fz >> 1) << 3) | ((fx & 1) << 2) | ((fy & 1) << 1) | (fz & 1);
+      if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
       const long long Q   = __double2ll_rn((tt - P.t_first) * WC_TIME_SCALE);
       const long long bin = Q >> WC_BIN_SHIFT;
       q.w                 = (int)(Q - (bin << WC_BIN_SHIFT));
       pay[l]              = q;
       const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
-      if ((unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
+      if (!ok || (unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
           Q < 0 || bin >= WC_MAX_BINS)
         st->err_range = 1;
       else
@@ -972,8 +977,9 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   cudaStream_t st = c->stream;
   const float  vsf = c->prm.voxel_size;
   ExtractParams P;
-  P.voxel = (double)vsf, P.q0 = (double)(float)(vsf / 4), P.q1 = (double)(float)((float)(vsf / 4) / 2);
-  P.inv_voxel = 1.0 / P.voxel;
+  P.v4 = vsf / 4, P.v8 = vsf / 8, P.inv_v4 = 1.0f / P.v4;  // divisions by powers of two: exact
+  if (!(vsf > 0.f) || !isfinite(vsf) || (double)P.v8 * WC_COORD_SCALE >= 1073741824.0 || (double)P.v4 * 4 != (double)vsf)
+    WC_FAIL(c, WC_EINVAL, "voxel_size out of range");
   P.t_first = c->t_first, P.n = n;
   for (int k = 0; k < 3; ++k) P.vox0[k] = c->vox0[k];
 
@@ -995,7 +1001,7 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   { ++c->n_launches; voxel_scan<<<1, 1024, 0, st>>>(c->d_vox_count, c->d_vox_off, c->d_xstat); }
   { ++c->n_launches; voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vox_off, c->d_vox_cursor, c->d_seg); }
   EmitParams E;
-  E.voxel = P.voxel, E.q0 = P.q0, E.q1 = P.q1, E.t_first = P.t_first;
+  E.voxel = (double)vsf, E.q0 = (double)P.v4, E.q1 = (double)P.v8, E.t_first = P.t_first;
   E.thr = (double)c->prm.planer_threshold, E.min_like = c->prm.min_plane_likeness, E.gap = c->prm.cluster_time_gap;
   for (int k = 0; k < 3; ++k) E.view[k] = c->prm.view_point[k], E.vox0[k] = c->vox0[k], E.lps[k] = c->prm.layer_point_size[k];
   E.cmin = c->prm.cluster_min_points, E.max_layer = c->prm.max_layer;
