@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WC_ABI_VERSION 1
+#define WC_ABI_VERSION 2
 
 typedef enum wc_status {
   WC_OK                = 0,
@@ -135,6 +135,12 @@ typedef struct wc_params {
   int32_t max_imu_states;
 } wc_params;
 
+/* arithmetic of the fused lidar residual + Jacobian + J^T J kernel (BASELINE config 5: fp64 vs fp32 tolerance sweep).
+ * The IMU factors, the normal equations the tiles are summed into and the LM step are always fp64. */
+enum { WC_PREC_F64 = 0,   /* fp64 records, evaluation and accumulation (the reference's arithmetic; default)      */
+       WC_PREC_MIXED = 1, /* fp32 records (64 B instead of 128 B) and evaluation, fp64 J^T J accumulation           */
+       WC_PREC_F32 = 2 }; /* fp32 records, evaluation and per-tile J^T J accumulation, fp64 sums across tiles       */
+
 enum { WC_JAC_REFERENCE_OVERWRITE = 0, /* reproduce cost_functor.h:152-175 aliasing (Q1) */
        WC_JAC_EXACT = 1 };
 
@@ -153,6 +159,8 @@ typedef struct wc_solve_opts {
   double  function_tolerance;          /* 1e-6 */
   double  gradient_tolerance;          /* 1e-10 */
   double  parameter_tolerance;         /* 1e-8 */
+  int32_t precision;                   /* WC_PREC_F64 */
+  int32_t _pad;
 } wc_solve_opts;
 
 enum { WC_TERM_NO_CONVERGENCE = 0, WC_TERM_FUNCTION_TOL = 1, WC_TERM_GRADIENT_TOL = 2,

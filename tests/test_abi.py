@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     missing = [n for n in names if n not in exported]
     assert not missing, f"declared in wildcat_b200.h but not exported: {missing}"
-    assert lib.wc_abi_version() == 1
+    assert lib.wc_abi_version() == 2
 
 
 def test_struct_sizes_match_header(tmp_path):

@@ -63,6 +63,7 @@ extern "C" void wc_default_solve_opts(wc_solve_opts* o) {
   o->function_tolerance          = 1e-6;
   o->gradient_tolerance          = 1e-10;
   o->parameter_tolerance         = 1e-8;
+  o->precision                   = WC_PREC_F64;
 }
 
 extern "C" const char* wc_status_str(wc_status s) {

@@ -17,9 +17,12 @@
 #include <stdlib.h>
 
 #include "wc_ctx.h"
+#include <cooperative_groups.h>
+
 #include "wc_device_math.cuh"
 
 using namespace wcd;
+namespace cg = cooperative_groups;
 
 wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate);  // wc_comm.cu; no-op when world == 1
 wc_status wc_comm_check(wc_ctx* c);
@@ -66,6 +69,7 @@ struct SolveBufs {
   double* diag;     // D
   double* step;     // D
   double* A;        // D*D workspace when it does not fit shared memory
+  int*    act;      // wide systems: reduced columns some factor touches (H_cc != 0 at the first linearisation); act[D] = count
   LMState* st;
   int     N;        // 12 K
   int     fix_first;
@@ -200,8 +204,12 @@ __global__ void bucket_scatter(const double* __restrict__ tmp, const int* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ K5
+template <int PREC> struct TJSel { using type = double; };
+template <> struct TJSel<WC_PREC_F32> { using type = float; };
+
 struct LinArgs {
   const double* rec;
+  const float*  rec32;  // fp32 copy of the sorted records (WC_PREC_MIXED / WC_PREC_F32)
   int           stride, n_rec;
   SolveBufs     B;
   int           at_candidate;  // 0: linearise at x into buffer cur; 1: at xc into buffer 1-cur
@@ -266,6 +274,98 @@ __device__ __forceinline__ void lidar_eval(const double* __restrict__ rec, size_
   J[21] = -sr * g2r * wn.x, J[22] = -sr * g2r * wn.y, J[23] = -sr * g2r * wn.z;
 }
 
+
+// ---- fp32 evaluation of one lidar factor (WC_PREC_MIXED / WC_PREC_F32): same formulas as lidar_eval, single precision.
+// The rotation matrix comes from Rodrigues' formula instead of the quaternion detour; Jr(r) = A I + B a a^T - C Hat(a).
+struct F3 {
+  float x, y, z;
+};
+__device__ __forceinline__ F3 f3(float x, float y, float z) { return F3{x, y, z}; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return F3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 operator*(float s, F3 a) { return F3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float fdot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 fcross(F3 a, F3 b) { return F3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+struct Rod {
+  float A, B, C, D;  // sin(th)/th, (1 - sin(th)/th)/th^2, (1 - cos(th))/th^2, th^2
+};
+__device__ __forceinline__ Rod rodrigues(F3 r) {
+  const float t2 = fdot(r, r);
+  Rod         k;
+  k.D = t2;
+  if (t2 < 1e-8f) {
+    k.A = 1.f - t2 * (1.f / 6.f), k.B = 1.f / 6.f - t2 * (1.f / 120.f), k.C = 0.5f - t2 * (1.f / 24.f);
+  } else {
+    const float th = sqrtf(t2);
+    float       sn, cs;
+    sincosf(th, &sn, &cs);
+    k.A = sn / th, k.B = (1.f - k.A) / t2, k.C = (1.f - cs) / t2;
+  }
+  return k;
+}
+// Exp(r) v = v + A (r x v) + C r x (r x v);  Exp(r)^T u = Exp(-r) u
+__device__ __forceinline__ F3 rot_apply(const Rod& k, F3 r, F3 v, float sign) {
+  const F3 rv = fcross(r, v);
+  return v + (sign * k.A) * rv + k.C * fcross(r, rv);
+}
+// w^T Jr(r) = A w + B (w . r) r - C (w x r)   (Jr(r) = Jl(-r), utils.h:35-49; A, B, C per unit of |r|^2 absorbed)
+__device__ __forceinline__ F3 row_times_Jr(const Rod& k, F3 r, F3 w) { return k.A * w + (k.B * fdot(w, r)) * r - k.C * fcross(w, r); }
+
+template <typename TJ>
+__device__ __forceinline__ void lidar_eval32(const float* __restrict__ rec, size_t S, int i, const double* __restrict__ x, int jac_mode,
+                                             float cb, float cc, TJ J[24], TJ& r_out, double& cost_out, int& b1l, int& b2l, int& bk) {
+  const float* o  = rec + i;
+  const F3     v1 = f3(o[0 * S], o[1 * S], o[2 * S]), v2 = f3(o[3 * S], o[4 * S], o[5 * S]);
+  const F3     d0 = f3(o[6 * S], o[7 * S], o[8 * S]), wn = f3(o[9 * S], o[10 * S], o[11 * S]);
+  const float  f1 = o[12 * S], f2 = o[13 * S];
+  const int    w14 = __float_as_int(o[14 * S]), w15 = __float_as_int(o[15 * S]);
+  b1l = w14 >> 16, b2l = w14 & 0xffff;
+  const int mode = w15 >> 24;
+  bk             = w15 & 0xffffff;
+  const double* x2l = x + 12 * b2l;
+  const F3 r2 = (1.f - f2) * f3((float)x2l[0], (float)x2l[1], (float)x2l[2]) + f2 * f3((float)x2l[12], (float)x2l[13], (float)x2l[14]);
+  const F3 t2 = (1.f - f2) * f3((float)x2l[3], (float)x2l[4], (float)x2l[5]) + f2 * f3((float)x2l[15], (float)x2l[16], (float)x2l[17]);
+  const Rod k2 = rodrigues(r2);
+  F3        r1 = f3(0, 0, 0), t1 = f3(0, 0, 0);
+  Rod       k1 = Rod{1.f, 1.f / 6.f, 0.5f, 0.f};
+  const bool unary = b1l < 0;
+  if (!unary) {
+    const double* x1l = x + 12 * b1l;
+    r1 = (1.f - f1) * f3((float)x1l[0], (float)x1l[1], (float)x1l[2]) + f1 * f3((float)x1l[12], (float)x1l[13], (float)x1l[14]);
+    t1 = (1.f - f1) * f3((float)x1l[3], (float)x1l[4], (float)x1l[5]) + f1 * f3((float)x1l[15], (float)x1l[16], (float)x1l[17]);
+    k1 = rodrigues(r1);
+  }
+  const F3    e   = (rot_apply(k1, r1, v1, 1.f) + t1 + d0) - (rot_apply(k2, r2, v2, 1.f) + t2);
+  const float r   = fdot(wn, e);
+  const float s   = r * r;
+  const float sum = 1.f + s * cc, inv = 1.f / sum;
+  cost_out        = 0.5 * (double)(cb * logf(sum));
+  const float sr  = sqrtf(fmaxf(FLT_MIN, inv));
+  r_out           = (TJ)(r * sr);
+  // a2 = wn^T R2 Hat(v2) Jr(r2) = ((R2^T wn) x v2)^T Jr(r2);  a1 likewise with -wn
+  const F3 a2 = row_times_Jr(k2, r2, fcross(rot_apply(k2, r2, wn, -1.f), v2));
+  float    g1l = 1.f - f1, g1r = f1;
+  const float g2l = 1.f - f2, g2r = f2;
+  if (jac_mode == WC_JAC_REFERENCE_OVERWRITE) {
+    if (mode == 1) g1r = 0.f;
+    if (mode == 2) g1l = 0.f, g1r = 0.f;
+  }
+  if (unary) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) J[k] = (TJ)0;
+  } else {
+    const F3 a1 = row_times_Jr(k1, r1, fcross(rot_apply(k1, r1, -1.f * wn, -1.f), v1));
+    J[0] = (TJ)(sr * g1l * a1.x), J[1] = (TJ)(sr * g1l * a1.y), J[2] = (TJ)(sr * g1l * a1.z);
+    J[3] = (TJ)(sr * g1l * wn.x), J[4] = (TJ)(sr * g1l * wn.y), J[5] = (TJ)(sr * g1l * wn.z);
+    J[6] = (TJ)(sr * g1r * a1.x), J[7] = (TJ)(sr * g1r * a1.y), J[8] = (TJ)(sr * g1r * a1.z);
+    J[9] = (TJ)(sr * g1r * wn.x), J[10] = (TJ)(sr * g1r * wn.y), J[11] = (TJ)(sr * g1r * wn.z);
+  }
+  J[12] = (TJ)(sr * g2l * a2.x), J[13] = (TJ)(sr * g2l * a2.y), J[14] = (TJ)(sr * g2l * a2.z);
+  J[15] = (TJ)(-sr * g2l * wn.x), J[16] = (TJ)(-sr * g2l * wn.y), J[17] = (TJ)(-sr * g2l * wn.z);
+  J[18] = (TJ)(sr * g2r * a2.x), J[19] = (TJ)(sr * g2r * a2.y), J[20] = (TJ)(sr * g2r * a2.z);
+  J[21] = (TJ)(-sr * g2r * wn.x), J[22] = (TJ)(-sr * g2r * wn.y), J[23] = (TJ)(-sr * g2r * wn.z);
+}
+
 // block (bi, bj), bi <= bj, of the 7x7 grid of 4x4 blocks, enumerated by lane 0..27
 __device__ __forceinline__ void lane_block(int lane, int& bi, int& bj) {
   int l = lane;
@@ -274,9 +374,11 @@ __device__ __forceinline__ void lane_block(int lane, int& bi, int& bj) {
   bj = bi + l;
 }
 
+template <int PREC>
 __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* sm, int cta, int ncta) {
-  double* Jt    = sm;            // JR x JS
-  double* stage = sm + JR * JS;  // NGRP x 28 x 16 (flush staging; separate from Jt: a flush can happen mid-tile)
+  using TJ = typename TJSel<PREC>::type;   // element type of the tile's Jacobian rows and of the J^T J partial blocks
+  TJ* Jt    = reinterpret_cast<TJ*>(sm);  // JR x JS
+  TJ* stage = Jt + JR * JS;               // NGRP x 28 x 16 (flush staging; separate from Jt: a flush can happen mid-tile)
   __shared__ int sbk[LT];
   __shared__ int sb1[LT], sb2[LT];
   __shared__ int heads[LT];
@@ -295,9 +397,9 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
   const int t = threadIdx.x, lane = t & 31, grp = t >> 5;
   int       bi, bj;
   lane_block(lane < 28 ? lane : 0, bi, bj);
-  double acc[16];
+  TJ acc[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  for (int k = 0; k < 16; ++k) acc[k] = (TJ)0;
   double cost_local = 0.0;
   int    cur_b1 = -2, cur_b2 = -2, cur_bk = -1;
 
@@ -310,7 +412,7 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
     __syncthreads();
     if (lane < 28)
 #pragma unroll
-      for (int k = 0; k < 16; ++k) stage[(grp * 28 + lane) * 16 + k] = acc[k], acc[k] = 0.0;
+      for (int k = 0; k < 16; ++k) stage[(grp * 28 + lane) * 16 + k] = acc[k], acc[k] = (TJ)0;
     __syncthreads();
     if (cur_bk >= 0) {
       for (int o = t; o < 28 * 16; o += LT) {
@@ -321,7 +423,7 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
         if (p > q || p >= 24 || q > 24) continue;
         double v = 0.0;
 #pragma unroll
-        for (int gi = 0; gi < NGRP; ++gi) v += stage[(gi * 28 + blk) * 16 + k];
+        for (int gi = 0; gi < NGRP; ++gi) v += (double)stage[(gi * 28 + blk) * 16 + k];
         if (v == 0.0) continue;
         const int sa = p / 6, gpb = (sa < 2 ? cur_b1 + sa : cur_b2 + sa - 2);
         if (sa < 2 && cur_b1 < 0) continue;  // unary factor: no s1 blocks
@@ -343,18 +445,22 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
   for (int tile = tile0; tile < tile1; ++tile) {
     const int  i     = tile * LT + t;
     const bool valid = i < a.n_rec;
-    double     J[24], r = 0.0, cst = 0.0;
+    TJ         J[24], r = (TJ)0;
+    double     cst = 0.0;
     int        b1l = -2, b2l = -2, bk = -1;
-    if (valid) lidar_eval(a.rec, S, i, x, a.jac_mode, a.cauchy_b, a.cauchy_c, J, r, cst, b1l, b2l, bk);
-    else
+    if (valid) {
+      if constexpr (PREC == WC_PREC_F64) lidar_eval(a.rec, S, i, x, a.jac_mode, a.cauchy_b, a.cauchy_c, J, r, cst, b1l, b2l, bk);
+      else lidar_eval32<TJ>(a.rec32, S, i, x, a.jac_mode, (float)a.cauchy_b, (float)a.cauchy_c, J, r, cst, b1l, b2l, bk);
+    } else {
 #pragma unroll
-      for (int k = 0; k < 24; ++k) J[k] = 0.0;
+      for (int k = 0; k < 24; ++k) J[k] = (TJ)0;
+    }
     cost_local += cst;
     __syncthreads();  // previous tile's SYRK reads are done
 #pragma unroll
     for (int k = 0; k < 24; ++k) Jt[k * JS + t] = J[k];
     Jt[24 * JS + t] = r;
-    Jt[25 * JS + t] = 0.0, Jt[26 * JS + t] = 0.0, Jt[27 * JS + t] = 0.0;
+    Jt[25 * JS + t] = (TJ)0, Jt[26 * JS + t] = (TJ)0, Jt[27 * JS + t] = (TJ)0;
     sbk[t] = bk, sb1[t] = b1l, sb2[t] = b2l;
     if (t == 0) nheads = 0;
     __syncthreads();
@@ -372,13 +478,13 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
         const int c0 = grp * 32;
         for (int c = c0; c < c0 + 32; ++c) {
           if (sbk[c] != b) continue;
-          double ra[4], rb[4];
+          TJ ra[4], rb[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) ra[k] = Jt[(4 * bi + k) * JS + c], rb[k] = Jt[(4 * bj + k) * JS + c];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) acc[4 * u + v] = fma(ra[u], rb[v], acc[4 * u + v]);
+            for (int v = 0; v < 4; ++v) acc[4 * u + v] += ra[u] * rb[v];
         }
       }
     }
@@ -564,10 +670,24 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
 // IMU triplets on the first n_imu CTAs, lidar tiles on the rest: one launch per linearisation.  The IMU warps run long
 // serial chains (Log / Exp / 12 x 36 Jacobians per triplet); scheduled first, they overlap with the lidar tiles
 // instead of forming the kernel's tail.
+template <int PREC>
 __global__ void __launch_bounds__(LT) window_linearize(LinArgs a, ImuArgs b, int n_lidar, int n_imu) {
   extern __shared__ __align__(16) double sm[];
   if ((int)blockIdx.x < n_imu) imu_linearize_body(b, sm, blockIdx.x);
-  else lidar_linearize_body(a, sm, blockIdx.x - n_imu, n_lidar);
+  else lidar_linearize_body<PREC>(a, sm, blockIdx.x - n_imu, n_lidar);
+}
+
+// one-time conversion of the sorted fp64 records to the 64-byte fp32 records of WC_PREC_MIXED / WC_PREC_F32
+__global__ void rec_to_f32(const double* __restrict__ rec, int n, int stride, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t S = (size_t)stride;
+#pragma unroll
+  for (int c = 0; c < 14; ++c) out[c * S + i] = (float)rec[c * S + i];
+  const long long w14 = __double_as_longlong(rec[14 * S + i]), w15 = __double_as_longlong(rec[15 * S + i]);
+  const int b1l = (int)(w14 >> 32), b2l = (int)(w14 & 0xffffffffll), mode = (int)(w15 >> 32), bk = (int)(w15 & 0xffffffffll);
+  out[14 * S + i] = __int_as_float((b1l << 16) | (b2l & 0xffff));
+  out[15 * S + i] = __int_as_float((mode << 24) | bk);
 }
 
 // ------------------------------------------------------------------------------------------------ K7
@@ -627,6 +747,12 @@ __global__ void __launch_bounds__(LMT) lm_init(SolveBufs B, wc_solve_opts o) {
   gm = block_max(gm, red);
   xn = block_sum(xn, red);
   if (threadIdx.x == 0) {
+    // Unknowns no factor touches (zero row / column of J^T J: e.g. the bias blocks of a lidar-only window) decouple: their
+    // damped system is diag / radius * delta = 0, so delta = 0 exactly.  The wide-system step leaves them out.
+    int na = 0;
+    for (int c = 0; c < D; ++c)
+      if (H[(size_t)amb_of(c, ff) * N + amb_of(c, ff)] != 0.0) B.act[na++] = c;
+    B.act[D] = na;
     st->D = D;
     st->x_cost = st->initial_cost = *B.cost[st->cur];
     st->grad_max = gm, st->x_norm = sqrt(xn);
@@ -1178,6 +1304,265 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   write_back();
 }
 
+
+// ---------------------------------------------------------------------------------------------- K7, wide systems
+// Systems that do not fit one SM's shared memory (more than ~21 control poses): one COOPERATIVE launch over all SMs.
+// Blocked right-looking Cholesky (block WNB = 32) of the active unknowns in global memory (L2 resident), the right-hand
+// side carried as an extra row; per block column: every CTA factorises the diagonal block redundantly in shared memory
+// (no broadcast, no extra barrier), the panel rows are spread over the CTAs, grid barrier, the trailing 32 x 32 tiles are
+// spread over the CTAs, grid barrier.  CTA 0 does the LM bookkeeping before and the blocked backward substitution after.
+constexpr int WNB = 32;
+
+// row-per-lane Cholesky of a WNB x WNB block held in shared memory (leading dimension WNB + 1) by ONE warp; also leaves
+// the reciprocal pivots.  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool wide_factor_diag(double (*L)[WNB + 1], double* rinv) {
+  const int lane = threadIdx.x & 31;
+  double    a[WNB];
+#pragma unroll
+  for (int c = 0; c < WNB; ++c) a[c] = c <= lane ? L[lane][c] : 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < WNB; ++j) {
+    const double djj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
+    const double rs = rsqrt(djj);
+    if (lane == j) rinv[j] = rs;
+    if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
+#pragma unroll
+    for (int k = j + 1; k < WNB; ++k) {
+      const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+      if (lane >= k) a[k] -= a[j] * lkj;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < WNB; ++c)
+    if (c <= lane) L[lane][c] = a[c];
+  return !__any_sync(0xffffffffu, bad);
+}
+
+__global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o, int zero_next) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[LMT / 32];
+  __shared__ int    s_accept, s_fail;
+  __shared__ __align__(16) LMState sst;  // CTA 0's working copy of the LM state
+  __shared__ double sL[WNB][WNB + 1], sPi[WNB][WNB + 1], sPj[WNB][WNB + 1];
+  __shared__ double sRinv[WNB], sx[WNB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, cta = blockIdx.x, ncta = gridDim.x;
+  LMState*  gst = B.st;
+  if (cta == 0) {
+    for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
+      reinterpret_cast<unsigned long long*>(&sst)[k] = reinterpret_cast<const unsigned long long*>(gst)[k];
+    __syncthreads();
+    if (!sst.done) {
+      if (sst.pending) lm_decide_dev(B, &sst, o, red, &s_accept);
+      __syncthreads();
+      if (t == 0 && !sst.done) {
+        int term = -1;
+        if (sst.iteration >= o.max_num_iterations) term = WC_TERM_NO_CONVERGENCE;
+        else if (sst.last_successful && sst.grad_max <= o.gradient_tolerance) term = WC_TERM_GRADIENT_TOL;
+        else if (sst.radius < o.min_trust_region_radius) term = WC_TERM_MIN_RADIUS;
+        if (term >= 0) sst.done = 1, sst.termination = term;
+      }
+      __syncthreads();
+      for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
+        reinterpret_cast<unsigned long long*>(gst)[k] = reinterpret_cast<const unsigned long long*>(&sst)[k];
+      __threadfence();
+    }
+  }
+  grid.sync();
+  if (*(volatile int*)&gst->done) return;  // uniform over the grid
+  const int     N = B.N, ff = B.fix_first, D = *(volatile int*)&gst->D, cur = *(volatile int*)&gst->cur;
+  const double  radius = *(volatile double*)&gst->radius;
+  const int     reuse  = *(volatile int*)&gst->reuse_diagonal;
+  const double* H = B.H[cur];
+  const double* g = B.g[cur];
+  const int     Da = B.act[D], nblk = (Da + WNB - 1) / WNB, Dp = nblk * WNB, LD = Dp;
+  double*       A  = B.A;  // (Dp + 1) x LD: lower triangle of the damped scaled system, row Dp = scaled gradient
+  // ---- build
+  for (int r = cta * (LMT / 32) + warp; r <= Dp; r += ncta * (LMT / 32)) {
+    double* Ar = A + (size_t)r * LD;
+    if (r < Da) {
+      const int    cr = B.act[r], ir = amb_of(cr, ff);
+      const double sr = B.scale[cr];
+      for (int c = lane; c <= r; c += 32) {
+        const int cc = B.act[c];
+        double    x  = H[(size_t)ir * N + amb_of(cc, ff)] * sr * B.scale[cc];
+        if (c == r) {
+          double d = B.diag[cr];
+          if (!reuse) {
+            d          = fmin(fmax(H[(size_t)ir * N + ir] * sr * sr, o.min_lm_diagonal), o.max_lm_diagonal);
+            B.diag[cr] = d;
+          }
+          const double sq = sqrt(d / radius);
+          x += sq * sq;
+        }
+        Ar[c] = x;
+      }
+    } else if (r < Dp) {
+      for (int c = lane; c <= r; c += 32) Ar[c] = c == r ? 1.0 : 0.0;
+    } else {
+      for (int c = lane; c < Dp; c += 32) Ar[c] = c < Da ? g[amb_of(B.act[c], ff)] * B.scale[B.act[c]] : 0.0;
+    }
+  }
+  grid.sync();
+  // ---- factorisation
+  bool ok = true;
+  for (int k = 0; k < nblk && ok; ++k) {
+    const int k0 = k * WNB;
+    // (a) diagonal block, redundantly in every CTA
+    for (int e = t; e < WNB * WNB; e += LMT) {
+      const int r = e / WNB, c = e % WNB;
+      sL[r][c] = c <= r ? __ldcg(A + (size_t)(k0 + r) * LD + k0 + c) : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const bool good = wide_factor_diag(sL, sRinv);
+      if (lane == 0) s_fail = good ? 0 : 1;
+    }
+    __syncthreads();
+    ok = !s_fail;
+    if (!ok) break;  // every CTA computed the same block: uniform over the grid
+    if (cta == 0)
+      for (int e = t; e < WNB * WNB; e += LMT) {
+        const int r = e / WNB, c = e % WNB;
+        if (c <= r) A[(size_t)(k0 + r) * LD + k0 + c] = sL[r][c];
+      }
+    // (b) panel rows below (and the right-hand-side row): L[i][k0..k0+WNB) = A[i][k0..) * Lkk^-T, one thread per row,
+    //     rows dealt to the CTAs first so that the latency-bound solves run on as many SMs as possible
+    const int nrow = Dp + 1 - (k0 + WNB);
+    for (int q = cta + ncta * t; q < nrow; q += ncta * LMT) {
+      double*   Ai = A + (size_t)(k0 + WNB + q) * LD + k0;
+      double    li[WNB];
+#pragma unroll
+      for (int b = 0; b < WNB; ++b) li[b] = __ldcg(Ai + b);
+#pragma unroll
+      for (int b = 0; b < WNB; ++b) {
+        double v = li[b];
+#pragma unroll
+        for (int c = 0; c < WNB; ++c)
+          if (c < b) v = fma(-li[c], sL[b][c], v);
+        li[b] = v * sRinv[b];
+      }
+#pragma unroll
+      for (int b = 0; b < WNB; ++b) Ai[b] = li[b];
+    }
+    grid.sync();
+    // (c) trailing update: tiles (bi >= bj > k) of WNB x WNB plus the right-hand-side row, dealt round robin
+    const int nb = nblk - k - 1;                   // block rows / columns left
+    const int ntile = nb * (nb + 1) / 2 + nb;      // lower triangle + the right-hand-side row's nb tiles
+    for (int q = cta; q < ntile; q += ncta) {
+      int bi, bj;
+      if (q < nb * (nb + 1) / 2) {
+        bi = (int)((sqrtf(1.f + 8.f * (float)q) - 1.f) * 0.5f);
+        while (bi * (bi + 1) / 2 > q) --bi;
+        while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
+        bj = q - bi * (bi + 1) / 2;
+      } else {
+        bi = nb, bj = q - nb * (nb + 1) / 2;       // bi == nb: the single right-hand-side row
+      }
+      const int i0 = k0 + WNB + bi * WNB, j0 = k0 + WNB + bj * WNB;
+      const int ni = bi == nb ? 1 : WNB;
+      __syncthreads();
+      for (int e = t; e < WNB * WNB; e += LMT) {
+        const int r = e / WNB, c = e % WNB;
+        sPi[r][c] = r < ni ? __ldcg(A + (size_t)(i0 + r) * LD + k0 + c) : 0.0;
+        sPj[r][c] = __ldcg(A + (size_t)(j0 + r) * LD + k0 + c);
+      }
+      __syncthreads();
+      for (int e = t; e < WNB * WNB; e += LMT) {
+        const int r = e / WNB, c = e % WNB;
+        if (r >= ni || (bi == bj && c > r)) continue;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < WNB; b += 2) s0 = fma(sPi[r][b], sPj[c][b], s0), s1 = fma(sPi[r][b + 1], sPj[c][b + 1], s1);
+        A[(size_t)(i0 + r) * LD + j0 + c] -= s0 + s1;
+      }
+    }
+    grid.sync();
+  }
+  // ---- the other CTAs clear the normal-equation buffer the next linearisation accumulates into, CTA 0 finishes the step
+  if (cta != 0) {
+    if (zero_next) {
+      const int nbuf = 1 - cur;
+      double2*  Hz   = reinterpret_cast<double2*>(B.H[nbuf]);
+      for (size_t i = (size_t)(cta - 1) * LMT + t; i < (size_t)N * N / 2; i += (size_t)(ncta - 1) * LMT) Hz[i] = make_double2(0.0, 0.0);
+      if (cta == 1) {
+        for (int i = t; i < N; i += LMT) B.g[nbuf][i] = 0.0;
+        if (t == 0) *B.cost[nbuf] = 0.0;
+      }
+    }
+    return;
+  }
+  // blocked backward substitution L^T x = z (z = row Dp), last block first; y = -x scattered to the reduced columns
+  double* y    = B.step;
+  double* zrow = A + (size_t)Dp * LD;
+  for (int c = t; c < D; c += LMT) y[c] = 0.0;
+  __syncthreads();
+  if (ok) {
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+      const int k0 = kb * WNB;
+      // z[k0 + c] -= sum_{i >= k0 + WNB} L[i][k0 + c] x_i : warp w sums rows i = k0 + WNB + w, + 16, ... for all 32 columns
+      double part = 0.0;
+      for (int i = k0 + WNB + warp; i < Dp; i += LMT / 32) part = fma(__ldcg(A + (size_t)i * LD + k0 + lane), zrow[i], part);
+      sPi[warp][lane] = part;  // LMT / 32 = 16 partial rows
+      for (int e = t; e < WNB * WNB; e += LMT) {
+        const int r = e / WNB, c = e % WNB;
+        sL[r][c] = c <= r ? A[(size_t)(k0 + r) * LD + k0 + c] : 0.0;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        double z = zrow[k0 + lane];
+#pragma unroll
+        for (int w = 0; w < LMT / 32; ++w) z -= sPi[w][lane];
+        // upper-triangular solve L_kk^T x = z: column lane, last unknown first
+#pragma unroll
+        for (int j = WNB - 1; j >= 0; --j) {
+          const double xj = __shfl_sync(0xffffffffu, z, j) / sL[j][j];
+          if (lane == j) z = xj;
+          else if (lane < j) z = fma(-sL[j][lane], xj, z);
+        }
+        zrow[k0 + lane] = z;  // x overwrites z
+        if (k0 + lane < Da) y[B.act[k0 + lane]] = -z;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  bool   valid = ok;
+  double part = 0.0, bad = 0.0;
+  if (valid)
+    for (int c = t; c < D; c += LMT) {
+      const double sq = sqrt(B.diag[c] / radius);
+      part += 0.5 * y[c] * (sq * sq * y[c] - g[amb_of(c, ff)] * B.scale[c]);  // inactive columns: y = 0
+      if (!isfinite(y[c])) bad = 1.0;
+    }
+  const double mcc  = block_sum(part, red);
+  const double nbad = block_sum(bad, red);
+  valid             = valid && nbad == 0.0 && mcc > 0.0;
+  double sn = 0.0;
+  for (int i = t; i < N; i += LMT) {
+    const int    c = col_of(i, ff);
+    const double d = (valid && c >= 0) ? y[c] * B.scale[c] : 0.0;
+    B.xc[i]        = B.x[i] + d;
+    sn += d * d;
+  }
+  sn = block_sum(sn, red);
+  if (t == 0) {
+    sst.iteration += 1;
+    sst.last_successful   = 0;
+    sst.reuse_diagonal    = 1;
+    sst.step_valid        = valid ? 1 : 0;
+    sst.pending           = 1;
+    sst.model_cost_change = mcc;
+    sst.step_norm         = sqrt(sn);
+    const int it          = sst.iteration < WC_MAX_ITER_LOG ? sst.iteration : WC_MAX_ITER_LOG - 1;
+    sst.iter_radius[it]   = radius;
+  }
+  __syncthreads();
+  for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
+    reinterpret_cast<unsigned long long*>(gst)[k] = reinterpret_cast<const unsigned long long*>(&sst)[k];
+}
+
 __global__ void extract_ts(const wc_sample_state* __restrict__ s, int K, double* __restrict__ ts, double* __restrict__ x) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -1192,6 +1577,8 @@ struct wc_solve_mem {
   double*  ts;
   double*  tmp;
   double*  rec;
+  float*   rec32;        // fp32 copy of rec (allocated and filled on the first reduced-precision solve of a window)
+  int      rec32_valid;
   int*     bucket;
   int*     hist;
   int*     off;
@@ -1206,10 +1593,13 @@ struct wc_solve_mem {
   double*  step;
   double*  A;
   int      Ncap;
+  int*     act;
   LMState* st;
   LMState* h_st;
   double*  h_x;
   double   grav[3];
+  cudaEvent_t lin_ev[2 * WC_MAX_ITER_LOG + 4];  // begin / end of the linearisation passes of one solve
+  int         n_lin_ev;
 };
 
 static wc_status solve_alloc(wc_ctx* c) {
@@ -1242,14 +1632,18 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->scale, N * 8));
   WC_CUDA(c, cudaMalloc(&m->diag, N * 8));
   WC_CUDA(c, cudaMalloc(&m->step, N * 8));
-  WC_CUDA(c, cudaMalloc(&m->A, ((N + 12) * (N + 10) + N + 8) * 8));
+  WC_CUDA(c, cudaMalloc(&m->A, ((N + 40) * (N + 40) + N + 8) * 8));
+  WC_CUDA(c, cudaMalloc(&m->act, (N + 1) * 4));
   WC_CUDA(c, cudaMalloc(&c->d_x, N * 8));
   WC_CUDA(c, cudaMalloc(&c->d_xc, N * 8));
   WC_CUDA(c, cudaMalloc(&c->d_x0, N * 8));
   WC_CUDA(c, cudaMalloc(&m->st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
-  WC_CUDA(c, cudaFuncSetAttribute(window_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  WC_CUDA(c, cudaFuncSetAttribute(window_linearize<WC_PREC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  WC_CUDA(c, cudaFuncSetAttribute(window_linearize<WC_PREC_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  WC_CUDA(c, cudaFuncSetAttribute(window_linearize<WC_PREC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  for (int i = 0; i < 2 * WC_MAX_ITER_LOG + 4; ++i) WC_CUDA(c, cudaEventCreate(&m->lin_ev[i]));
   WC_CUDA(c, cudaFuncSetAttribute(lm_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return WC_OK;
 }
@@ -1260,8 +1654,10 @@ void wc_solve_free(wc_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (!m) return;
-  void* mp[] = {m->ts, m->tmp, m->rec, m->bucket, m->hist, m->off, m->cursor, m->Hbuf[0], m->Hbuf[1], m->gbuf[0], m->gbuf[1],
-                m->cost, m->scale, m->diag, m->step, m->A, m->st};
+  for (auto& e : m->lin_ev)
+    if (e) cudaEventDestroy(e);
+  void* mp[] = {m->rec32, m->ts, m->tmp, m->rec, m->bucket, m->hist, m->off, m->cursor, m->Hbuf[0], m->Hbuf[1], m->gbuf[0], m->gbuf[1],
+                m->cost, m->scale, m->diag, m->step, m->A, m->st, m->act};
   for (void* p : mp)
     if (p) cudaFree(p);
   if (m->h_st) cudaFreeHost(m->h_st);
@@ -1274,7 +1670,7 @@ static SolveBufs make_bufs(wc_ctx* c, int fix_first) {
   wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
   SolveBufs     B;
   for (int b = 0; b < 2; ++b) B.H[b] = m->Hbuf[b], B.g[b] = m->gbuf[b], B.cost[b] = m->cost + b;
-  B.x = c->d_x, B.xc = c->d_xc, B.scale = m->scale, B.diag = m->diag, B.step = m->step, B.A = m->A, B.st = m->st;
+  B.x = c->d_x, B.xc = c->d_xc, B.scale = m->scale, B.diag = m->diag, B.step = m->step, B.A = m->A, B.st = m->st, B.act = m->act;
   B.N = (int)(12 * c->K), B.fix_first = fix_first;
   return B;
 }
@@ -1292,6 +1688,7 @@ wc_status wc_window_prepare_device(wc_ctx* c) {
   const int C  = (int)(n_sld_corr + n_fix_corr);
   const int c0 = (int)((long long)C * c->rank / c->world), c1 = (int)((long long)C * (c->rank + 1) / c->world);
   c->n_rec     = (size_t)(c1 - c0);
+  m->rec32_valid = 0;
   const int nb = (int)(K * K);
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemsetAsync(m->hist, 0, (size_t)nb * 4, st));
@@ -1383,8 +1780,16 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     zeroed = 1;  // cleared by wc_comm_begin_solve / by the reduction two epochs back
   }
   if (!zeroed) { ++c->n_launches; zero_buffers<<<64, 256, 0, st>>>(B, at_candidate); }
+  const int prec = o->precision;
+  if (prec != WC_PREC_F64 && prec != WC_PREC_MIXED && prec != WC_PREC_F32) WC_FAIL(c, WC_EINVAL, "unknown precision mode %d", prec);
+  if (prec != WC_PREC_F64 && !m->rec32_valid) {
+    if (!m->rec32) WC_CUDA(c, cudaMalloc(&m->rec32, (size_t)REC_COLS * m->stride * 4));
+    if (c->K * c->K >= (1u << 24) || c->K >= 32768) WC_FAIL(c, WC_ECAPACITY, "too many sample states for the fp32 record format");
+    if (c->n_rec) { ++c->n_launches; rec_to_f32<<<(unsigned)((c->n_rec + 255) / 256), 256, 0, st>>>(m->rec, (int)c->n_rec, m->stride, m->rec32); }
+    m->rec32_valid = 1;
+  }
   LinArgs a;
-  a.rec = m->rec, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
+  a.rec = m->rec, a.rec32 = m->rec32, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
   a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
   const int ntiles  = (int)((c->n_rec + LT - 1) / LT);
   // one tile per CTA while that stays within a few waves (the SMs hold 4-5 tiles each); beyond that, contiguous chunks
@@ -1400,7 +1805,16 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     for (int k = 0; k < 3; ++k) b.grav[k] = m->grav[k];
     n_imu_cta = (int)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS);
   }
-  if (n_lidar + n_imu_cta > 0) { ++c->n_launches; window_linearize<<<n_lidar + n_imu_cta, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta); }
+  const bool timed = m->n_lin_ev + 2 <= 2 * WC_MAX_ITER_LOG + 4;
+  if (timed) WC_CUDA(c, cudaEventRecord(m->lin_ev[m->n_lin_ev++], st));
+  if (n_lidar + n_imu_cta > 0) {
+    ++c->n_launches;
+    const unsigned grid = (unsigned)(n_lidar + n_imu_cta);
+    if (prec == WC_PREC_F64) window_linearize<WC_PREC_F64><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
+    else if (prec == WC_PREC_MIXED) window_linearize<WC_PREC_MIXED><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
+    else window_linearize<WC_PREC_F32><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
+  }
+  if (timed) WC_CUDA(c, cudaEventRecord(m->lin_ev[m->n_lin_ev++], st));
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }
@@ -1431,9 +1845,12 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   const size_t  a_bytes     = ((size_t)(Dp + 4) * LD + Dp) * 8;
   const int     a_in_smem   = a_bytes <= 200 * 1024;
   const size_t  smem        = a_in_smem ? a_bytes : 0;
+  static const int no_wide  = getenv("WC_LM_NO_WIDE") != nullptr;  // test hook: the single-CTA global-memory step
+  const bool    use_wide    = !a_in_smem && !no_wide;
   WC_CUDA(c, cudaEventRecord(c->ev[4], st));
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+  m->n_lin_ev = 0;
   wc_status s = wc_comm_begin_solve(c);
   if (s) return s;
   if ((s = enqueue_linearize(c, B, &o, 0, 0))) return s;
@@ -1449,8 +1866,16 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
     for (int b = 0; b < batch; ++b) {
       // decide(previous candidate) + next trust-region step + clear the candidate buffer, then linearise there
       if (dbg_ev && n_ev + 3 < 256) cudaEventRecord(evs[n_ev++], st);
-      { ++c->n_launches; if (a_in_smem) lm_step<true><<<1, LMT, smem, st>>>(B, o, c->world == 1);
-        else lm_step<false><<<1, LMT, 0, st>>>(B, o, c->world == 1); }
+      ++c->n_launches;
+      if (a_in_smem) {
+        lm_step<true><<<1, LMT, smem, st>>>(B, o, c->world == 1);
+      } else if (use_wide) {
+        int   zn      = c->world == 1;
+        void* args[3] = {(void*)&B, (void*)&o, (void*)&zn};
+        WC_CUDA(c, cudaLaunchCooperativeKernel((const void*)lm_step_wide, dim3((unsigned)c->num_sms), dim3(LMT), args, 0, st));
+      } else {
+        lm_step<false><<<1, LMT, 0, st>>>(B, o, c->world == 1);
+      }
       if (dbg_ev && n_ev + 3 < 256) cudaEventRecord(evs[n_ev++], st);
       if ((s = enqueue_linearize(c, B, &o, 1, 1))) return s;
       if ((s = wc_comm_allreduce(c, 1))) return s;
@@ -1475,6 +1900,13 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
     float ms;
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
     summary->gpu_ms_total = ms;
+    // executed passes only: launches enqueued after the solver terminated return at once
+    double lin = 0.0;
+    for (int i = 0; i + 1 < m->n_lin_ev && i / 2 < m->h_st->num_linearizations; i += 2) {
+      cudaEventElapsedTime(&ms, m->lin_ev[i], m->lin_ev[i + 1]);
+      lin += ms;
+    }
+    summary->gpu_ms_linearize = lin;
   }
   if (data_cor_out) memcpy(data_cor_out, m->h_x, (size_t)N * 8);
   if (m->h_st->termination == WC_TERM_FAILURE) WC_FAIL(c, WC_ENUMERIC, "solve failed: non-finite cost or 5 consecutive invalid steps");
@@ -1510,6 +1942,7 @@ extern "C" wc_status wc_window_evaluate(wc_ctx* c, const wc_surfel* sld, size_t 
   SolveBufs     B  = make_bufs(c, 0);
   WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_x, c->d_x0, N * 8, cudaMemcpyDeviceToDevice, st));
+  m->n_lin_ev = 0;
   if ((s = wc_comm_begin_solve(c))) return s;
   if ((s = enqueue_linearize(c, B, &o, 0, 0))) return s;
   if ((s = wc_comm_allreduce(c, 0))) return s;

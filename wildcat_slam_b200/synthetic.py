@@ -310,3 +310,95 @@ def make_window(cfg, seed=20240116) -> Window:
         fix_imu["timestamp"], fix_imu["pos"], fix_imu["rot"], fix_imu["gyr"], fix_imu["acc"] = ts_f, pf, qf, gf, af
         fix_pts = _scan(cfg, seed, 22, cfg.fix_points, cfg.t0 - 0.002 - T_fix, fix_imu, planes, start)
     return Window(cfg, seed, pts, imu, samples, fix_pts, fix_imu, tp, tq)
+
+
+# --------------------------------------------------------------------------------- C5: correspondence stress
+@dataclass
+class StressWindow:
+    """BASELINE config 5: surfels sampled directly on the scene planes and correspondences generated
+    directly (extraction and matching skipped), K control poses over a long window."""
+    name: str
+    seed: int
+    surfels: np.ndarray      # SURFEL, body frame, prior poses, time ordered
+    corr: np.ndarray         # CORR sliding-window pairs, timestamp(s1) < timestamp(s2)
+    samples: np.ndarray      # K SampleStates (prior poses, zero corrections)
+    truth_sample_pos: np.ndarray
+
+
+def prior_pose(t, start, dp_scale=0.02, dth_scale=0.002):
+    """truth composed with a smooth prior error of the SURVEY §8d form: dp = dp_scale [sin .5t, cos .4t, sin .3t] m,
+    dtheta = dth_scale [cos .6t, sin .5t, cos .35t] rad.  (With the 5 cm / 10 mrad of the sweep configs the 20 m lever arms
+    of this room saturate the Cauchy loss and the solver crawls for ~100 iterations; 2 cm / 2 mrad converges in ~20.)"""
+    p, q = truth_pose(t, start)
+    dp = dp_scale * np.stack([np.sin(0.5 * t), np.cos(0.4 * t), np.sin(0.3 * t)], axis=-1)
+    dth = dth_scale * np.stack([np.cos(0.6 * t), np.sin(0.5 * t), np.cos(0.35 * t)], axis=-1)
+    return p + dp, quat_mul(so3_exp(dth), q)
+
+
+def quat_to_matrix(q):
+    x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    return np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                     np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                     np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], -2)
+
+
+def make_stress_window(n_corr=10_000_000, K=64, seed=20240116, span=8.0, room=(40.0, 30.0, 8.0), t0=1000.0, name="C5",
+                       chunk=1 << 20) -> StressWindow:
+    """n_corr surfels (one pair each): surfel i lies on room plane i mod 6 (centre uniform on the plane plus N(0, 1 cm)
+    along the normal, covariance diag(1e-4, 0.04, 0.05) in the plane's frame), observed at t_i (stratified uniform over
+    `span` seconds, so the array is time ordered) from the TRUE pose and stored in the body frame with the PRIOR pose;
+    it is paired with a later surfel of the same plane, j = i + 6 m with m uniform, so the interval pairs cover the
+    upper triangle uniformly."""
+    S = int(n_corr)
+    start = np.array([0.0, 0.0, 1.5])
+    Lx, Ly, H = room
+    ex, ey, ez = np.eye(3)
+    # (point on plane, normal, in-plane axes, half extents)
+    planes = [(np.array([Lx / 2, 0, H / 2]), ex, ey, ez, Ly / 2, H / 2), (np.array([-Lx / 2, 0, H / 2]), -ex, ey, ez, Ly / 2, H / 2),
+              (np.array([0, Ly / 2, H / 2]), ey, ex, ez, Lx / 2, H / 2), (np.array([0, -Ly / 2, H / 2]), -ey, ex, ez, Lx / 2, H / 2),
+              (np.array([0, 0, 0.0]), -ez, ex, ey, Lx / 2, Ly / 2), (np.array([0, 0, H]), ez, ex, ey, Lx / 2, Ly / 2)]
+    pc = np.stack([p[0] for p in planes]); pn = np.stack([p[1] for p in planes])
+    pa = np.stack([p[2] for p in planes]); pb = np.stack([p[3] for p in planes])
+    pha = np.array([p[4] for p in planes]); phb = np.array([p[5] for p in planes])
+    lam = np.array([1e-4, 0.04, 0.05])
+    out = np.zeros(S, dtype=T.SURFEL)
+    corr = np.zeros(S, dtype=T.CORR)
+    for s in range(0, S, chunk):
+        i = np.arange(s, min(S, s + chunk), dtype=np.int64)
+        iu = i.astype(np.uint64)
+        t_rel = span * (i + uniform(seed, 31, iu)) / S
+        pl = (i % 6).astype(np.int64)
+        ua, ub = uniform(seed, 32, iu), uniform(seed, 33, iu)
+        c_true = pc[pl] + pa[pl] * ((2 * ua - 1) * pha[pl])[:, None] + pb[pl] * ((2 * ub - 1) * phb[pl])[:, None]
+        c_true = c_true + pn[pl] * (0.01 * normal(seed, 34, iu))[:, None]
+        Rw = np.stack([pn[pl], pa[pl], pb[pl]], axis=-1)                  # columns: normal, in-plane axes
+        cov_w = np.einsum("nij,j,nkj->nik", Rw, lam, Rw)
+        p_t, q_t = truth_pose(t_rel, start)
+        p_p, q_p = prior_pose(t_rel, start)
+        Rt = quat_to_matrix(q_t)
+        # body-frame observation through the TRUE pose; the prior pose is what the window starts from
+        c_b = np.einsum("nji,nj->ni", Rt, c_true - p_t)
+        cov_b = np.einsum("nji,njk,nkl->nil", Rt, cov_w, Rt)
+        n_b = np.einsum("nji,nj->ni", Rt, pn[pl])
+        flip = np.sum(n_b * c_b, axis=1) < 0   # normal away from the view point (the sensor origin in the body frame)
+        n_b = np.where(flip[:, None], -n_b, n_b)
+        out["timestamp"][i] = t0 + t_rel
+        out["resolution"][i] = 0.8
+        out["plane_std_deviation"][i] = 0.01
+        out["rot"][i], out["pos"][i] = q_p, p_p
+        out["center"][i], out["covariance"][i], out["norm"][i] = c_b, cov_b.reshape(-1, 9), n_b
+        out["is_in_body_frame"][i] = 1
+        # partner: a later surfel of the same plane
+        room_m = (S - 1 - i) // 6
+        m = 1 + np.floor(uniform(seed, 35, iu) * np.maximum(room_m, 1)).astype(np.int64)
+        j = np.minimum(i + 6 * m, S - 1 - ((S - 1 - i) % 6))
+        corr["s1"][i], corr["s2"][i] = i, j
+    corr = corr[corr["s2"] > corr["s1"]]
+    corr = corr[out["timestamp"][corr["s1"]] < out["timestamp"][corr["s2"]]].copy()
+    smp = np.zeros(K, dtype=T.SAMPLE)
+    eps = 1e-3
+    ts = -eps + (span + 2 * eps) * np.arange(K) / (K - 1)
+    smp["timestamp"] = t0 + ts
+    smp["grav"] = GRAV
+    smp["pos"], smp["rot"] = prior_pose(ts, start)
+    return StressWindow(name, seed, out, corr, smp, truth_pose(ts, start)[0])

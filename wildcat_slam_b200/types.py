@@ -57,6 +57,7 @@ WC_MAX_ITER_LOG = 128
 WC_OK, WC_EINVAL, WC_EINVAL_TIME_ORDER, WC_EOUT_OF_SPAN, WC_ETOO_FEW_TARGETS = 0, 1, 2, 3, 4
 WC_ECAPACITY, WC_ECUDA, WC_ECOMM, WC_ENUMERIC = 5, 6, 7, 8
 WC_JAC_REFERENCE_OVERWRITE, WC_JAC_EXACT = 0, 1
+WC_PREC_F64, WC_PREC_MIXED, WC_PREC_F32 = 0, 1, 2
 TERMINATION = ["NO_CONVERGENCE", "FUNCTION_TOL", "GRADIENT_TOL", "PARAMETER_TOL", "MIN_RADIUS", "FAILURE"]
 
 
@@ -108,6 +109,8 @@ class SolveOpts(C.Structure):
         ("function_tolerance", C.c_double),
         ("gradient_tolerance", C.c_double),
         ("parameter_tolerance", C.c_double),
+        ("precision", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 
