@@ -1313,31 +1313,42 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 // spread over the CTAs, grid barrier.  CTA 0 does the LM bookkeeping before and the blocked backward substitution after.
 constexpr int WNB = 32;
 
-// row-per-lane Cholesky of a WNB x WNB block held in shared memory (leading dimension WNB + 1) by ONE warp; also leaves
-// the reciprocal pivots.  Returns false on a non-positive pivot.
-__device__ __forceinline__ bool wide_factor_diag(double (*L)[WNB + 1], double* rinv) {
-  const int lane = threadIdx.x & 31;
-  double    a[WNB];
-#pragma unroll
-  for (int c = 0; c < WNB; ++c) a[c] = c <= lane ? L[lane][c] : 0.0;
-  bool bad = false;
-#pragma unroll
+// Cholesky of a WNB x WNB block held in shared memory (leading dimension WNB + 1) by the whole CTA: thread e owns the
+// elements e and e + LMT of the block; per pivot ONE barrier: everybody reads the (still unscaled) pivot column, applies
+// the rank-1 update to its elements of the trailing block, and the owners of the pivot column write its scaled values at
+// the start of the next round (nobody reads that column again).  Leaves the reciprocal pivots; *fail is set on a
+// non-positive pivot.  (A one-warp register version of this block is 18x slower here: its 32-entry row does not fit the
+// 128 registers a 512-thread CTA leaves per thread.)
+__device__ __forceinline__ void wide_factor_diag(double (*L)[WNB + 1], double* rinv, int* fail) {
+  const int t = threadIdx.x;
+  static_assert(WNB * WNB == 2 * LMT, "two elements per thread");
+  const int r0 = t >> 5, c0 = t & 31, r1 = r0 + WNB / 2;  // elements (r0, c0) and (r1, c0)
+  if (t == 0) *fail = 0;
+  __syncthreads();
+  double rs_prev = 0.0;
+#pragma unroll 1
   for (int j = 0; j < WNB; ++j) {
-    const double djj = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(djj > 0.0) || !isfinite(djj)) bad = true;
-    const double rs = rsqrt(djj);
-    if (lane == j) rinv[j] = rs;
-    if (lane >= j) a[j] = (lane == j) ? djj * rs : a[j] * rs;
-#pragma unroll
-    for (int k = j + 1; k < WNB; ++k) {
-      const double lkj = __shfl_sync(0xffffffffu, a[j], k);
-      if (lane >= k) a[k] -= a[j] * lkj;
+    if (j > 0 && c0 == j - 1) {  // scale the previous pivot column (its readers are past the barrier)
+      if (r0 >= j - 1) L[r0][c0] *= rs_prev;
+      if (r1 >= j - 1) L[r1][c0] *= rs_prev;
     }
+    const double d = L[j][j];
+    if (t == 0 && (!(d > 0.0) || !isfinite(d))) *fail = 1;
+    const double rs = rsqrt(d), rs2 = rs * rs;
+    if (t == 0) rinv[j] = rs;
+    if (c0 > j) {
+      const double lc = L[c0][j] * rs2;
+      if (c0 <= r0) L[r0][c0] -= L[r0][j] * lc;  // (j < c0 <= r: the row is below the pivot too)
+      if (c0 <= r1) L[r1][c0] -= L[r1][j] * lc;
+    }
+    rs_prev = rs;
+    __syncthreads();
   }
-#pragma unroll
-  for (int c = 0; c < WNB; ++c)
-    if (c <= lane) L[lane][c] = a[c];
-  return !__any_sync(0xffffffffu, bad);
+  if (c0 == WNB - 1) {
+    if (r0 >= WNB - 1) L[r0][c0] *= rs_prev;
+    if (r1 >= WNB - 1) L[r1][c0] *= rs_prev;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o, int zero_next) {
@@ -1349,6 +1360,10 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
   __shared__ double sRinv[WNB], sx[WNB];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, cta = blockIdx.x, ncta = gridDim.x;
   LMState*  gst = B.st;
+#ifdef WC_LM_TIMING
+  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c_fac = 0, c_pan = 0, c_upd = 0, c0;
+  tk[0] = clock64();
+#endif
   if (cta == 0) {
     for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
       reinterpret_cast<unsigned long long*>(&sst)[k] = reinterpret_cast<const unsigned long long*>(gst)[k];
@@ -1370,6 +1385,9 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
     }
   }
   grid.sync();
+#ifdef WC_LM_TIMING
+  tk[1] = clock64();
+#endif
   if (*(volatile int*)&gst->done) return;  // uniform over the grid
   const int     N = B.N, ff = B.fix_first, D = *(volatile int*)&gst->D, cur = *(volatile int*)&gst->cur;
   const double  radius = *(volatile double*)&gst->radius;
@@ -1405,21 +1423,21 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
     }
   }
   grid.sync();
+#ifdef WC_LM_TIMING
+  tk[2] = clock64();
+#endif
   // ---- factorisation
   bool ok = true;
   for (int k = 0; k < nblk && ok; ++k) {
     const int k0 = k * WNB;
+    WC_TICK();
     // (a) diagonal block, redundantly in every CTA
     for (int e = t; e < WNB * WNB; e += LMT) {
       const int r = e / WNB, c = e % WNB;
       sL[r][c] = c <= r ? __ldcg(A + (size_t)(k0 + r) * LD + k0 + c) : 0.0;
     }
     __syncthreads();
-    if (warp == 0) {
-      const bool good = wide_factor_diag(sL, sRinv);
-      if (lane == 0) s_fail = good ? 0 : 1;
-    }
-    __syncthreads();
+    wide_factor_diag(sL, sRinv, &s_fail);
     ok = !s_fail;
     if (!ok) break;  // every CTA computed the same block: uniform over the grid
     if (cta == 0)
@@ -1427,6 +1445,8 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
         const int r = e / WNB, c = e % WNB;
         if (c <= r) A[(size_t)(k0 + r) * LD + k0 + c] = sL[r][c];
       }
+    WC_TOCK(c_fac);
+    WC_TICK();
     // (b) panel rows below (and the right-hand-side row): L[i][k0..k0+WNB) = A[i][k0..) * Lkk^-T, one thread per row,
     //     rows dealt to the CTAs first so that the latency-bound solves run on as many SMs as possible
     const int nrow = Dp + 1 - (k0 + WNB);
@@ -1447,6 +1467,8 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
       for (int b = 0; b < WNB; ++b) Ai[b] = li[b];
     }
     grid.sync();
+    WC_TOCK(c_pan);
+    WC_TICK();
     // (c) trailing update: tiles (bi >= bj > k) of WNB x WNB plus the right-hand-side row, dealt round robin
     const int nb = nblk - k - 1;                   // block rows / columns left
     const int ntile = nb * (nb + 1) / 2 + nb;      // lower triangle + the right-hand-side row's nb tiles
@@ -1479,7 +1501,11 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
       }
     }
     grid.sync();
+    WC_TOCK(c_upd);
   }
+#ifdef WC_LM_TIMING
+  tk[3] = clock64();
+#endif
   // ---- the other CTAs clear the normal-equation buffer the next linearisation accumulates into, CTA 0 finishes the step
   if (cta != 0) {
     if (zero_next) {
@@ -1502,9 +1528,14 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
     for (int kb = nblk - 1; kb >= 0; --kb) {
       const int k0 = kb * WNB;
       // z[k0 + c] -= sum_{i >= k0 + WNB} L[i][k0 + c] x_i : warp w sums rows i = k0 + WNB + w, + 16, ... for all 32 columns
-      double part = 0.0;
-      for (int i = k0 + WNB + warp; i < Dp; i += LMT / 32) part = fma(__ldcg(A + (size_t)i * LD + k0 + lane), zrow[i], part);
-      sPi[warp][lane] = part;  // LMT / 32 = 16 partial rows
+      double part = 0.0, part2 = 0.0;
+      int    i    = k0 + WNB + warp;
+      for (; i + LMT / 32 < Dp; i += 2 * (LMT / 32)) {  // two independent loads in flight
+        const double l0 = __ldcg(A + (size_t)i * LD + k0 + lane), l1 = __ldcg(A + (size_t)(i + LMT / 32) * LD + k0 + lane);
+        part = fma(l0, zrow[i], part), part2 = fma(l1, zrow[i + LMT / 32], part2);
+      }
+      if (i < Dp) part = fma(__ldcg(A + (size_t)i * LD + k0 + lane), zrow[i], part);
+      sPi[warp][lane] = part + part2;  // LMT / 32 = 16 partial rows
       for (int e = t; e < WNB * WNB; e += LMT) {
         const int r = e / WNB, c = e % WNB;
         sL[r][c] = c <= r ? A[(size_t)(k0 + r) * LD + k0 + c] : 0.0;
@@ -1514,10 +1545,11 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
         double z = zrow[k0 + lane];
 #pragma unroll
         for (int w = 0; w < LMT / 32; ++w) z -= sPi[w][lane];
-        // upper-triangular solve L_kk^T x = z: column lane, last unknown first
+        // upper-triangular solve L_kk^T x = z: column lane, last unknown first (reciprocal pivots: no division in the chain)
+        const double rp = 1.0 / sL[lane][lane];
 #pragma unroll
         for (int j = WNB - 1; j >= 0; --j) {
-          const double xj = __shfl_sync(0xffffffffu, z, j) / sL[j][j];
+          const double xj = __shfl_sync(0xffffffffu, z * rp, j);
           if (lane == j) z = xj;
           else if (lane < j) z = fma(-sL[j][lane], xj, z);
         }
@@ -1528,6 +1560,9 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
     }
   }
   __syncthreads();
+#ifdef WC_LM_TIMING
+  tk[4] = clock64();
+#endif
   bool   valid = ok;
   double part = 0.0, bad = 0.0;
   if (valid)
@@ -1557,6 +1592,12 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
     sst.step_norm         = sqrt(sn);
     const int it          = sst.iteration < WC_MAX_ITER_LOG ? sst.iteration : WC_MAX_ITER_LOG - 1;
     sst.iter_radius[it]   = radius;
+#ifdef WC_LM_TIMING
+    tk[5] = clock64();
+    if (sst.iteration == 3)
+      printf("lm_step_wide cycles: decide+sync %lld build %lld chol %lld (factor %lld, panel+sync %lld, update+sync %lld) back %lld finish %lld total %lld, Da %d\n",
+             tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], c_fac, c_pan, c_upd, tk[4] - tk[3], tk[5] - tk[4], tk[5] - tk[0], Da);
+#endif
   }
   __syncthreads();
   for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
