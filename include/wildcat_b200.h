@@ -249,6 +249,23 @@ wc_status wc_undistort_sweep(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu,
 wc_status wc_undistort_upload(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu, const wc_point48* in, size_t n);
 
 /* ------------------------------------------------------------------------------------------------
+ * Wire ingestion — replaces pcl::fromROSMsg(*msg, *cloud) in HandleLidarMessage
+ * (wildcat_slam_node.cc:46-52) for the point type registered at common.h:21-28: fields x, y, z, intensity
+ * (FLOAT32), timestamp (FLOAT64), ring (UINT16) of a sensor_msgs/PointCloud2 payload, found by NAME and
+ * datatype at arbitrary byte offsets inside a point_step-byte record, become the 48-byte hilti_ros::Point
+ * records every other entry point consumes.  A field the message does not carry (offset -1) stays zero, as
+ * pcl::fromROSMsg leaves it.  The raw payload is uploaded as it came off the wire and unpacked by a kernel.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wc_pc2_layout {
+  uint32_t point_step;                                       /* bytes per point in the message            */
+  int32_t  off_x, off_y, off_z, off_intensity;               /* FLOAT32 fields, byte offsets (-1: absent) */
+  int32_t  off_time;                                         /* FLOAT64 "timestamp"                       */
+  int32_t  off_ring;                                         /* UINT16 "ring"                             */
+} wc_pc2_layout;
+wc_status wc_unpack_pointcloud2(wc_ctx* ctx, const uint8_t* data, size_t n_points, const wc_pc2_layout* layout,
+                                wc_point48* out);
+
+/* ------------------------------------------------------------------------------------------------
  * Surfel poses — replaces UpdateSurfelPoses (lidar_odometry.cc:160-170) + Surfel::UpdatePose
  * (surfel.h:48-58): interpolate the IMU pose at each surfel time (lerp / Eigen slerp) and move the
  * surfel to the body frame on first call.  In-place on host surfels.

@@ -75,3 +75,25 @@ def test_unknown_precision_is_rejected(c5):
     with pytest.raises(WildcatError) as e:
         od.SolveWindow(w.surfels[:1000], None, w.corr[:10], None, None, w.samples, opts=o, ctx=ctx)
     assert e.value.status == T.WC_EINVAL
+
+
+def test_tma_staged_and_direct_linearize_agree(c5, monkeypatch):
+    """The fused lidar kernel reads its record tiles either straight from global memory (small windows) or from shared
+    memory stages filled by TMA bulk copies (large windows); both must give the same normal equations."""
+    od, ctx, w = c5
+    rng = np.random.default_rng(5)
+    smp = w.samples.copy()
+    smp["data_cor"][:, :6] = rng.normal(size=(len(smp), 6)) * 1e-3
+    out = {}
+    for staged in ("0", "1"):
+        monkeypatch.setenv("WC_LIN_STAGED", staged)
+        c2 = od.Context(0)
+        try:
+            out[staged] = od.EvaluateWindow(w.surfels, None, w.corr, None, None, smp, opts=_opts(), ctx=c2)
+        finally:
+            c2.close()
+    monkeypatch.delenv("WC_LIN_STAGED")
+    (c0, g0, H0), (c1, g1, H1) = out["0"], out["1"]
+    assert c1 == pytest.approx(c0, rel=1e-13)
+    np.testing.assert_allclose(g1, g0, rtol=0, atol=1e-11 * np.abs(g0).max())
+    np.testing.assert_allclose(H1, H0, rtol=0, atol=1e-11 * np.abs(H0).max())

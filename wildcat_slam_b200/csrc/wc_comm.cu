@@ -54,8 +54,19 @@ __global__ void __launch_bounds__(256) comm_allreduce(CommArgs a) {
   __threadfence_system();
   const int    buf   = a.at_candidate ? 1 - cur : cur;
   const size_t nH    = (size_t)a.N * a.N;
-  const size_t total = nH + a.N + 1;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  // only the lower triangle of J^T J is ever accumulated or read: packed index k -> (row, col), then gradient and cost
+  const size_t nL    = (size_t)a.N * (a.N + 1) / 2;
+  const size_t total = nL + a.N + 1;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    size_t i;
+    if (k < nL) {
+      size_t row = (size_t)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
+      while (row * (row + 1) / 2 > k) --row;
+      while ((row + 1) * (row + 2) / 2 <= k) ++row;
+      i = row * a.N + (k - row * (row + 1) / 2);
+    } else {
+      i = nH + (k - nL);
+    }
     double s = 0.0;
     for (int r = 0; r < a.world; ++r) s += *((const volatile double*)&a.part[r][i]);
     if (i < nH) a.H[buf][i] = s;
@@ -241,9 +252,9 @@ wc_status wc_comm_allreduce(wc_ctx* c, int at_candidate) {
   a.state = (const int*)state, a.err = c->d_comm_err;
   a.epoch = c->comm_epoch, a.rank = c->rank, a.world = c->world, a.at_candidate = at_candidate;
   a.timeout_cycles = 4000000000ll;  // ~2 s at 2 GHz
-  const size_t total = (size_t)a.N * a.N + a.N + 1;
+  const size_t total = (size_t)a.N * (a.N + 1) / 2 + a.N + 1;
   int          grid  = (int)((total + 255) / 256);
-  if (grid > 64) grid = 64;
+  if (grid > 2 * c->num_sms) grid = 2 * c->num_sms;
   { ++c->n_launches; comm_allreduce<<<grid, 256, 0, c->stream>>>(a); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;

@@ -14,12 +14,14 @@
 //                       damping, dense Cholesky in shared memory, step, accept/reject, radius update, termination —
 //                       one CTA, state resident on the device
 #include <float.h>
+#include <type_traits>
 #include <stdlib.h>
 
 #include "wc_ctx.h"
 #include <cooperative_groups.h>
 
 #include "wc_device_math.cuh"
+#include "wc_tma.cuh"
 
 using namespace wcd;
 namespace cg = cooperative_groups;
@@ -36,7 +38,9 @@ constexpr int LT       = 128;       // linearize tile = threads per CTA (43 KB o
 constexpr int JR       = 28;        // augmented row count: 24 Jacobian columns, residual, 3 pad
 constexpr int JS       = LT + 1;    // padded row stride (doubles)
 constexpr int NGRP     = LT / 32;
-constexpr int LIN_SMEM = (JR * JS + NGRP * 28 * 16) * 8;
+constexpr int LIN_SMEM_BASE = ((JR * JS + NGRP * 28 * 16) * 8 + 127) / 128 * 128;  // Jacobian tile + flush staging
+constexpr int LIN_SMEM      = LIN_SMEM_BASE + 2 * REC_COLS * LT * 8;                   // + two record stages (TMA), fp64 records
+constexpr int LIN_SMEM_R32  = LIN_SMEM_BASE + 2 * REC_COLS * LT * 4;                   // fp32 records
 
 struct LMState {
   // control
@@ -374,7 +378,7 @@ __device__ __forceinline__ void lane_block(int lane, int& bi, int& bj) {
   bj = bi + l;
 }
 
-template <int PREC>
+template <int PREC, bool STAGED>
 __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* sm, int cta, int ncta) {
   using TJ = typename TJSel<PREC>::type;   // element type of the tile's Jacobian rows and of the J^T J partial blocks
   TJ* Jt    = reinterpret_cast<TJ*>(sm);  // JR x JS
@@ -407,6 +411,26 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
   const int per    = (ntiles + ncta - 1) / ncta;
   const int tile0 = cta * per, tile1 = min(ntiles, tile0 + per);
 
+  // Record tiles are staged in shared memory by the TMA unit (cp.async.bulk: one 1-D bulk copy per SoA column, 16 per
+  // tile, all completing on one mbarrier), double buffered: the copy of tile k + 1 is in flight while tile k is evaluated
+  // and its J^T J accumulated.  Full tiles are always copied (the column stride is padded, rows past n_rec are ignored).
+  using TR = typename std::conditional<PREC == WC_PREC_F64, double, float>::type;
+  TR* srec = reinterpret_cast<TR*>(reinterpret_cast<unsigned char*>(sm) + LIN_SMEM_BASE);  // [2][REC_COLS][LT]
+  __shared__ __align__(8) uint64_t full_bar[2];
+  const TR* grec = PREC == WC_PREC_F64 ? reinterpret_cast<const TR*>(a.rec) : reinterpret_cast<const TR*>(a.rec32);
+  auto issue = [&](int tile, int stg) {  // threads 0 .. REC_COLS - 1: one column each; thread 0 also arms the barrier
+    if (t == 0) wctma::mbar_expect_tx(&full_bar[stg], (unsigned)(REC_COLS * LT * sizeof(TR)));
+    wctma::bulk_g2s(srec + (stg * REC_COLS + t) * LT, grec + (size_t)t * S + (size_t)tile * LT, (unsigned)(LT * sizeof(TR)), &full_bar[stg]);
+  };
+  if constexpr (STAGED) {
+    if (t == 0) {
+      wctma::mbar_init(&full_bar[0], 1);
+      wctma::mbar_init(&full_bar[1], 1);
+      wctma::mbar_fence_init();
+    }
+    __syncthreads();
+    if (t < REC_COLS && tile0 < tile1) issue(tile0, 0);
+  }
   // flush the per-thread 4x4 partial blocks of the current bucket into the dense normal equations
   auto flush = [&]() {
     __syncthreads();
@@ -434,8 +458,11 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
           const int sb = q / 6, gqb = (sb < 2 ? cur_b1 + sb : cur_b2 + sb - 2);
           if (sb < 2 && cur_b1 < 0) continue;
           const int gq = 12 * gqb + q % 6;
-          atomicAdd(&H[(size_t)gp * N + gq], v);
-          if (p != q) atomicAdd(&H[(size_t)gq * N + gp], v);
+          // lower triangle only (the LM step reads nothing else; wc_window_evaluate mirrors it for the caller).  Blocks of
+          // two factors' shared sample states overlap, so an entry and its mirror image can both occur: they are summed.
+          // (two different local columns on the same unknown — aliased intervals in WC_JAC_EXACT mode — meet on the
+          // diagonal, where the old mirrored pair of additions counted them twice, as (J_p + J_q)^2 requires)
+          atomicAdd(&H[(size_t)max(gp, gq) * N + min(gp, gq)], (gp == gq && p != q) ? 2.0 * v : v);
         }
       }
     }
@@ -445,12 +472,21 @@ __device__ __forceinline__ void lidar_linearize_body(const LinArgs& a, double* s
   for (int tile = tile0; tile < tile1; ++tile) {
     const int  i     = tile * LT + t;
     const bool valid = i < a.n_rec;
+    const int  stg   = (tile - tile0) & 1;
+    // the other stage was last read two barriers ago (every thread is past the previous tile's barriers): refill it
+    const TR* trec = grec + (size_t)tile * LT;  // !STAGED: straight from global memory (one tile per CTA: nothing to overlap)
+    size_t    tS   = S;
+    if constexpr (STAGED) {
+      if (t < REC_COLS && tile + 1 < tile1) issue(tile + 1, stg ^ 1);
+      wctma::mbar_wait(&full_bar[stg], (unsigned)(((tile - tile0) >> 1) & 1));
+      trec = srec + stg * REC_COLS * LT, tS = (size_t)LT;
+    }
     TJ         J[24], r = (TJ)0;
     double     cst = 0.0;
     int        b1l = -2, b2l = -2, bk = -1;
     if (valid) {
-      if constexpr (PREC == WC_PREC_F64) lidar_eval(a.rec, S, i, x, a.jac_mode, a.cauchy_b, a.cauchy_c, J, r, cst, b1l, b2l, bk);
-      else lidar_eval32<TJ>(a.rec32, S, i, x, a.jac_mode, (float)a.cauchy_b, (float)a.cauchy_c, J, r, cst, b1l, b2l, bk);
+      if constexpr (PREC == WC_PREC_F64) lidar_eval(trec, tS, t, x, a.jac_mode, a.cauchy_b, a.cauchy_c, J, r, cst, b1l, b2l, bk);
+      else lidar_eval32<TJ>(trec, tS, t, x, a.jac_mode, (float)a.cauchy_b, (float)a.cauchy_c, J, r, cst, b1l, b2l, bk);
     } else {
 #pragma unroll
       for (int k = 0; k < 24; ++k) J[k] = (TJ)0;
@@ -662,19 +698,23 @@ __device__ __forceinline__ void imu_linearize_body(const ImuArgs& a, double* sm,
     for (int r = 0; r < 12; ++r) v = fma(jac[r * IMU_LD + p], jac[r * IMU_LD + qc], v);
     if (v == 0.0) continue;
     const int gp = 12 * sblk[wid][p / 12] + p % 12;
-    if (q == nc) atomicAdd(&g[gp], v);
-    else atomicAdd(&H[(size_t)gp * N + 12 * sblk[wid][q / 12] + q % 12], v);
+    if (q == nc) {
+      atomicAdd(&g[gp], v);
+    } else {
+      const int gq = 12 * sblk[wid][q / 12] + q % 12;
+      if (gq <= gp) atomicAdd(&H[(size_t)gp * N + gq], v);  // lower triangle only
+    }
   }
 }
 
 // IMU triplets on the first n_imu CTAs, lidar tiles on the rest: one launch per linearisation.  The IMU warps run long
 // serial chains (Log / Exp / 12 x 36 Jacobians per triplet); scheduled first, they overlap with the lidar tiles
 // instead of forming the kernel's tail.
-template <int PREC>
+template <int PREC, bool STAGED>
 __global__ void __launch_bounds__(LT) window_linearize(LinArgs a, ImuArgs b, int n_lidar, int n_imu) {
   extern __shared__ __align__(16) double sm[];
   if ((int)blockIdx.x < n_imu) imu_linearize_body(b, sm, blockIdx.x);
-  else lidar_linearize_body<PREC>(a, sm, blockIdx.x - n_imu, n_lidar);
+  else lidar_linearize_body<PREC, STAGED>(a, sm, blockIdx.x - n_imu, n_lidar);
 }
 
 // one-time conversion of the sorted fp64 records to the 64-byte fp32 records of WC_PREC_MIXED / WC_PREC_F32
@@ -1604,6 +1644,14 @@ __global__ void __launch_bounds__(LMT) lm_step_wide(SolveBufs B, wc_solve_opts o
     reinterpret_cast<unsigned long long*>(gst)[k] = reinterpret_cast<const unsigned long long*>(&sst)[k];
 }
 
+// mirror the lower triangle (what the linearisation accumulates) into the upper one, for callers that want J^T J
+__global__ void symmetrize_lower(double* __restrict__ H, int N) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * N) return;
+  const int r = (int)(i / N), c = (int)(i % N);
+  if (c > r) H[i] = H[(size_t)c * N + r];
+}
+
 __global__ void extract_ts(const wc_sample_state* __restrict__ s, int K, double* __restrict__ ts, double* __restrict__ x) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -1641,6 +1689,7 @@ struct wc_solve_mem {
   double   grav[3];
   cudaEvent_t lin_ev[2 * WC_MAX_ITER_LOG + 4];  // begin / end of the linearisation passes of one solve
   int         n_lin_ev;
+  int         lin_timing_off;  // no event records while a batch is being captured into a graph
 };
 
 static wc_status solve_alloc(wc_ctx* c) {
@@ -1681,9 +1730,12 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
-  WC_CUDA(c, cudaFuncSetAttribute(window_linearize<WC_PREC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
-  WC_CUDA(c, cudaFuncSetAttribute(window_linearize<WC_PREC_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
-  WC_CUDA(c, cudaFuncSetAttribute(window_linearize<WC_PREC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_F64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
+  WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_MIXED, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_R32));
+  WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_F32, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_R32));
+  WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_F64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_BASE));
+  WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_MIXED, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_BASE));
+  WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_F32, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_BASE));
   for (int i = 0; i < 2 * WC_MAX_ITER_LOG + 4; ++i) WC_CUDA(c, cudaEventCreate(&m->lin_ev[i]));
   WC_CUDA(c, cudaFuncSetAttribute(lm_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return WC_OK;
@@ -1833,8 +1885,13 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
   a.rec = m->rec, a.rec32 = m->rec32, a.stride = m->stride, a.n_rec = (int)c->n_rec, a.B = B, a.at_candidate = at_candidate;
   a.jac_mode = o->jacobian_mode, a.cauchy_b = c->prm.cauchy_a * c->prm.cauchy_a, a.cauchy_c = 1.0 / a.cauchy_b;
   const int ntiles  = (int)((c->n_rec + LT - 1) / LT);
-  // one tile per CTA while that stays within a few waves (the SMs hold 4-5 tiles each); beyond that, contiguous chunks
-  const int n_lidar = ntiles <= 8 * c->num_sms ? ntiles : 4 * c->num_sms;
+  // Small windows (a few waves of tiles): one tile per CTA, records straight from global memory.  Large windows:
+  // resident CTAs with contiguous chunks of tiles, the record tiles staged by TMA bulk copies so that the copy of a CTA's
+  // next tile overlaps the evaluation of its current one.  (Measured at C3, 707 tiles: staging a CTA's only tile costs
+  // 6 us per launch — there is nothing to overlap with; at 2 M records it gains 12 %.)
+  static const int force_staged = getenv("WC_LIN_STAGED") ? atoi(getenv("WC_LIN_STAGED")) : -1;  // test hook
+  const bool staged  = force_staged >= 0 ? force_staged != 0 : ntiles > 8 * c->num_sms;
+  const int  n_lidar = !staged ? ntiles : (ntiles <= 3 * c->num_sms ? ntiles : 3 * c->num_sms);
   ImuArgs b;
   memset(&b, 0, sizeof(b));
   int n_imu_cta = 0;
@@ -1846,14 +1903,20 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     for (int k = 0; k < 3; ++k) b.grav[k] = m->grav[k];
     n_imu_cta = (int)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS);
   }
-  const bool timed = m->n_lin_ev + 2 <= 2 * WC_MAX_ITER_LOG + 4;
+  const bool timed = !m->lin_timing_off && m->n_lin_ev + 2 <= 2 * WC_MAX_ITER_LOG + 4;
   if (timed) WC_CUDA(c, cudaEventRecord(m->lin_ev[m->n_lin_ev++], st));
   if (n_lidar + n_imu_cta > 0) {
     ++c->n_launches;
     const unsigned grid = (unsigned)(n_lidar + n_imu_cta);
-    if (prec == WC_PREC_F64) window_linearize<WC_PREC_F64><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
-    else if (prec == WC_PREC_MIXED) window_linearize<WC_PREC_MIXED><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
-    else window_linearize<WC_PREC_F32><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
+    if (staged) {
+      if (prec == WC_PREC_F64) window_linearize<WC_PREC_F64, true><<<grid, LT, LIN_SMEM, st>>>(a, b, n_lidar, n_imu_cta);
+      else if (prec == WC_PREC_MIXED) window_linearize<WC_PREC_MIXED, true><<<grid, LT, LIN_SMEM_R32, st>>>(a, b, n_lidar, n_imu_cta);
+      else window_linearize<WC_PREC_F32, true><<<grid, LT, LIN_SMEM_R32, st>>>(a, b, n_lidar, n_imu_cta);
+    } else {
+      if (prec == WC_PREC_F64) window_linearize<WC_PREC_F64, false><<<grid, LT, LIN_SMEM_BASE, st>>>(a, b, n_lidar, n_imu_cta);
+      else if (prec == WC_PREC_MIXED) window_linearize<WC_PREC_MIXED, false><<<grid, LT, LIN_SMEM_BASE, st>>>(a, b, n_lidar, n_imu_cta);
+      else window_linearize<WC_PREC_F32, false><<<grid, LT, LIN_SMEM_BASE, st>>>(a, b, n_lidar, n_imu_cta);
+    }
   }
   if (timed) WC_CUDA(c, cudaEventRecord(m->lin_ev[m->n_lin_ev++], st));
   WC_CUDA(c, cudaGetLastError());
@@ -1903,7 +1966,7 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   static int evs_init = 0;
   int n_ev = 0;
   if (dbg_ev && !evs_init) { for (auto& e : evs) cudaEventCreate(&e); evs_init = 1; }
-  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
+  auto enqueue_batch = [&]() -> wc_status {
     for (int b = 0; b < batch; ++b) {
       // decide(previous candidate) + next trust-region step + clear the candidate buffer, then linearise there
       if (dbg_ev && n_ev + 3 < 256) cudaEventRecord(evs[n_ev++], st);
@@ -1918,13 +1981,36 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
         lm_step<false><<<1, LMT, 0, st>>>(B, o, c->world == 1);
       }
       if (dbg_ev && n_ev + 3 < 256) cudaEventRecord(evs[n_ev++], st);
-      if ((s = enqueue_linearize(c, B, &o, 1, 1))) return s;
-      if ((s = wc_comm_allreduce(c, 1))) return s;
+      wc_status es;
+      if ((es = enqueue_linearize(c, B, &o, 1, 1))) return es;
+      if ((es = wc_comm_allreduce(c, 1))) return es;
     }
+    return WC_OK;
+  };
+  // One batch of LM iterations is a fixed sequence of launches (every kernel reads its branch from the device-resident
+  // LM state): with WC_LM_GRAPH it is captured once per solve and replayed, which shortens the kernel-to-kernel gaps.
+  static const int use_graph = getenv("WC_LM_GRAPH") ? atoi(getenv("WC_LM_GRAPH")) : 0;
+  cudaGraphExec_t  gexec = nullptr;
+  if (use_graph && !dbg_ev && c->world == 1 && !use_wide) {
+    cudaGraph_t g = nullptr;
+    m->lin_timing_off = 1;
+    WC_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    s = enqueue_batch();
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    m->lin_timing_off = 0;
+    if (s) return s;
+    WC_CUDA(c, ce);
+    WC_CUDA(c, cudaGraphInstantiate(&gexec, g, 0));
+    cudaGraphDestroy(g);
+  }
+  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
+    if (gexec) WC_CUDA(c, cudaGraphLaunch(gexec, st));
+    else if ((s = enqueue_batch())) return s;
     WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));
     done = m->h_st->done;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
   WC_CUDA(c, cudaMemcpyAsync(m->h_x, c->d_x, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaEventRecord(c->ev[5], st));
   WC_CUDA(c, cudaStreamSynchronize(st));
@@ -1989,7 +2075,10 @@ extern "C" wc_status wc_window_evaluate(wc_ctx* c, const wc_surfel* sld, size_t 
   if ((s = wc_comm_allreduce(c, 0))) return s;
   if (cost) WC_CUDA(c, cudaMemcpyAsync(cost, m->cost, 8, cudaMemcpyDeviceToHost, st));
   if (grad) WC_CUDA(c, cudaMemcpyAsync(grad, m->gbuf[0], N * 8, cudaMemcpyDeviceToHost, st));
-  if (jtj) WC_CUDA(c, cudaMemcpyAsync(jtj, m->Hbuf[0], N * N * 8, cudaMemcpyDeviceToHost, st));
+  if (jtj) {
+    { ++c->n_launches; symmetrize_lower<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(m->Hbuf[0], (int)N); }
+    WC_CUDA(c, cudaMemcpyAsync(jtj, m->Hbuf[0], N * N * 8, cudaMemcpyDeviceToHost, st));
+  }
   WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());

@@ -146,6 +146,28 @@ __global__ void undistort_repack(const wc_imu_state* __restrict__ imu, int n_imu
   time[i] = t;
 }
 
+
+// ---- PointCloud2 payload -> 48-byte records (pcl::fromROSMsg for hilti_ros::Point, wildcat_slam_node.cc:49)
+// One thread per point; the fields sit at arbitrary (possibly unaligned) byte offsets of the point_step-byte record.
+__device__ __forceinline__ unsigned ld_u32_unaligned(const unsigned char* p) {
+  return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+}
+__global__ void unpack_pointcloud2(const unsigned char* __restrict__ data, int n, wc_pc2_layout L, wc_point48* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* r = data + (size_t)i * L.point_step;
+  wc_point48           p;
+  memset(&p, 0, sizeof(p));
+  if (L.off_x >= 0) p.x = __uint_as_float(ld_u32_unaligned(r + L.off_x));
+  if (L.off_y >= 0) p.y = __uint_as_float(ld_u32_unaligned(r + L.off_y));
+  if (L.off_z >= 0) p.z = __uint_as_float(ld_u32_unaligned(r + L.off_z));
+  if (L.off_intensity >= 0) p.intensity = __uint_as_float(ld_u32_unaligned(r + L.off_intensity));
+  if (L.off_time >= 0)
+    p.time = __longlong_as_double((long long)(((unsigned long long)ld_u32_unaligned(r + L.off_time + 4) << 32) | ld_u32_unaligned(r + L.off_time)));
+  if (L.off_ring >= 0) p.ring = (uint16_t)((unsigned)r[L.off_ring] | ((unsigned)r[L.off_ring + 1] << 8));
+  out[i] = p;
+}
+
 }  // namespace
 
 struct wc_sweep_mem {
@@ -157,6 +179,8 @@ struct wc_sweep_mem {
   int*          h_flags;  // pinned
   float4*       h_first;  // pinned: first undistorted point (anchors the relative voxel keys)
   double*       h_t0;
+  unsigned char* raw;     // PointCloud2 payload staging (grown on demand)
+  size_t        raw_cap;
 };
 
 static wc_status sweep_alloc(wc_ctx* c) {
@@ -178,7 +202,7 @@ static wc_status sweep_alloc(wc_ctx* c) {
 void wc_sweep_free(wc_ctx* c) {
   wc_sweep_mem* m = (wc_sweep_mem*)c->d_sweep;
   if (!m) return;
-  void* ptrs[] = {m->in, m->out, m->imu, m->blk_cnt, m->flags};
+  void* ptrs[] = {m->in, m->out, m->imu, m->blk_cnt, m->flags, m->raw};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (m->h_flags) cudaFreeHost(m->h_flags);
@@ -282,5 +306,33 @@ extern "C" wc_status wc_undistort_upload(wc_ctx* c, const wc_imu_state* imu, siz
   c->vox0[0] = (int)floor((double)m->h_first->x / vs), c->vox0[1] = (int)floor((double)m->h_first->y / vs),
   c->vox0[2] = (int)floor((double)m->h_first->z / vs);
   c->t_first = in[0].time, c->t_last = in[n - 1].time;
+  return WC_OK;
+}
+
+extern "C" wc_status wc_unpack_pointcloud2(wc_ctx* c, const uint8_t* data, size_t n, const wc_pc2_layout* L, wc_point48* out) {
+  if (!c || !L || (n && (!data || !out))) return WC_EINVAL;
+  if (n == 0) return WC_OK;
+  if (n > (size_t)c->prm.max_points) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_points", n);
+  const int32_t offs[6] = {L->off_x, L->off_y, L->off_z, L->off_intensity, L->off_time, L->off_ring};
+  const int     size[6] = {4, 4, 4, 4, 8, 2};
+  for (int k = 0; k < 6; ++k)
+    if (offs[k] >= 0 && (size_t)offs[k] + size[k] > L->point_step) WC_FAIL(c, WC_EINVAL, "PointCloud2 field %d lies outside the %u-byte point", k, L->point_step);
+  if (L->point_step == 0) WC_FAIL(c, WC_EINVAL, "point_step is zero");
+  wc_status s = sweep_alloc(c);
+  if (s) return s;
+  wc_sweep_mem* m  = (wc_sweep_mem*)c->d_sweep;
+  cudaStream_t  st = c->stream;
+  const size_t  bytes = n * (size_t)L->point_step;
+  if (bytes > m->raw_cap) {
+    if (m->raw) cudaFree(m->raw);
+    m->raw = nullptr, m->raw_cap = 0;
+    WC_CUDA(c, cudaMalloc(&m->raw, bytes));
+    m->raw_cap = bytes;
+  }
+  WC_CUDA(c, cudaMemcpyAsync(m->raw, data, bytes, cudaMemcpyHostToDevice, st));
+  { ++c->n_launches; unpack_pointcloud2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->raw, (int)n, *L, m->out); }
+  WC_CUDA(c, cudaMemcpyAsync(out, m->out, n * sizeof(wc_point48), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }

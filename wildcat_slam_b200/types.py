@@ -139,6 +139,12 @@ class PassStats(C.Structure):
                                           "ms_solve")] + [(n, C.c_int64) for n in ("n_surfels", "n_sld_corr", "n_fix_corr", "n_launches")]
 
 
+class Pc2Layout(C.Structure):
+    """wc_pc2_layout: where the fields of hilti_ros::Point sit inside one PointCloud2 point (-1: absent)."""
+    _fields_ = [("point_step", C.c_uint32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("off_time", C.c_int32), ("off_ring", C.c_int32)]
+
+
 class SweepFilter(C.Structure):
     """wc_sweep_filter: lidar -> IMU extrinsic, range limits and blind box (lio_config.h:18-30)."""
 
