@@ -144,6 +144,7 @@ def run_c5(args, rank, world, local_rank):
     from wildcat_slam_b200 import synthetic as S
     from wildcat_slam_b200 import types as T
 
+    os.environ.setdefault("WC_TIME_PASSES", "1")  # summary.gpu_ms_linearize: per-pass CUDA events (read once per process)
     w = S.make_stress_window(args.n_corr, K=args.poses)
     workload = _c5_workload(w, args)
     o = T.default_solve_opts()

@@ -266,6 +266,30 @@ wc_status wc_unpack_pointcloud2(wc_ctx* ctx, const uint8_t* data, size_t n_point
                                 wc_point48* out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Observability outputs — the numeric half of PrintSurfelResiduals /
+ * PrintImuResiduals (lidar_odometry.cc:56-93: ceres::Problem::Evaluate with apply_loss_function = true, i.e. the
+ * residuals after the Cauchy corrector) and of PubSurfels (surfel_extraction.cc:360-417: per-surfel marker pose,
+ * scale and colour from the eigen-decomposition of the world covariance).  Formatting (Histogram::ToString,
+ * histogram.cc:29-77) and message publishing stay on the host: wildcat_slam_b200/report.py.
+ *
+ * wc_window_residuals works on the window last handed to wc_window_upload / wc_window_solve* and evaluates at
+ * `data_cor` (K x 12; NULL: the window's uploaded starting point).  Lidar residuals come back in the solver's
+ * bucket order (a histogram does not care) with a per-residual flag telling the fixed-window (unary) blocks from
+ * the sliding-window (binary) ones; IMU residuals are 12 per block (gyro, acc, gyro bias, acc bias x 3).
+ * On a multi-GPU context every rank returns the residuals of its own block of correspondences.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct wc_marker {
+  double position[3];     /* GetCenterInWorld                                                   */
+  double orientation[4];  /* Eigen::Quaterniond(right-handed eigenvectors), coeff order x y z w */
+  double scale[3];        /* 3 sqrt(eigenvalue), after makeRightHanded's swap                    */
+  float  color[4];        /* ((n + 1) / 2, a = 1), n = GetNormInWorld                            */
+} wc_marker;
+wc_status wc_surfel_markers(wc_ctx* ctx, const wc_surfel* surfels, size_t n, wc_marker* out);
+wc_status wc_window_residuals(wc_ctx* ctx, const wc_solve_opts* opts, const double* data_cor, double* lidar_res,
+                              uint8_t* lidar_is_fix, size_t lidar_cap, size_t* n_lidar, double* imu_res, size_t imu_cap,
+                              size_t* n_imu_blocks);
+
+/* ------------------------------------------------------------------------------------------------
  * Surfel poses — replaces UpdateSurfelPoses (lidar_odometry.cc:160-170) + Surfel::UpdatePose
  * (surfel.h:48-58): interpolate the IMU pose at each surfel time (lerp / Eigen slerp) and move the
  * surfel to the body frame on first call.  In-place on host surfels.

@@ -151,6 +151,25 @@ def window_solve(sld, fix, sld_corr, fix_corr, imu, samples, params=None, opts=N
     return st, samples, summ
 
 
+def window_residuals(sld, fix, sld_corr, fix_corr, imu, samples, params=None, opts=None):
+    """PrintSurfelResiduals / PrintImuResiduals numbers: (status, sliding residuals, fixed residuals, imu residuals (n, 12))."""
+    prm, o = params or T.default_params(), opts or T.default_solve_opts()
+    keep, args, samples = _window_args(sld, fix, sld_corr, fix_corr, imu, samples)
+    ns, nf = len(keep[2]), len(keep[3])
+    lid = np.zeros(max(1, ns + nf))
+    ires = np.zeros((max(1, len(keep[4])), 12))
+    nb = C.c_int64(0)
+    st = lib().wco_window_residuals(C.byref(prm), C.byref(o), *args, _p(lid), _p(ires), C.byref(nb))
+    return st, lid[:ns].copy(), lid[ns:ns + nf].copy(), ires[:nb.value].copy()
+
+
+def surfel_markers(surfels):
+    surfels = np.ascontiguousarray(surfels, dtype=T.SURFEL)
+    out = np.zeros(max(1, len(surfels)), dtype=T.MARKER)
+    lib().wco_surfel_markers(_p(surfels), C.c_int64(len(surfels)), _p(out))
+    return out[:len(surfels)].copy()
+
+
 def lidar_factor(s1, s2, unary, sample_ts, x, params=None, jacobian_mode=T.WC_JAC_REFERENCE_OVERWRITE):
     prm = params or T.default_params()
     s1 = np.ascontiguousarray(s1, dtype=T.SURFEL).reshape(1)

@@ -633,3 +633,83 @@ extern "C" int wco_imu_factor(const wc_params* prm, const wc_imu_state* i3, cons
   if (!EvalImu(prm, f, xs, V3(grav3), residual12, jac)) return -WC_EOUT_OF_SPAN;
   return 12;
 }
+
+// ---- observability outputs --------------------------------------------------------------------------
+// PrintSurfelResiduals / PrintImuResiduals (lidar_odometry.cc:56-93): ceres::Problem::Evaluate with apply_loss_function =
+// true returns the residuals after the loss corrector, r * sqrt(rho') for the Cauchy blocks, unchanged for the IMU
+// blocks (TrivialLoss).  lidar_res: sliding-window blocks first, then the fixed-window blocks, in construction order.
+extern "C" int wco_window_residuals(const wc_params* prm, const wc_solve_opts* opts, const wc_surfel* sld, int64_t n_sld,
+                                    const wc_surfel* fix, int64_t n_fix, const wc_corr_idx* sld_corr, int64_t n_sld_corr,
+                                    const wc_corr_idx* fix_corr, int64_t n_fix_corr, const wc_imu_state* imu, int64_t n_imu,
+                                    const wc_sample_state* samples, int64_t K, double* lidar_res, double* imu_res,
+                                    int64_t* n_imu_blocks) {
+  Problem p;
+  int     st = Assemble(prm, opts, sld, n_sld, fix, n_fix, sld_corr, n_sld_corr, fix_corr, n_fix_corr, imu, n_imu, samples, K, &p);
+  if (st) return st;
+  std::vector<double> x(12 * K);
+  for (int64_t k = 0; k < K; ++k)
+    for (int j = 0; j < 12; ++j) x[12 * k + j] = samples[k].data_cor[j];
+  Cauchy loss(prm->cauchy_a);
+  size_t i = 0;
+  for (const LidarFactor& f : p.lidar) {
+    LidarEval e;
+    EvalLidar(f, x.data(), p.opts.jacobian_mode, false, &e);
+    double rho[3];
+    loss.Evaluate(e.r * e.r, rho);
+    lidar_res[i++] = e.r * std::sqrt(rho[1]);
+  }
+  *n_imu_blocks = (int64_t)p.imu.size();
+  size_t b = 0;
+  for (const ImuFactorDef& f : p.imu) {
+    const double* xs[3] = {x.data() + 12 * f.blk[0], x.data() + 12 * f.blk[1], f.mode == 0 ? x.data() + 12 * f.blk[2] : nullptr};
+    if (!EvalImu(prm, f, xs, p.gravity, imu_res + 12 * b, nullptr)) return WC_EOUT_OF_SPAN;
+    ++b;
+  }
+  return 0;
+}
+
+// PubSurfels (surfel_extraction.cc:360-417) without the ROS message.  The eigenvector signs follow this file's SymEig3
+// restatement of Eigen's solver (parity unpinned: Eigen is absent from this image).
+extern "C" void wco_surfel_markers(const wc_surfel* s, int64_t n, wc_marker* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    WorldSurfel w = World(s[i]);
+    Q4          q = Q4::FromCoeffs(s[i].rot);
+    double      ev[3];
+    M3          V;
+    SymEig3(w.covw, ev, V);
+    auto unit = [](V3 v) { return v / std::sqrt(dot(v, v)); };
+    V3   c0 = unit(V.col(0)), c1 = unit(V.col(1)), c2 = unit(V.col(2));
+    if (dot(cross(c0, c1), c2) < 0) {  // makeRightHanded :340-358
+      std::swap(c0, c1);
+      std::swap(ev[0], ev[1]);
+    }
+    const double m[3][3] = {{c0.x, c1.x, c2.x}, {c0.y, c1.y, c2.y}, {c0.z, c1.z, c2.z}};
+    double       qq[4];
+    double       t = m[0][0] + m[1][1] + m[2][2];
+    if (t > 0.0) {  // Eigen::Quaterniond(Matrix3d)
+      t     = std::sqrt(t + 1.0);
+      qq[3] = 0.5 * t;
+      t     = 0.5 / t;
+      qq[0] = (m[2][1] - m[1][2]) * t, qq[1] = (m[0][2] - m[2][0]) * t, qq[2] = (m[1][0] - m[0][1]) * t;
+    } else {
+      int a = 0;
+      if (m[1][1] > m[0][0]) a = 1;
+      if (m[2][2] > m[a][a]) a = 2;
+      const int b = (a + 1) % 3, c = (b + 1) % 3;
+      t     = std::sqrt(m[a][a] - m[b][b] - m[c][c] + 1.0);
+      qq[a] = 0.5 * t;
+      t     = 0.5 / t;
+      qq[3] = (m[c][b] - m[b][c]) * t;
+      qq[b] = (m[b][a] + m[a][b]) * t;
+      qq[c] = (m[c][a] + m[a][c]) * t;
+    }
+    const bool body = s[i].is_in_body_frame != 0;
+    V3         cen  = body ? w.cw : V3(s[i].center);
+    V3         nw   = body ? q * V3(s[i].norm) : V3(s[i].norm);
+    wc_marker& k    = out[i];
+    k.position[0] = cen.x, k.position[1] = cen.y, k.position[2] = cen.z;
+    for (int j = 0; j < 4; ++j) k.orientation[j] = qq[j];
+    for (int j = 0; j < 3; ++j) k.scale[j] = 3.0 * std::sqrt(ev[j]);
+    k.color[0] = (float)((nw.x + 1) / 2), k.color[1] = (float)((nw.y + 1) / 2), k.color[2] = (float)((nw.z + 1) / 2), k.color[3] = 1.f;
+  }
+}

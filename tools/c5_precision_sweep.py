@@ -1,8 +1,10 @@
 """BASELINE config 5: fp64 vs fp32 tolerance sweep of the fused lidar kernel.  For each size, solves the same stress
 window with WC_PREC_F64 / WC_PREC_MIXED / WC_PREC_F32 and prints iterations, final cost, the largest difference of the
 solution from the fp64 one, and the time of one linearisation pass."""
+import os
 import sys
 
+os.environ.setdefault("WC_TIME_PASSES", "1")
 sys.path.insert(0, ".")
 import numpy as np
 

@@ -59,6 +59,8 @@ def load():
     lib.wc_filter_points.argtypes = [vp, P(T.SweepFilter), vp, sz, vp, sz, P(sz)]
     lib.wc_undistort_sweep.argtypes = [vp, vp, sz, vp, sz, vp]
     lib.wc_undistort_upload.argtypes = [vp, vp, sz, vp, sz]
+    lib.wc_surfel_markers.argtypes = [vp, vp, sz, vp]
+    lib.wc_window_residuals.argtypes = [vp, P(T.SolveOpts), vp, vp, vp, sz, P(sz), vp, sz, P(sz)]
     lib.wc_unpack_pointcloud2.argtypes = [vp, vp, sz, P(T.Pc2Layout), vp]
     lib.wc_update_surfel_poses.argtypes = [vp, vp, sz, vp, sz]
     lib.wc_match.argtypes = [vp, vp, sz, vp, sz, i32, vp, sz, P(sz), vp, P(dbl)]

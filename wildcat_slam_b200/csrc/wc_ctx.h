@@ -155,7 +155,7 @@ struct wc_ctx {
   void*            h_lm;      // pinned mirror
   int*             d_status;  // assemble errors
   void*            d_spline;  // wc_spline_mem
-  int              n_imu_blocks;
+  int              n_imu_blocks, first_imu_block;
   int              lm_batch;  // LM iterations enqueued between host checks of the termination flag
 
   // ---- multi-GPU exchange

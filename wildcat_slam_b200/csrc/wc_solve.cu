@@ -1652,6 +1652,108 @@ __global__ void symmetrize_lower(double* __restrict__ H, int N) {
   if (c > r) H[i] = H[(size_t)c * N + r];
 }
 
+
+// ---------------------------------------------------------------------------------------------- outputs (8f rank 4)
+// residual after the Cauchy corrector of every packed lidar record, in record order; unary (fixed-window) flag
+__global__ void lidar_residuals(const double* __restrict__ rec, int n, int stride, const double* __restrict__ x, int jac_mode, double cb,
+                                double cc, double* __restrict__ out, unsigned char* __restrict__ is_fix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double J[24], r, cst;
+  int    b1l, b2l, bk;
+  lidar_eval(rec, (size_t)stride, i, x, jac_mode, cb, cc, J, r, cst, b1l, b2l, bk);
+  out[i]    = r;
+  is_fix[i] = b1l < 0;
+}
+
+// the 12 residuals of every IMU triplet inside the sample span (BuildImuResiduals, lidar_odometry.cc:319-363), one thread
+// per triplet; out[12 * slot ..], slot = rank of the triplet among the valid ones (they form one contiguous range)
+__global__ void imu_residuals(ImuArgs a, const double* __restrict__ x, int first_valid, double* __restrict__ out, int* __restrict__ err) {
+  const int i = first_valid + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 2 >= a.n_imu) return;
+  const wc_imu_state &i1 = a.imu[i], &i2 = a.imu[i + 1], &i3 = a.imu[i + 2];
+  if (i1.timestamp < a.ts[0] || i3.timestamp > a.ts[a.K - 1]) return;
+  const int sp2  = upper_bound_ts(a.ts, a.K, i1.timestamp);
+  const int mode = (sp2 == a.K - 1) ? 1 : 0;
+  const double tsv[3] = {a.ts[sp2 - 1], a.ts[sp2], mode == 0 ? a.ts[sp2 + 1] : DBL_MAX};
+  const double* xs[3] = {x + 12 * (sp2 - 1), x + 12 * sp2, x + 12 * (mode == 0 ? sp2 + 1 : sp2)};
+  StateCorr    c[3];
+  const double tt[3] = {i1.timestamp, i2.timestamp, i3.timestamp};
+  for (int s = 0; s < 3; ++s) {
+    const double t = tt[s];
+    int          l = 0;
+    if (mode == 0) {
+      const bool in12 = t >= tsv[0] && t < tsv[1], in23 = t >= tsv[1] && t <= tsv[2];
+      if (!(in12 || in23)) *err = WC_EOUT_OF_SPAN;
+      l = in12 ? 0 : 1;
+    } else if (!(t >= tsv[0] && t <= tsv[1])) {
+      *err = WC_EOUT_OF_SPAN;
+    }
+    state_corr(xs[l], xs[l + 1], (t - tsv[l]) / (tsv[l + 1] - tsv[l]), c[s]);
+  }
+  const Q4 R1 = ldq(i1.rot), R2 = ldq(i2.rot);
+  const Q4 E1R1 = Exp(c[0].r) * R1;
+  const V3 gyr_est = Log((conj(E1R1) * Exp(c[1].r)) * R2) / a.dt;
+  const V3 acc_est = ((c[2].t + ld3(i3.pos)) + (c[0].t + ld3(i1.pos)) - 2.0 * (c[1].t + ld3(i2.pos))) / (a.dt * a.dt);
+  const V3 rg  = a.wg * ((ld3(i1.gyr) + ld3(i2.gyr)) / 2.0 - gyr_est - c[0].bg);
+  const V3 ra  = a.wa * (E1R1 * (ld3(i1.acc) - c[0].ba) - acc_est + ld3(a.grav));
+  const V3 rbg = a.wbg * (c[0].bg - c[1].bg);
+  const V3 rba = a.wba * (c[0].ba - c[1].ba);
+  double*  o   = out + 12 * (size_t)(i - first_valid);
+  o[0] = rg.x, o[1] = rg.y, o[2] = rg.z, o[3] = ra.x, o[4] = ra.y, o[5] = ra.z;
+  o[6] = rbg.x, o[7] = rbg.y, o[8] = rbg.z, o[9] = rba.x, o[10] = rba.y, o[11] = rba.z;
+}
+
+// PubSurfels (surfel_extraction.cc:360-417) without the ROS message: marker pose / scale / colour per surfel
+__global__ void surfel_markers(const wc_surfel* __restrict__ s, int n, wc_marker* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Q4 q = ldq(s[i].rot);
+  const M3 R = ToMatrix(q);
+  const M3 cw = (R * ld33(s[i].covariance)) * transpose(R);  // GetCovarianceInWorld (surfel.h:89-91)
+  double   ev[3];
+  M3       V;
+  SymEig3(cw.m[0][0], cw.m[1][0], cw.m[2][0], cw.m[1][1], cw.m[2][1], cw.m[2][2], ev, V);  // lower triangle like Eigen
+  // makeRightHanded (:340-358)
+  auto unit = [](V3 v) { return v / sqrt(dot(v, v)); };
+  V3 c0 = unit(col(V, 0)), c1 = unit(col(V, 1)), c2 = unit(col(V, 2));
+  if (dot(cross(c0, c1), c2) < 0) {
+    const V3 t = c0;
+    c0 = c1, c1 = t;
+    const double e = ev[0];
+    ev[0] = ev[1], ev[1] = e;
+  }
+  const double m[3][3] = {{c0.x, c1.x, c2.x}, {c0.y, c1.y, c2.y}, {c0.z, c1.z, c2.z}};
+  // Eigen::Quaterniond(rot): trace branch, else the largest diagonal element
+  double qq[4];  // x y z w
+  double t = m[0][0] + m[1][1] + m[2][2];
+  if (t > 0.0) {
+    t     = sqrt(t + 1.0);
+    qq[3] = 0.5 * t;
+    t     = 0.5 / t;
+    qq[0] = (m[2][1] - m[1][2]) * t, qq[1] = (m[0][2] - m[2][0]) * t, qq[2] = (m[1][0] - m[0][1]) * t;
+  } else {
+    int a = 0;
+    if (m[1][1] > m[0][0]) a = 1;
+    if (m[2][2] > m[a][a]) a = 2;
+    const int b = (a + 1) % 3, c = (b + 1) % 3;
+    t     = sqrt(m[a][a] - m[b][b] - m[c][c] + 1.0);
+    qq[a] = 0.5 * t;
+    t     = 0.5 / t;
+    qq[3] = (m[c][b] - m[b][c]) * t;
+    qq[b] = (m[b][a] + m[a][b]) * t;
+    qq[c] = (m[c][a] + m[a][c]) * t;
+  }
+  const V3 cen = s[i].is_in_body_frame ? q * ld3(s[i].center) + ld3(s[i].pos) : ld3(s[i].center);  // GetCenterInWorld
+  const V3 nw  = s[i].is_in_body_frame ? q * ld3(s[i].norm) : ld3(s[i].norm);
+  wc_marker k;
+  k.position[0] = cen.x, k.position[1] = cen.y, k.position[2] = cen.z;
+  for (int j = 0; j < 4; ++j) k.orientation[j] = qq[j];
+  for (int j = 0; j < 3; ++j) k.scale[j] = 3.0 * sqrt(ev[j]);
+  k.color[0] = (float)((nw.x + 1) / 2), k.color[1] = (float)((nw.y + 1) / 2), k.color[2] = (float)((nw.z + 1) / 2), k.color[3] = 1.f;
+  out[i] = k;
+}
+
 __global__ void extract_ts(const wc_sample_state* __restrict__ s, int K, double* __restrict__ ts, double* __restrict__ x) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -1687,6 +1789,18 @@ struct wc_solve_mem {
   LMState* h_st;
   double*  h_x;
   double   grav[3];
+  wc_surfel*  mk_in;      // surfel staging of wc_surfel_markers (grown on demand)
+  size_t      mk_cap;
+  void*       rec_markers(wc_ctx* c, size_t n) {
+    if (n > mk_cap) {
+      if (mk_in) cudaFree(mk_in);
+      mk_in = nullptr, mk_cap = 0;
+      if (cudaMalloc(&mk_in, n * sizeof(wc_surfel)) != cudaSuccess) return nullptr;
+      mk_cap = n;
+    }
+    (void)c;
+    return mk_in;
+  }
   cudaEvent_t lin_ev[2 * WC_MAX_ITER_LOG + 4];  // begin / end of the linearisation passes of one solve
   int         n_lin_ev;
   int         lin_timing_off;  // no event records while a batch is being captured into a graph
@@ -1749,7 +1863,7 @@ void wc_solve_free(wc_ctx* c) {
   if (!m) return;
   for (auto& e : m->lin_ev)
     if (e) cudaEventDestroy(e);
-  void* mp[] = {m->rec32, m->ts, m->tmp, m->rec, m->bucket, m->hist, m->off, m->cursor, m->Hbuf[0], m->Hbuf[1], m->gbuf[0], m->gbuf[1],
+  void* mp[] = {m->mk_in, m->rec32, m->ts, m->tmp, m->rec, m->bucket, m->hist, m->off, m->cursor, m->Hbuf[0], m->Hbuf[1], m->gbuf[0], m->gbuf[1],
                 m->cost, m->scale, m->diag, m->step, m->A, m->st, m->act};
   for (void* p : mp)
     if (p) cudaFree(p);
@@ -1829,9 +1943,12 @@ extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_
   if (n_imu) WC_CUDA(c, cudaMemcpyAsync(c->d_imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_samples, samples, K * sizeof(wc_sample_state), cudaMemcpyHostToDevice, st));
   for (int k = 0; k < 3; ++k) m->grav[k] = samples[K - 1].grav[k];  // lidar_odometry.cc:341,355
-  c->n_imu_blocks = 0;  // BuildImuResiduals' block count (:320-329), for the summary only
+  c->n_imu_blocks = 0, c->first_imu_block = 0;  // BuildImuResiduals' blocks (:320-329): one contiguous range of triplets
   for (size_t i = 0; i + 2 < n_imu; ++i)
-    if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) ++c->n_imu_blocks;
+    if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) {
+      if (c->n_imu_blocks == 0) c->first_imu_block = (int)i;
+      ++c->n_imu_blocks;
+    }
   return wc_window_prepare_device(c);
 }
 
@@ -1853,9 +1970,12 @@ wc_status wc_window_upload_aux(wc_ctx* c, const wc_imu_state* imu, size_t n_imu,
   if (n_imu) WC_CUDA(c, cudaMemcpyAsync(c->d_imu, imu, n_imu * sizeof(wc_imu_state), cudaMemcpyHostToDevice, st));
   WC_CUDA(c, cudaMemcpyAsync(c->d_samples, samples, K * sizeof(wc_sample_state), cudaMemcpyHostToDevice, st));
   for (int k = 0; k < 3; ++k) m->grav[k] = samples[K - 1].grav[k];  // lidar_odometry.cc:341,355
-  c->n_imu_blocks = 0;
+  c->n_imu_blocks = 0, c->first_imu_block = 0;
   for (size_t i = 0; i + 2 < n_imu; ++i)
-    if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) ++c->n_imu_blocks;
+    if (imu[i].timestamp >= samples[0].timestamp && imu[i + 2].timestamp <= samples[K - 1].timestamp) {
+      if (c->n_imu_blocks == 0) c->first_imu_block = (int)i;
+      ++c->n_imu_blocks;
+    }
   WC_CUDA(c, cudaStreamSynchronize(st));
   return WC_OK;
 }
@@ -1903,7 +2023,9 @@ static wc_status enqueue_linearize(wc_ctx* c, const SolveBufs& B_in, const wc_so
     for (int k = 0; k < 3; ++k) b.grav[k] = m->grav[k];
     n_imu_cta = (int)((c->n_imu - 2 + IMU_WARPS - 1) / IMU_WARPS);
   }
-  const bool timed = !m->lin_timing_off && m->n_lin_ev + 2 <= 2 * WC_MAX_ITER_LOG + 4;
+  // per-pass event records (summary.gpu_ms_linearize) cost ~5 us of stream time each: only on request (WC_TIME_PASSES=1)
+  static const int time_passes = getenv("WC_TIME_PASSES") ? atoi(getenv("WC_TIME_PASSES")) : 0;
+  const bool timed = time_passes && !m->lin_timing_off && m->n_lin_ev + 2 <= 2 * WC_MAX_ITER_LOG + 4;
   if (timed) WC_CUDA(c, cudaEventRecord(m->lin_ev[m->n_lin_ev++], st));
   if (n_lidar + n_imu_cta > 0) {
     ++c->n_launches;
@@ -1988,10 +2110,12 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
     return WC_OK;
   };
   // One batch of LM iterations is a fixed sequence of launches (every kernel reads its branch from the device-resident
-  // LM state): with WC_LM_GRAPH it is captured once per solve and replayed, which shortens the kernel-to-kernel gaps.
-  static const int use_graph = getenv("WC_LM_GRAPH") ? atoi(getenv("WC_LM_GRAPH")) : 0;
+  // LM state): it is captured once per solve and replayed as a CUDA graph, which shortens the kernel-to-kernel gaps
+  // (WC_LM_GRAPH=0 turns that off).
+  static const int use_graph = getenv("WC_LM_GRAPH") ? atoi(getenv("WC_LM_GRAPH")) : 1;  // measured at C3: solve 2.54 -> 2.35 ms
   cudaGraphExec_t  gexec = nullptr;
-  if (use_graph && !dbg_ev && c->world == 1 && !use_wide) {
+  static const int time_passes_g = getenv("WC_TIME_PASSES") ? atoi(getenv("WC_TIME_PASSES")) : 0;
+  if (use_graph && !dbg_ev && !time_passes_g && c->world == 1 && !use_wide) {
     cudaGraph_t g = nullptr;
     m->lin_timing_off = 1;
     WC_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -2093,4 +2217,76 @@ void wc_solve_exchange_views(wc_ctx* c, int which, double** H, double** g, doubl
   H[0] = m->Hbuf[0], H[1] = m->Hbuf[1], g[0] = m->gbuf[0], g[1] = m->gbuf[1], cost[0] = m->cost, cost[1] = m->cost + 1;
   *N     = (int)(12 * c->K);
   *state = m->st;
+}
+
+extern "C" wc_status wc_window_residuals(wc_ctx* c, const wc_solve_opts* opts, const double* data_cor, double* lidar_res,
+                                         uint8_t* lidar_is_fix, size_t lidar_cap, size_t* n_lidar, double* imu_res, size_t imu_cap,
+                                         size_t* n_imu_blocks) {
+  if (!c || !c->d_lm || c->K < 2 || !n_lidar || !n_imu_blocks) return WC_EINVAL;
+  wc_solve_opts o;
+  if (opts) o = *opts; else wc_default_solve_opts(&o);
+  wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
+  cudaStream_t  st = c->stream;
+  const size_t  N  = 12 * c->K;
+  *n_lidar = c->n_rec, *n_imu_blocks = 0;
+  if (c->n_rec > lidar_cap) WC_FAIL(c, WC_ECAPACITY, "%zu lidar residuals exceed the output capacity %zu", c->n_rec, lidar_cap);
+  if (c->n_rec && (!lidar_res || !lidar_is_fix)) return WC_EINVAL;
+  // evaluation point
+  if (data_cor) WC_CUDA(c, cudaMemcpyAsync(c->d_xc, data_cor, N * 8, cudaMemcpyHostToDevice, st));
+  else WC_CUDA(c, cudaMemcpyAsync(c->d_xc, c->d_x0, N * 8, cudaMemcpyDeviceToDevice, st));
+  // scratch: the unsorted staging columns of the pack stage are free after wc_window_upload
+  double*        d_res = m->tmp;
+  unsigned char* d_fix = (unsigned char*)(m->tmp + m->stride);
+  if (c->n_rec) {
+    ++c->n_launches;
+    lidar_residuals<<<(unsigned)((c->n_rec + 255) / 256), 256, 0, st>>>(m->rec, (int)c->n_rec, m->stride, c->d_xc, o.jacobian_mode,
+                                                                     c->prm.cauchy_a * c->prm.cauchy_a, 1.0 / (c->prm.cauchy_a * c->prm.cauchy_a),
+                                                                     d_res, d_fix);
+    WC_CUDA(c, cudaMemcpyAsync(lidar_res, d_res, c->n_rec * 8, cudaMemcpyDeviceToHost, st));
+    WC_CUDA(c, cudaMemcpyAsync(lidar_is_fix, d_fix, c->n_rec, cudaMemcpyDeviceToHost, st));
+  }
+  // IMU blocks: the triplets inside the sample span are contiguous; their range comes from the host copy of the counts
+  if (o.use_imu_factors && c->n_imu >= 3 && c->n_imu_blocks > 0 && c->rank == 0) {
+    if ((size_t)c->n_imu_blocks > imu_cap) WC_FAIL(c, WC_ECAPACITY, "%d IMU blocks exceed the output capacity %zu", c->n_imu_blocks, imu_cap);
+    if (!imu_res) return WC_EINVAL;
+    if ((size_t)c->n_imu_blocks * 12 > (size_t)(REC_COLS - 2) * m->stride) WC_FAIL(c, WC_ECAPACITY, "IMU residual scratch too small");
+    ImuArgs b;
+    memset(&b, 0, sizeof(b));
+    b.imu = c->d_imu, b.n_imu = (int)c->n_imu, b.ts = m->ts, b.K = (int)c->K;
+    b.wg = c->prm.weight_gyr, b.wa = c->prm.weight_acc, b.wbg = c->prm.weight_bg, b.wba = c->prm.weight_ba;
+    b.dt = 1.0 / c->prm.imu_rate;
+    for (int k = 0; k < 3; ++k) b.grav[k] = m->grav[k];
+    double* d_imu_res = m->tmp + 2 * (size_t)m->stride;
+    WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
+    ++c->n_launches;
+    imu_residuals<<<(unsigned)((c->n_imu_blocks + 127) / 128), 128, 0, st>>>(b, c->d_xc, c->first_imu_block, d_imu_res, &m->st->err);
+    WC_CUDA(c, cudaMemcpyAsync(imu_res, d_imu_res, (size_t)c->n_imu_blocks * 96, cudaMemcpyDeviceToHost, st));
+    WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+    *n_imu_blocks = (size_t)c->n_imu_blocks;
+  }
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  if (*n_imu_blocks && m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "IMU state outside its sample interval");
+  return WC_OK;
+}
+
+extern "C" wc_status wc_surfel_markers(wc_ctx* c, const wc_surfel* surfels, size_t n, wc_marker* out) {
+  if (!c || (n && (!surfels || !out))) return WC_EINVAL;
+  if (n == 0) return WC_OK;
+  if (n > (size_t)c->prm.max_surfels) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_surfels", n);
+  wc_status s = solve_alloc(c);
+  if (s) return s;
+  wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
+  cudaStream_t  st = c->stream;
+  if (n * sizeof(wc_marker) > (size_t)REC_COLS * m->stride * 8) WC_FAIL(c, WC_ECAPACITY, "marker scratch too small (raise max_corrs)");
+  // d_fix is free between windows only if the caller is not mid-solve: markers use their own staging, the pack scratch
+  wc_surfel* d_in = (wc_surfel*)m->rec_markers(c, n);
+  if (!d_in) WC_FAIL(c, WC_ECUDA, "marker staging allocation failed");
+  WC_CUDA(c, cudaMemcpyAsync(d_in, surfels, n * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
+  wc_marker* d_out = (wc_marker*)m->tmp;
+  { ++c->n_launches; surfel_markers<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, (int)n, d_out); }
+  WC_CUDA(c, cudaMemcpyAsync(out, d_out, n * sizeof(wc_marker), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
+  return WC_OK;
 }

@@ -47,6 +47,7 @@ SAMPLE = np.dtype(
 IMU = np.dtype(
     [("timestamp", "<f8"), ("pos", "<f8", (3,)), ("rot", "<f8", (4,)), ("acc", "<f8", (3,)), ("gyr", "<f8", (3,))]
 )
+MARKER = np.dtype([("position", "<f8", (3,)), ("orientation", "<f8", (4,)), ("scale", "<f8", (3,)), ("color", "<f4", (4,))])
 ASSIGN = np.dtype([("vx", "<i4"), ("vy", "<i4"), ("vz", "<i4"), ("leaf", "<i4")])
 
 assert POINT48.itemsize == 48 and SURFEL.itemsize == 208 and SAMPLE.itemsize == 184 and IMU.itemsize == 112
