@@ -362,6 +362,29 @@ wc_status wc_pass_upload(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu, con
                          size_t K, const wc_surfel* fix, size_t n_fix);
 wc_status wc_window_pass_resident(wc_ctx* ctx, const wc_solve_opts* opts, wc_solve_summary* summary,
                                   double* data_cor_out /* K*12, may be NULL */, wc_pass_stats* stats);
+
+/* Windows resident across sweeps (second half; lidar_odometry.cc:527-528,228-250,574-580).
+ * The reference keeps every surfel of the last ~6 s in surfels_sld_win_, appends each new sweep's surfels to it, updates
+ * the poses of ALL of them, and matches / solves over the whole window; ShrinkToFit then moves the surfels older than the
+ * first IMU state of the trimmed window to the front of the fixed window.  Here both windows live in HBM:
+ *   wc_pass_upload_windows  like wc_pass_upload, plus the body-frame sliding-window surfels of the earlier sweeps.  With
+ *                           WC_KEEP_SLD / WC_KEEP_FIX the window left on the device by the previous pass (and
+ *                           wc_window_shrink) is kept and the corresponding host array is ignored: only the new sweep,
+ *                           the IMU states and the sample states cross PCIe.
+ *   wc_window_pass_resident appends the new sweep's surfels behind the earlier ones, then steps 8-13 on the whole window.
+ *   wc_window_shrink        the surfel half of ShrinkToFit: sliding-window surfels with timestamp < t_front_imu move, newest
+ *                           first, to the front of the fixed window (std::deque::push_front order).  trim_fixed = 0
+ *                           reproduces the reference, whose trim loop compares back() with back() and never removes
+ *                           anything; trim_fixed = 1 drops fixed-window surfels older than
+ *                           fix_window_duration behind the newest one.
+ *   wc_windows_fetch        copies both resident windows to the host (tests, hand-over to another context). */
+enum { WC_KEEP_SLD = 1, WC_KEEP_FIX = 2 };
+wc_status wc_pass_upload_windows(wc_ctx* ctx, const wc_imu_state* imu, size_t n_imu, const wc_sample_state* samples, size_t K,
+                                 const wc_surfel* fix, size_t n_fix, const wc_surfel* sld_prev, size_t n_sld_prev, int keep_flags);
+wc_status wc_window_shrink(wc_ctx* ctx, double t_front_imu, double fix_window_duration, int trim_fixed, size_t* n_sld,
+                           size_t* n_fix);
+wc_status wc_windows_fetch(wc_ctx* ctx, wc_surfel* sld, size_t sld_cap, size_t* n_sld, wc_surfel* fix, size_t fix_cap,
+                           size_t* n_fix);
 /* number of CUDA kernels this ctx has launched since creation */
 int64_t   wc_launch_count(const wc_ctx* ctx);
 

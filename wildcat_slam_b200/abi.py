@@ -74,6 +74,9 @@ def load():
     lib.wc_apply_corrections.argtypes = [vp, vp, sz, vp, sz]
     lib.wc_predict_states.argtypes = [vp, vp, sz, vp, vp, vp, dbl, dbl, sz, vp]
     lib.wc_pass_upload.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+    lib.wc_pass_upload_windows.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, i32]
+    lib.wc_window_shrink.argtypes = [vp, dbl, dbl, i32, P(sz), P(sz)]
+    lib.wc_windows_fetch.argtypes = [vp, vp, sz, P(sz), vp, sz, P(sz)]
     lib.wc_window_pass_resident.argtypes = [vp, P(T.SolveOpts), P(T.SolveSummary), vp, P(T.PassStats)]
     lib.wc_launch_count.argtypes = [vp]
     lib.wc_launch_count.restype = C.c_int64

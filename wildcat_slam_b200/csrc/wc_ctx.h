@@ -143,6 +143,8 @@ struct wc_ctx {
   wc_corr_rec*     d_rec;
   wc_imu_rec*      d_imu_rec;
   size_t           n_sld, n_fix, n_sld_corr, n_fix_corr, n_imu, K, n_rec, n_imu_rec;
+  size_t           n_sld_prev;  // sliding-window surfels of earlier sweeps in d_sld[0 .. n_sld_prev): the pass appends behind them
+  wc_surfel*       d_fix_tmp;   // staging of wc_window_shrink
   double*          d_x;       // 12K current point
   double*          d_xc;      // candidate
   double*          d_x0;      // uploaded start

@@ -1804,6 +1804,7 @@ struct wc_solve_mem {
   cudaEvent_t lin_ev[2 * WC_MAX_ITER_LOG + 4];  // begin / end of the linearisation passes of one solve
   int         n_lin_ev;
   int         lin_timing_off;  // no event records while a batch is being captured into a graph
+  cudaGraphExec_t gexec;       // one batch of LM iterations, kept across solves and updated in place
 };
 
 static wc_status solve_alloc(wc_ctx* c) {
@@ -1857,10 +1858,11 @@ static wc_status solve_alloc(wc_ctx* c) {
 
 void wc_solve_free(wc_ctx* c) {
   wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
-  void* ptrs[] = {c->d_sld, c->d_fix, c->d_sld_corr, c->d_fix_corr, c->d_imu, c->d_samples, c->d_x, c->d_xc, c->d_x0};
+  void* ptrs[] = {c->d_sld, c->d_fix, c->d_sld_corr, c->d_fix_corr, c->d_imu, c->d_samples, c->d_x, c->d_xc, c->d_x0, c->d_fix_tmp, c->d_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (!m) return;
+  if (m->gexec) cudaGraphExecDestroy(m->gexec);
   for (auto& e : m->lin_ev)
     if (e) cudaEventDestroy(e);
   void* mp[] = {m->mk_in, m->rec32, m->ts, m->tmp, m->rec, m->bucket, m->hist, m->off, m->cursor, m->Hbuf[0], m->Hbuf[1], m->gbuf[0], m->gbuf[1],
@@ -1936,6 +1938,7 @@ extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_
   if (n_imu > (size_t)c->prm.max_imu_states) WC_FAIL(c, WC_ECAPACITY, "too many IMU states");
   cudaStream_t st = c->stream;
   c->n_sld = n_sld, c->n_fix = n_fix, c->n_sld_corr = n_sld_corr, c->n_fix_corr = n_fix_corr, c->n_imu = n_imu, c->K = K;
+  c->n_sld_prev = 0;
   if (n_sld) WC_CUDA(c, cudaMemcpyAsync(c->d_sld, sld, n_sld * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
   if (n_fix) WC_CUDA(c, cudaMemcpyAsync(c->d_fix, fix, n_fix * sizeof(wc_surfel), cudaMemcpyHostToDevice, st));
   if (n_sld_corr) WC_CUDA(c, cudaMemcpyAsync(c->d_sld_corr, sld_corr, n_sld_corr * sizeof(wc_corr_idx), cudaMemcpyHostToDevice, st));
@@ -2113,9 +2116,11 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   // LM state): it is captured once per solve and replayed as a CUDA graph, which shortens the kernel-to-kernel gaps
   // (WC_LM_GRAPH=0 turns that off).
   static const int use_graph = getenv("WC_LM_GRAPH") ? atoi(getenv("WC_LM_GRAPH")) : 1;  // measured at C3: solve 2.54 -> 2.35 ms
-  cudaGraphExec_t  gexec = nullptr;
   static const int time_passes_g = getenv("WC_TIME_PASSES") ? atoi(getenv("WC_TIME_PASSES")) : 0;
+  cudaGraphExec_t  gexec = nullptr;
   if (use_graph && !dbg_ev && !time_passes_g && c->world == 1 && !use_wide) {
+    // capture (a few microseconds per launch), then update the executable graph kept from the previous solve in place:
+    // same topology, new kernel parameters — instantiating from scratch costs more than the gaps it saves
     cudaGraph_t g = nullptr;
     m->lin_timing_off = 1;
     WC_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -2124,8 +2129,17 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
     m->lin_timing_off = 0;
     if (s) return s;
     WC_CUDA(c, ce);
-    WC_CUDA(c, cudaGraphInstantiate(&gexec, g, 0));
+    if (m->gexec) {
+      cudaGraphExecUpdateResultInfo info;
+      if (cudaGraphExecUpdate(m->gexec, g, &info) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphExecDestroy(m->gexec);
+        m->gexec = nullptr;
+      }
+    }
+    if (!m->gexec) WC_CUDA(c, cudaGraphInstantiate(&m->gexec, g, 0));
     cudaGraphDestroy(g);
+    gexec = m->gexec;
   }
   for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
     if (gexec) WC_CUDA(c, cudaGraphLaunch(gexec, st));
@@ -2134,7 +2148,6 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
     WC_CUDA(c, cudaStreamSynchronize(st));
     done = m->h_st->done;
   }
-  if (gexec) cudaGraphExecDestroy(gexec);
   WC_CUDA(c, cudaMemcpyAsync(m->h_x, c->d_x, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaEventRecord(c->ev[5], st));
   WC_CUDA(c, cudaStreamSynchronize(st));

@@ -365,3 +365,53 @@ class ResidentPass:
         st = self.ctx.lib.wc_window_pass_resident(self.ctx.handle, C.byref(o), C.byref(summ), T.ptr(x), C.byref(stats))
         self.ctx.check(st, "wc_window_pass_resident")
         return x, summ, stats
+
+
+class ResidentWindows:
+    """surfels_sld_win_ / surfels_fix_win_ of LidarOdometry kept in HBM across sweeps (lidar_odometry.cc:527-528,228-250):
+    AddSweep appends the new sweep's surfels to the sliding window and runs steps 8-13 over the whole window, ShrinkToFit
+    moves the surfels that fell out of the sliding window to the front of the fixed window.  Only the new sweep, the IMU
+    states and the sample states cross PCIe; the sample / IMU deques themselves (a few KB) stay with the caller."""
+
+    WC_KEEP_SLD, WC_KEEP_FIX = 1, 2
+
+    def __init__(self, ctx=None, fix_body=None, sld_body=None):
+        self.ctx = ctx or default_context()
+        self._fix0 = np.ascontiguousarray(fix_body if fix_body is not None else np.zeros(0, T.SURFEL), dtype=T.SURFEL)
+        self._sld0 = np.ascontiguousarray(sld_body if sld_body is not None else np.zeros(0, T.SURFEL), dtype=T.SURFEL)
+        self._resident = False
+        self.n_sld, self.n_fix = len(self._sld0), len(self._fix0)
+
+    def AddSweep(self, cloud, imu, samples, opts=None):
+        lib, h = self.ctx.lib, self.ctx.handle
+        cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
+        imu = np.ascontiguousarray(imu, dtype=T.IMU)
+        samples = np.ascontiguousarray(samples, dtype=T.SAMPLE)
+        self.ctx.check(lib.wc_points_upload(h, T.ptr(cloud), len(cloud)), "wc_points_upload")
+        keep = (self.WC_KEEP_SLD | self.WC_KEEP_FIX) if self._resident else 0
+        st = lib.wc_pass_upload_windows(h, T.ptr(imu), len(imu), T.ptr(samples), len(samples), T.ptr(self._fix0), len(self._fix0),
+                                        T.ptr(self._sld0), len(self._sld0), keep)
+        self.ctx.check(st, "wc_pass_upload_windows")
+        self._resident = True
+        o = opts or T.default_solve_opts()
+        summ, stats = T.SolveSummary(), T.PassStats()
+        x = np.zeros((len(samples), 12))
+        self.ctx.check(lib.wc_window_pass_resident(h, C.byref(o), C.byref(summ), T.ptr(x), C.byref(stats)), "wc_window_pass_resident")
+        self.n_sld += int(stats.n_surfels)
+        return x, summ, stats
+
+    def ShrinkToFit(self, t_front_imu, fix_window_duration=20.0, trim_fixed=False):
+        ns, nf = C.c_size_t(0), C.c_size_t(0)
+        st = self.ctx.lib.wc_window_shrink(self.ctx.handle, C.c_double(t_front_imu), C.c_double(fix_window_duration), int(trim_fixed),
+                                           C.byref(ns), C.byref(nf))
+        self.ctx.check(st, "wc_window_shrink")
+        self.n_sld, self.n_fix = ns.value, nf.value
+        return self.n_sld, self.n_fix
+
+    def Fetch(self):
+        sld = np.zeros(max(1, self.n_sld), dtype=T.SURFEL)
+        fix = np.zeros(max(1, self.n_fix), dtype=T.SURFEL)
+        ns, nf = C.c_size_t(0), C.c_size_t(0)
+        st = self.ctx.lib.wc_windows_fetch(self.ctx.handle, T.ptr(sld), len(sld), C.byref(ns), T.ptr(fix), len(fix), C.byref(nf))
+        self.ctx.check(st, "wc_windows_fetch")
+        return sld[: ns.value], fix[: nf.value]
