@@ -385,6 +385,8 @@ wc_status wc_window_shrink(wc_ctx* ctx, double t_front_imu, double fix_window_du
                            size_t* n_fix);
 wc_status wc_windows_fetch(wc_ctx* ctx, wc_surfel* sld, size_t sld_cap, size_t* n_sld, wc_surfel* fix, size_t fix_cap,
                            size_t* n_fix);
+/* timing hook: `reps` peer-memory reductions of the packed normal equations of a K-pose window (multi-GPU ctx; collective) */
+wc_status wc_comm_bench(wc_ctx* ctx, size_t K, int reps, double* ms_per_call);
 /* number of CUDA kernels this ctx has launched since creation */
 int64_t   wc_launch_count(const wc_ctx* ctx);
 

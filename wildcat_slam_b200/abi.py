@@ -83,6 +83,7 @@ def load():
     lib.wc_comm_export.argtypes = [vp, vp]
     lib.wc_comm_connect.argtypes = [vp, i32, i32, vp]
     lib.wc_comm_disconnect.argtypes = [vp]
+    lib.wc_comm_bench.argtypes = [vp, sz, i32, P(dbl)]
     for name in declared_symbols():
         f = getattr(lib, name)  # raises AttributeError if the library lacks a declared entry point
         if name not in ("wc_abi_version", "wc_default_params", "wc_default_solve_opts", "wc_destroy", "wc_last_error",

@@ -315,3 +315,26 @@ wc_status wc_comm_check(wc_ctx* c) {
   }
   return WC_OK;
 }
+
+// Timing hook for the exchange step alone (tools/allreduce_compare.py puts it beside ncclAllReduce on the same buffer
+// size): `reps` reductions of the packed normal equations of a K-pose window, back to back on the ctx stream.  Every
+// rank must call it with the same arguments.
+wc_status wc_solve_exchange_reset(wc_ctx* c, size_t K);  // wc_solve.cu
+extern "C" wc_status wc_comm_bench(wc_ctx* c, size_t K, int reps, double* ms_per_call) {
+  if (!c || !ms_per_call || reps < 1) return WC_EINVAL;
+  if (c->world <= 1 || !c->comm_ready) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
+  wc_status s = wc_solve_exchange_reset(c, K);
+  if (s) return s;
+  if ((s = wc_comm_begin_solve(c))) return s;
+  for (int i = 0; i < 3; ++i)
+    if ((s = wc_comm_allreduce(c, 0))) return s;
+  WC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  for (int i = 0; i < reps; ++i)
+    if ((s = wc_comm_allreduce(c, 0))) return s;
+  WC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  WC_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  *ms_per_call = ms / reps;
+  return wc_comm_check(c);
+}

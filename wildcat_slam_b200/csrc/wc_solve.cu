@@ -2303,3 +2303,14 @@ extern "C" wc_status wc_surfel_markers(wc_ctx* c, const wc_surfel* surfels, size
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }
+
+// exchange-step timing hook (wc_comm_bench): a K-pose window with a cleared LM state (done = 0, cur = 0)
+wc_status wc_solve_exchange_reset(wc_ctx* c, size_t K) {
+  wc_status s = solve_alloc(c);
+  if (s) return s;
+  if (K < 2 || K > (size_t)c->prm.max_samples) WC_FAIL(c, WC_ECAPACITY, "K out of range");
+  wc_solve_mem* m = (wc_solve_mem*)c->d_lm;
+  c->K = K;
+  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), c->stream));
+  return WC_OK;
+}
