@@ -529,6 +529,7 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
   unsigned*      leafbin = skey + ECAP;                                // ECAP
   int*           sid     = reinterpret_cast<int*>(leafbin + ECAP);     // ECAP slot ids
   unsigned char* flag    = reinterpret_cast<unsigned char*>(sid + ECAP);  // ECAP: 1 group head, 2 node head, 4 cluster head
+  unsigned short* jobs   = reinterpret_cast<unsigned short*>(flag + ECAP);  // ECAP: cluster heads that need a plane fit
   double*        rec     = reinterpret_cast<double*>(smem_raw + ECAP * 16);  // STAGE: ECAP x REC doubles
   // entry e -> its record (shared memory when staged, else built from the slot in L2)
   auto get_rec = [&](int e, double* tmp) -> const double* {
@@ -541,7 +542,7 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
   __shared__ unsigned char l1_cut[8];  // layer-1 child analysed and not planar => its children exist
   __shared__ unsigned      bitmap[128];   // presence bits of the 64 x 64 (node, local bin) key space
   __shared__ unsigned      bprefix[128];
-  __shared__ int           s_bmin, s_bmax;
+  __shared__ int           s_bmin, s_bmax, s_njobs;
 
   const int nv = st->n_voxels;
   for (int v = blockIdx.x; v < nv; v += gridDim.x) {
@@ -730,9 +731,25 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
       for (int i = threadIdx.x; i < E; i += NT, ++trip)
         if ((my_starts >> trip) & 1ull) flag[i] |= 4;
       __syncthreads();
-      // one thread per cluster: accumulate, fit, test, emit
+      // One thread per cluster counts its points; the clusters that reach cluster_min_points (surfel_extraction.cc:33) become
+      // fit jobs.  The jobs are then taken by consecutive threads, so the eigen-solves of a voxel run on one or two full
+      // warps instead of a few lanes of every warp.
+      if (threadIdx.x == 0) s_njobs = 0;
+      __syncthreads();
       for (int i = threadIdx.x; i < E; i += NT) {
         if (!(flag[i] & 4)) continue;
+        double n = 0.0;
+        for (int j = i; j < E && (j == i || !(flag[j] & 6)); ++j) {
+          const int e = skey[j] & 16383u;
+          n += STAGE ? rec[e * REC] : (double)slots[sid[e]].n;
+        }
+        if (n < (double)P.cmin) continue;
+        jobs[atomicAdd(&s_njobs, 1)] = (unsigned short)i;
+      }
+      __syncthreads();
+      const int njobs = s_njobs;
+      for (int q = threadIdx.x; q < njobs; q += NT) {
+        const int      i   = jobs[q];
         const unsigned lk0 = skey[i] >> 14;
         Mom            m;
         mom_zero(m);
@@ -743,14 +760,19 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
           tA += r[10];
           tB += r[11];
         }
-        if (m.n < (double)P.cmin) continue;  // surfel_extraction.cc:33
         PlaneFit f;
         plane_fit(m, f);
-        if (f.ev[0] > P.thr || f.like < P.min_like) continue;  // :54
+        const bool accepted = !(f.ev[0] > P.thr || f.like < P.min_like);  // :54
+        // output slots: one counter bump per warp (the lanes of this trip that accepted their cluster)
+        const unsigned act = __activemask(), acc = __ballot_sync(act, accepted);
+        if (!accepted) continue;
+        const int leader = __ffs(acc) - 1, lane_id = threadIdx.x & 31;
+        int       idx    = 0;
+        if (lane_id == leader) idx = atomicAdd(&st->n_surfels, __popc(acc));
+        idx = __shfl_sync(acc, idx, leader) + __popc(acc & ((1u << lane_id) - 1u));
         const double cxw = ccx + f.mu[0], cyw = ccy + f.mu[1], czw = ccz + f.mu[2];
         V3           nrm = col(f.evec, 0);
         if (nrm.x * (cxw - P.view[0]) + nrm.y * (cyw - P.view[1]) + nrm.z * (czw - P.view[2]) < 0) nrm = -nrm;
-        const int idx = atomicAdd(&st->n_surfels, 1);
         if (idx >= P.surf_cap) {
           st->err_capacity = 1;
           continue;
