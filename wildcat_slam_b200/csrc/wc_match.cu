@@ -342,12 +342,59 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
       }
     };
     int  kphase    = 0;
-    auto scan_cell = [&](int p0, int p1) {
-      KSTAT(2 + kphase, p1 - p0);
+    // One cell per lane (c0 = first member row, cn = member count or 0, lb = lower bound of the 6-D distance from the
+    // query to anything in the cell): the cells are taken nearest first and their members are scanned as ONE flat index
+    // space, 32 per step, until the bound of the next cell exceeds the k-th best distance.
+    auto flat_scan = [&](int c0, int cn, double lb, const bool sorted) {
+        if (!__any_sync(0xffffffffu, cn > 0)) return;  // a round of misses
+        // Nearest cells first (32-lane bitonic sort on the box bound): the members of cells whose bound already exceeds the
+        // k-th best distance are never loaded — a wall query skips the floor surfels that share its cells, because their
+        // normals put the whole cell far away in feature space — and the scan stops at the first such cell.  Exact: a
+        // skipped cell cannot hold a better or tying candidate (same test as the far-cell phase below).
+        if (sorted) {
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1)
+#pragma unroll
+          for (int j = kk >> 1; j > 0; j >>= 1) {
+            const double ol = __shfl_xor_sync(0xffffffffu, lb, j);
+            const int    o0 = __shfl_xor_sync(0xffffffffu, c0, j), on = __shfl_xor_sync(0xffffffffu, cn, j);
+            const bool   up = (lane & kk) == 0, lower = (lane & j) == 0;
+            // ascending by (lb, c0): take the partner's entry when it belongs on this side
+            const bool o_less = ol < lb || (ol == lb && o0 < c0);
+            const bool differ = ol != lb || o0 != c0;
+            if (differ && ((lower == up) ? o_less : !o_less)) lb = ol, c0 = o0, cn = on;
+          }
+        }
+        int incl = cn;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl  = incl - cn;
 #pragma unroll 1
-      for (int base = p0; base < p1; base += 32) scan_batch(base + lane < p1 ? base + lane : -1);
+        for (int base = 0; base < total; base += 32) {
+          const int g  = base + lane;
+          int       lo = 0;  // last cell whose exclusive prefix is <= g
+#pragma unroll
+          for (int stp = 16; stp > 0; stp >>= 1) {
+            const int pv = __shfl_sync(0xffffffffu, excl, lo + stp);  // (lo + stp <= 31)
+            if (pv <= g) lo += stp;
+          }
+          const int    ce = __shfl_sync(0xffffffffu, excl, lo), cs = __shfl_sync(0xffffffffu, c0, lo);
+          const double cl = __shfl_sync(0xffffffffu, lb, lo);
+          // sorted: lane 0 holds the batch's nearest cell — if even that one is out of reach, so is everything after it
+          if (sorted && __shfl_sync(0xffffffffu, cl, 0) * (1.0 - 1e-12) > worst) break;
+          const bool take = g < total && !(cl * (1.0 - 1e-12) > worst);
+          if (!__any_sync(0xffffffffu, take)) continue;
+#ifdef WC_KNN_STATS
+          const int n_take = __popc(__ballot_sync(0xffffffffu, take));
+          KSTAT(2 + kphase, n_take);
+#endif
+          scan_batch(take ? cs + (g - ce) : -1);
+        }
     };
-
     const double    gx = f[0] * G.cs, gy = f[1] * G.cs, gz = f[2] * G.cs;  // grid coordinates of the query centre
     const double    cfx = floor(gx), cfy = floor(gy), cfz = floor(gz);
     const bool      rings_ok = fabs(cfx) < 1e6 && fabs(cfy) < 1e6 && fabs(cfz) < 1e6;
@@ -381,48 +428,7 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
             if (kk == WC_CELL_EMPTY) break;
           }
         }
-        if (!__any_sync(0xffffffffu, cn > 0)) return;  // a round of misses
-        // Nearest cells first (32-lane bitonic sort on the box bound): the members of cells whose bound already exceeds the
-        // k-th best distance are never loaded — a wall query skips the floor surfels that share its cells, because their
-        // normals put the whole cell far away in feature space — and the scan stops at the first such cell.  Exact: a
-        // skipped cell cannot hold a better or tying candidate (same test as the far-cell phase below).
-#pragma unroll
-        for (int kk = 2; kk <= 32; kk <<= 1)
-#pragma unroll
-          for (int j = kk >> 1; j > 0; j >>= 1) {
-            const double ol = __shfl_xor_sync(0xffffffffu, lb, j);
-            const int    o0 = __shfl_xor_sync(0xffffffffu, c0, j), on = __shfl_xor_sync(0xffffffffu, cn, j);
-            const bool   up = (lane & kk) == 0, lower = (lane & j) == 0;
-            // ascending by (lb, c0): take the partner's entry when it belongs on this side
-            const bool o_less = ol < lb || (ol == lb && o0 < c0);
-            const bool differ = ol != lb || o0 != c0;
-            if (differ && ((lower == up) ? o_less : !o_less)) lb = ol, c0 = o0, cn = on;
-          }
-        int incl = cn;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int excl  = incl - cn;
-#pragma unroll 1
-        for (int base = 0; base < total; base += 32) {
-          const int g  = base + lane;
-          int       lo = 0;  // last cell whose exclusive prefix is <= g
-#pragma unroll
-          for (int stp = 16; stp > 0; stp >>= 1) {
-            const int pv = __shfl_sync(0xffffffffu, excl, lo + stp);  // (lo + stp <= 31)
-            if (pv <= g) lo += stp;
-          }
-          const int    ce = __shfl_sync(0xffffffffu, excl, lo), cs = __shfl_sync(0xffffffffu, c0, lo);
-          const double cl = __shfl_sync(0xffffffffu, lb, lo);
-          // lane 0 holds the batch's nearest cell: if even that one is out of reach, so is everything after it
-          if (__shfl_sync(0xffffffffu, cl, 0) * (1.0 - 1e-12) > worst) break;
-          const bool take = g < total && !(cl * (1.0 - 1e-12) > worst);
-          KSTAT(2 + kphase, __popc(__ballot_sync(0xffffffffu, take)));
-          scan_batch(take ? cs + (g - ce) : -1);
-        }
+        flat_scan(c0, cn, lb, true);
       };
       // phase 0: the 3 x 3 x 3 block; lane 0 takes the query's own cell so that its members come first and tighten the
       // k-th distance early
@@ -459,12 +465,13 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
     if (!done) {
       KSTAT(1, 1);
       kphase = 1;
-      // phase 1: box-test the cells outside the scanned cube 32 at a time, scan the survivors one by one
+      // phase 1: box-test the cells outside the scanned cube 32 at a time; the survivors of a round are scanned together
+      // (nearest first, flat over their members — most cells of a sparse index hold a handful of surfels)
 #pragma unroll 1
       for (int cb = 0; cb < nc; cb += 32) {
         const int cell = cb + lane;
-        bool      take = false;
-        int       p0 = 0, p1 = 0;
+        int       p0 = 0, pn = 0;
+        double    lb = INFINITY;
         if (cell < nc) {
           bool visited = false;
           if (rings_ok) {
@@ -475,24 +482,23 @@ knn6_warp(const double* __restrict__ q, int qstr, int nq, int k, GridBufs G, int
           }
           if (!visited) {
             const double* bx = G.cbox + (size_t)cell * 12;
-            double        lb = 0.0;
+            double        l2 = 0.0;
 #pragma unroll
             for (int d = 0; d < 6; ++d) {
               const double ee = fmax(fmax(bx[d] - f[d], f[d] - bx[6 + d]), 0.0);
-              lb += ee * ee;
+              l2 += ee * ee;
             }
-            take = !(lb * (1.0 - 1e-12) > worst);  // skipped only if it cannot hold a better or tying candidate
-            p0 = G.off[cell], p1 = G.off[cell + 1];
+            if (!(l2 * (1.0 - 1e-12) > worst)) {  // skipped only if it cannot hold a better or tying candidate
+              lb = l2;
+              p0 = G.off[cell], pn = G.off[cell + 1] - p0;
+            }
           }
         }
-        unsigned m = __ballot_sync(0xffffffffu, take);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int q0 = __shfl_sync(0xffffffffu, p0, src), q1 = __shfl_sync(0xffffffffu, p1, src);
-          KSTAT(4, 1);
-          scan_cell(q0, q1);  // (the bound was tested against an older, larger k-th distance: still exact)
-        }
+#ifdef WC_KNN_STATS
+        const int n_cells_taken = __popc(__ballot_sync(0xffffffffu, pn > 0));
+        KSTAT(4, n_cells_taken);
+#endif
+        flat_scan(p0, pn, lb, false);  // (no ordering here: a sort per 32-cell round costs more than it prunes)
       }
     }
     if (lane < k) out_idx[(size_t)i * k + lane] = (my_i == 0x7fffffff) ? -1 : my_i, out_d2[(size_t)i * k + lane] = my_d;
