@@ -159,6 +159,7 @@ struct wc_ctx {
   void*            d_spline;  // wc_spline_mem
   int              n_imu_blocks, first_imu_block;
   int              lm_batch;  // LM iterations enqueued between host checks of the termination flag
+  int              last_lm_iters;  // iterations of the previous solve (how far to enqueue ahead)
 
   // ---- multi-GPU exchange
   int     rank, world;

@@ -518,8 +518,11 @@ __device__ void bitonic_sort_smem(unsigned* keys, int npad) {
 // One CTA per voxel whose entry count E lies in (E_LO, ECAP].
 // STAGE: the voxel's entry records are converted once and kept in shared memory (the per-node / per-cluster loops then
 // read ~30-cycle shared memory instead of chasing 128-byte slots through L2).
+#ifndef WC_EMIT_MINB
+#define WC_EMIT_MINB(NT) 1
+#endif
 template <int ECAP, int NT, bool STAGE>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, WC_EMIT_MINB(NT))
 cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg, const int* __restrict__ vox_off,
                  const unsigned long long* __restrict__ vox_key, wc_extract_status* __restrict__ st, EmitParams P, int e_lo,
                  wc_surfel* __restrict__ out, unsigned long long* __restrict__ sort_hi,
@@ -865,12 +868,14 @@ __global__ void __launch_bounds__(1024) bsort_scan(const int* __restrict__ bcnt,
   if (t == 1023) boff[SORT_NB] = run;
 }
 
-__global__ void bsort_scatter(const unsigned long long* __restrict__ hi, int n, double t_first, double bscale,
-                              const int* __restrict__ boff, int* __restrict__ bcur, unsigned* __restrict__ perm) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int b = sort_bucket(FromOrderedBits(hi[i]), t_first, bscale);
-  perm[boff[b] + atomicAdd(&bcur[b], 1)] = (unsigned)i;
+// (the surfel count is read on the device: the host does not wait for the emit kernels before enqueueing the sort)
+__global__ void bsort_scatter(const unsigned long long* __restrict__ hi, const wc_extract_status* __restrict__ st, int cap, double t_first,
+                              double bscale, const int* __restrict__ boff, int* __restrict__ bcur, unsigned* __restrict__ perm) {
+  const int n = min(st->n_surfels, cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = sort_bucket(FromOrderedBits(hi[i]), t_first, bscale);
+    perm[boff[b] + atomicAdd(&bcur[b], 1)] = (unsigned)i;
+  }
 }
 
 // one warp per bucket: out_idx[boff[b] + rank] = id, rank = number of bucket entries with a smaller exact key
@@ -903,13 +908,14 @@ bsort_rank(const unsigned long long* __restrict__ hi, const unsigned long long* 
   }
 }
 
-__global__ void gather_surfels(const wc_surfel* __restrict__ in, const unsigned* __restrict__ idx, int n,
-                               wc_surfel* __restrict__ out) {
+__global__ void gather_surfels(const wc_surfel* __restrict__ in, const unsigned* __restrict__ idx, const wc_extract_status* __restrict__ st,
+                               int cap, wc_surfel* __restrict__ out) {
   // 13 x 16-byte chunks per surfel; consecutive threads move consecutive chunks
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = t / 13, c = t % 13;
-  if (s >= n) return;
-  reinterpret_cast<uint4*>(out + s)[c] = reinterpret_cast<const uint4*>(in + idx[s])[c];
+  const long long n13 = 13ll * min(st->n_surfels, cap);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n13; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / 13), c = (int)(t % 13);
+    reinterpret_cast<uint4*>(out + s)[c] = reinterpret_cast<const uint4*>(in + idx[s])[c];
+  }
 }
 
 }  // namespace
@@ -1051,7 +1057,16 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   { ++c->n_launches; extract_cleanup<<<c->num_sms, 256, 0, st>>>(c->d_xstat, c->d_vkeys, c->d_vslot, c->d_vox_hpos, c->d_vox_count,
                                               c->d_vox_cursor); }
   WC_CUDA(c, cudaEventRecord(c->ev[2], st));
+  // final order by timestamp: enqueued without waiting for the surfel count (the kernels read it on the device), so the
+  // whole extraction has ONE host synchronisation
+  c->n_launches += 4;
+  bsort_scan<<<1, 1024, 0, st>>>(c->d_bcnt, c->d_boff, c->d_bcur);
+  bsort_scatter<<<c->num_sms * 2, 256, 0, st>>>(c->d_sort_hi, c->d_xstat, E.surf_cap, E.t_first, E.bscale, c->d_boff, c->d_bcur, c->d_sort_perm);
+  bsort_rank<<<SORT_NB / 8, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_boff, c->d_sort_perm, c->d_bcnt, c->d_sort_idx);
+  gather_surfels<<<c->num_sms * 8, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, c->d_xstat, E.surf_cap, c->d_surf);
+  WC_CUDA(c, cudaEventRecord(c->ev[3], st));
   WC_CUDA(c, cudaStreamSynchronize(st));
+  WC_CUDA(c, cudaGetLastError());
   const wc_extract_status hs = *c->h_xstat;
   if (hs.err_time_order) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "point timestamps are not non-decreasing");
   if (hs.err_range) WC_FAIL(c, WC_EINVAL, "sweep exceeds the key range (+-16384 voxels around the first point, 128 s)");
@@ -1059,16 +1074,6 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   const int S = hs.n_surfels;
   c->n_surfels = (size_t)S;
   c->last_slots = hs.n_slots, c->last_voxels = hs.n_voxels;
-  if (S > 0) {
-    c->n_launches += 4;
-    bsort_scan<<<1, 1024, 0, st>>>(c->d_bcnt, c->d_boff, c->d_bcur);
-    bsort_scatter<<<(S + 255) / 256, 256, 0, st>>>(c->d_sort_hi, S, E.t_first, E.bscale, c->d_boff, c->d_bcur, c->d_sort_perm);
-    bsort_rank<<<SORT_NB / 8, 256, 0, st>>>(c->d_sort_hi, c->d_sort_lo, c->d_boff, c->d_sort_perm, c->d_bcnt, c->d_sort_idx);
-    gather_surfels<<<(S * 13 + 255) / 256, 256, 0, st>>>(c->d_surf_raw, c->d_sort_idx, S, c->d_surf);
-  }
-  WC_CUDA(c, cudaEventRecord(c->ev[3], st));
-  WC_CUDA(c, cudaStreamSynchronize(st));
-  WC_CUDA(c, cudaGetLastError());
   float ms;
   if (gpu_ms_keys) { cudaEventElapsedTime(&ms, c->ev[4], c->ev[1]); *gpu_ms_keys = ms; }
   if (gpu_ms_emit) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[3]); *gpu_ms_emit = ms; }

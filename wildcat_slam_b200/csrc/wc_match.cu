@@ -731,27 +731,26 @@ wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_s
   WC_CUDA(c, cudaMemsetAsync(c->d_acc, 0xff, nq * 4, st));
   int* a = c->d_acc;
   int* b = c->d_acc2;
+  const unsigned gc = (unsigned)((nq + 1023) / 1024);
   for (int it = 0;; ++it) {
-    // acc <- F(acc) is a deterministic sweep; it has converged when a sweep reproduces its input.  Eight sweeps are
-    // enqueued before the first host check (the recurrence settles in a handful), the flag is cleared right before
-    // the last sweep of a batch so that it reports that sweep alone.
+    // acc <- F(acc) is a deterministic sweep; it has converged when a sweep reproduces its input.  Eight sweeps (the
+    // recurrence settles in a handful) AND the ordered compaction of their result are enqueued before the one host
+    // check; the flag is cleared right before the last sweep so that it reports that sweep alone.  In the rare case that
+    // the recurrence had not settled, more sweeps follow and the compaction is redone.
     const int sweeps = self_match ? 8 : 1;
     for (int s = 0; s < sweeps; ++s) {
       if (s == sweeps - 1) WC_CUDA(c, cudaMemsetAsync(c->d_flag, 0, 4, st));
       { ++c->n_launches; resolve_pairs<<<gq, 256, 0, st>>>(c->d_gated, (int)nq, k, self_match, a, b, c->d_flag); }
       int* tmp = a; a = b; b = tmp;
     }
-    if (!self_match) break;
-    WC_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, 4, cudaMemcpyDeviceToHost, st));
+    WC_CUDA(c, cudaMemsetAsync(c->d_flag + 3, 0, 4, st));
+    { ++c->n_launches; pair_count<<<gc, 1024, 0, st>>>(a, (int)nq, c->d_scan_tmp); }
+    { ++c->n_launches; pair_scatter<<<gc, 1024, 0, st>>>(a, (int)nq, c->d_scan_tmp, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
+    WC_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, 16, cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));
-    if (*c->h_flag == 0) break;
+    if (!self_match || c->h_flag[0] == 0) break;
     if (it > (int)nq) WC_FAIL(c, WC_ENUMERIC, "pair de-duplication did not converge");
   }
-  const unsigned gc = (unsigned)((nq + 1023) / 1024);
-  { ++c->n_launches; pair_count<<<gc, 1024, 0, st>>>(a, (int)nq, c->d_scan_tmp); }
-  { ++c->n_launches; pair_scatter<<<gc, 1024, 0, st>>>(a, (int)nq, c->d_scan_tmp, c->d_qfeat, tfeat, c->d_corr_out, c->d_fit_out, c->d_flag + 1); }
-  WC_CUDA(c, cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 12, cudaMemcpyDeviceToHost, st));
-  WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
   if (c->h_flag[2]) WC_FAIL(c, WC_EINVAL, "surfel centres outside the matcher grid range (+-1e6 cells) or non-finite");
   if (sharded) {

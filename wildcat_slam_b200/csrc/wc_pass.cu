@@ -7,10 +7,11 @@
 
 wc_status wc_window_upload_aux(wc_ctx* c, const wc_imu_state* imu, size_t n_imu, const wc_sample_state* samples, size_t K,
                                const wc_surfel* fix, size_t n_fix);
-wc_status wc_window_prepare_device(wc_ctx* c);
+wc_status wc_window_prepare_device(wc_ctx* c, int defer);
 wc_status wc_match_device(wc_ctx* c, const wc_surfel* d_q, size_t nq, const wc_surfel* d_t, size_t nt, int self_match,
                           size_t* n_out);
-wc_status wc_update_surfel_poses_device(wc_ctx* c, const wc_imu_state* d_imu, size_t n_imu, wc_surfel* d_surf, size_t n);
+wc_status wc_update_surfel_poses_device(wc_ctx* c, const wc_imu_state* d_imu, size_t n_imu, wc_surfel* d_surf, size_t n, int defer);
+wc_status wc_pose_update_check(wc_ctx* c);
 
 extern "C" wc_status wc_pass_upload(wc_ctx* c, const wc_imu_state* imu, size_t n_imu, const wc_sample_state* samples,
                                     size_t K, const wc_surfel* fix, size_t n_fix) {
@@ -63,11 +64,12 @@ extern "C" wc_status wc_window_pass_resident(wc_ctx* c, const wc_solve_opts* opt
   if (base + S > (size_t)c->prm.max_surfels) WC_FAIL(c, WC_ECAPACITY, "sliding window exceeds max_surfels");
   WC_CUDA(c, cudaMemcpyAsync(c->d_sld + base, c->d_surf, S * sizeof(wc_surfel), cudaMemcpyDeviceToDevice, st));
   const size_t W = base + S;
-  if ((s = wc_update_surfel_poses_device(c, c->d_imu, c->n_imu, c->d_sld, W))) return s;
+  if ((s = wc_update_surfel_poses_device(c, c->d_imu, c->n_imu, c->d_sld, W, /*defer=*/1))) return s;  // checked after the matcher's sync
   c->n_sld = W;
   // 9./10. sliding-window and fixed-window matchers
   size_t n_sc = 0, n_fc = 0;
   if ((s = wc_match_device(c, c->d_sld, W, c->d_sld, W, 1, &n_sc))) return s;
+  if ((s = wc_pose_update_check(c))) return s;
   if (n_sc > (size_t)c->prm.max_corrs) WC_FAIL(c, WC_ECAPACITY, "too many correspondences");
   if (n_sc) WC_CUDA(c, cudaMemcpyAsync(c->d_sld_corr, c->d_corr_out, n_sc * sizeof(wc_corr_idx), cudaMemcpyDeviceToDevice, st));
   if ((s = wc_match_device(c, c->d_sld, W, c->d_fix, c->n_fix, 0, &n_fc))) return s;
@@ -80,7 +82,7 @@ extern "C" wc_status wc_window_pass_resident(wc_ctx* c, const wc_solve_opts* opt
   ps.n_sld_corr = (int64_t)n_sc, ps.n_fix_corr = (int64_t)n_fc;
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
   // 11. problem assembly, 13. solve
-  if ((s = wc_window_prepare_device(c))) return s;
+  if ((s = wc_window_prepare_device(c, /*defer=*/1))) return s;  // pack errors surface at the solve's first host check
   WC_CUDA(c, cudaEventRecord(c->ev[1], st));
   wc_solve_summary local;
   s = wc_window_solve_resident(c, opts, summary ? summary : &local, data_cor_out);

@@ -109,7 +109,7 @@ struct PackArgs {
   int                stride;
   int*               bucket;  // per record
   int*               hist;
-  LMState*           st;
+  int*               err;   // pack errors (wc_status), separate from the LM state the solve re-initialises
 };
 
 __global__ void corr_pack(PackArgs a) {
@@ -119,12 +119,12 @@ __global__ void corr_pack(PackArgs a) {
   const wc_corr_idx ci   = unary ? a.fix_corr[i - a.n_sld_corr] : a.sld_corr[i];
   const int        n1    = unary ? a.n_fix : a.n_sld;
   if (ci.s1 < 0 || ci.s1 >= n1 || ci.s2 < 0 || ci.s2 >= a.n_sld) {
-    a.st->err = WC_EINVAL;
+    *a.err = WC_EINVAL;
     return;
   }
   const wc_surfel& s1 = unary ? a.fix[ci.s1] : a.sld[ci.s1];
   const wc_surfel& s2 = a.sld[ci.s2];
-  if (!(s1.timestamp < s2.timestamp)) a.st->err = WC_EINVAL_TIME_ORDER;  // CHECK_LT lidar_odometry.cc:256,301
+  if (!(s1.timestamp < s2.timestamp)) *a.err = WC_EINVAL_TIME_ORDER;  // CHECK_LT lidar_odometry.cc:256,301
   const Q4 q1 = ldq(s1.rot), q2 = ldq(s2.rot);
   const M3 R1 = ToMatrix(q1), R2 = ToMatrix(q2);
   // GetCovarianceInWorld (surfel.h:89-91) of both, summed; weight and direction (cost_functor.h:22-25,110-113)
@@ -151,7 +151,7 @@ __global__ void corr_pack(PackArgs a) {
     }
   }
   if (!ok) {
-    a.st->err = WC_EOUT_OF_SPAN;
+    *a.err = WC_EOUT_OF_SPAN;
     return;
   }
   const int    r  = i - a.c0;
@@ -1037,6 +1037,19 @@ __device__ __forceinline__ void chol_trailing_tiles(double* A, int LD, int Dp, i
 }
 
 #ifdef WC_LM_TIMING
+__device__ unsigned long long g_lm_stamps[512];
+__device__ int                g_lm_nstamp;
+__device__ __forceinline__ unsigned long long wc_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void lm_stamps_print() {
+  printf("lm_step start/end stamps (ns since the first):");
+  for (int i = 0; i < g_lm_nstamp && i < 512; ++i) printf(" %llu", g_lm_stamps[i] - g_lm_stamps[0]);
+  printf("\n");
+  g_lm_nstamp = 0;
+}
 #define WC_TICK() c0 = clock64()
 #define WC_TOCK(acc) acc += clock64() - c0
 #else
@@ -1166,6 +1179,9 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   const int t  = threadIdx.x;
   pdl_trigger();
   pdl_wait();
+#ifdef WC_LM_TIMING
+  if (t == 0) { const int k = atomicAdd(&g_lm_nstamp, 1); if (k < 512) g_lm_stamps[k] = wc_globaltimer(); }
+#endif
   for (int k = t; k < (int)(sizeof(LMState) / 8); k += LMT)
     reinterpret_cast<unsigned long long*>(&sst)[k] = reinterpret_cast<const unsigned long long*>(B.st)[k];
   __syncthreads();
@@ -1352,6 +1368,10 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
 #endif
   }
   write_back();
+#ifdef WC_LM_TIMING
+  __syncthreads();
+  if (t == 0) { const int k = atomicAdd(&g_lm_nstamp, 1); if (k < 512) g_lm_stamps[k] = wc_globaltimer(); }
+#endif
 }
 
 
@@ -1798,6 +1818,8 @@ struct wc_solve_mem {
   LMState* st;
   LMState* h_st;
   double*  h_x;
+  int*     d_perr;  // pack error word
+  int*     h_perr;  // pinned
   double   grav[3];
   wc_surfel*  mk_in;      // surfel staging of wc_surfel_markers (grown on demand)
   size_t      mk_cap;
@@ -1855,6 +1877,9 @@ static wc_status solve_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&m->st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_st, sizeof(LMState)));
   WC_CUDA(c, cudaMallocHost(&m->h_x, N * 8));
+  WC_CUDA(c, cudaMalloc(&m->d_perr, 16));
+  WC_CUDA(c, cudaMallocHost(&m->h_perr, 16));
+  m->h_perr[0] = 0;
   WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_F64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM));
   WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_MIXED, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_R32));
   WC_CUDA(c, cudaFuncSetAttribute((window_linearize<WC_PREC_F32, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_R32));
@@ -1881,6 +1906,8 @@ void wc_solve_free(wc_ctx* c) {
     if (p) cudaFree(p);
   if (m->h_st) cudaFreeHost(m->h_st);
   if (m->h_x) cudaFreeHost(m->h_x);
+  if (m->h_perr) cudaFreeHost(m->h_perr);
+  if (m->d_perr) cudaFree(m->d_perr);
   free(m);
   c->d_lm = nullptr;
 }
@@ -1897,7 +1924,15 @@ static SolveBufs make_bufs(wc_ctx* c, int fix_first) {
 // Device-side window preparation: sample timestamps / start point, factor construction for this rank's slice of the
 // correspondence list, bucketing by interval pair.  Expects d_sld/d_fix/d_sld_corr/d_fix_corr/d_imu/d_samples and the
 // counts in the ctx.
-wc_status wc_window_prepare_device(wc_ctx* c) {
+static wc_status pack_error(wc_ctx* c, int e) {
+  if (e == WC_EINVAL) WC_FAIL(c, WC_EINVAL, "correspondence index out of range");
+  if (e == WC_EINVAL_TIME_ORDER) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "correspondence with timestamp(s1) >= timestamp(s2)");
+  if (e == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the sample-state span");
+  return WC_OK;
+}
+
+// defer != 0: no host synchronisation; the error word is read back by the solve's first host check
+wc_status wc_window_prepare_device(wc_ctx* c, int defer) {
   wc_solve_mem* m  = (wc_solve_mem*)c->d_lm;
   cudaStream_t  st = c->stream;
   const size_t  K = c->K, n_sld = c->n_sld, n_fix = c->n_fix, n_sld_corr = c->n_sld_corr, n_fix_corr = c->n_fix_corr;
@@ -1909,7 +1944,7 @@ wc_status wc_window_prepare_device(wc_ctx* c) {
   c->n_rec     = (size_t)(c1 - c0);
   m->rec32_valid = 0;
   const int nb = (int)(K * K);
-  WC_CUDA(c, cudaMemsetAsync(m->st, 0, sizeof(LMState), st));
+  WC_CUDA(c, cudaMemsetAsync(m->d_perr, 0, 16, st));
   WC_CUDA(c, cudaMemsetAsync(m->hist, 0, (size_t)nb * 4, st));
   WC_CUDA(c, cudaMemsetAsync(m->cursor, 0, (size_t)nb * 4, st));
   if (c->n_rec) {
@@ -1917,19 +1952,17 @@ wc_status wc_window_prepare_device(wc_ctx* c) {
     a.sld = c->d_sld, a.fix = c->d_fix, a.sld_corr = c->d_sld_corr, a.fix_corr = c->d_fix_corr;
     a.n_sld = (int)n_sld, a.n_fix = (int)n_fix, a.n_sld_corr = (int)n_sld_corr, a.n_fix_corr = (int)n_fix_corr;
     a.c0 = c0, a.c1 = c1, a.ts = m->ts, a.K = (int)K, a.weight_floor = c->prm.weight_floor;
-    a.tmp = m->tmp, a.stride = m->stride, a.bucket = m->bucket, a.hist = m->hist, a.st = m->st;
+    a.tmp = m->tmp, a.stride = m->stride, a.bucket = m->bucket, a.hist = m->hist, a.err = m->d_perr;
     const unsigned grid = (unsigned)((c->n_rec + 255) / 256);
     { ++c->n_launches; corr_pack<<<grid, 256, 0, st>>>(a); }
     { ++c->n_launches; bucket_scan<<<1, 1024, 0, st>>>(m->hist, nb, m->off); }
     { ++c->n_launches; bucket_scatter<<<grid, 256, 0, st>>>(m->tmp, m->bucket, (int)c->n_rec, m->stride, m->off, m->cursor, m->rec); }
   }
-  WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
+  WC_CUDA(c, cudaMemcpyAsync(m->h_perr, m->d_perr, 4, cudaMemcpyDeviceToHost, st));
+  if (defer) return WC_OK;
   WC_CUDA(c, cudaStreamSynchronize(st));
   WC_CUDA(c, cudaGetLastError());
-  if (m->h_st->err == WC_EINVAL) WC_FAIL(c, WC_EINVAL, "correspondence index out of range");
-  if (m->h_st->err == WC_EINVAL_TIME_ORDER) WC_FAIL(c, WC_EINVAL_TIME_ORDER, "correspondence with timestamp(s1) >= timestamp(s2)");
-  if (m->h_st->err == WC_EOUT_OF_SPAN) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the sample-state span");
-  return WC_OK;
+  return pack_error(c, m->h_perr[0]);
 }
 
 extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_sld, const wc_surfel* fix, size_t n_fix,
@@ -1962,7 +1995,7 @@ extern "C" wc_status wc_window_upload(wc_ctx* c, const wc_surfel* sld, size_t n_
       if (c->n_imu_blocks == 0) c->first_imu_block = (int)i;
       ++c->n_imu_blocks;
     }
-  return wc_window_prepare_device(c);
+  return wc_window_prepare_device(c, 0);
 }
 
 // Upload of everything a device-resident window pass needs besides the sweep itself: IMU states, sample states and
@@ -2172,16 +2205,30 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
     cudaGraphDestroy(g);
     gexec = m->gexec;
   }
-  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch; it += batch) {
-    if (gexec) WC_CUDA(c, cudaGraphLaunch(gexec, st));
-    else if ((s = enqueue_batch())) return s;
+  // Consecutive windows take about the same number of iterations: that many batches are enqueued before the first host
+  // check of the termination flag (iterations enqueued after the solver terminated return at once).
+  int ahead = (c->last_lm_iters + 1 + batch - 1) / batch;
+  if (ahead < 1) ahead = 1;
+  if (ahead > 8) ahead = 8;
+  for (int done = 0, it = 0; !done && it <= o.max_num_iterations + 2 * batch;) {
+    for (int r = 0; r < ahead; ++r, it += batch) {
+      if (gexec) WC_CUDA(c, cudaGraphLaunch(gexec, st));
+      else if ((s = enqueue_batch())) return s;
+    }
+    ahead = 1;
     WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));
+    if ((s = pack_error(c, m->h_perr[0]))) return s;
     done = m->h_st->done;
   }
+  c->last_lm_iters = m->h_st->iteration;
   WC_CUDA(c, cudaMemcpyAsync(m->h_x, c->d_x, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
   WC_CUDA(c, cudaEventRecord(c->ev[5], st));
   WC_CUDA(c, cudaStreamSynchronize(st));
+#ifdef WC_LM_TIMING
+  lm_stamps_print<<<1, 1, 0, st>>>();
+  cudaStreamSynchronize(st);
+#endif
   if (dbg_ev) {
     printf("LM timeline (us between consecutive events: step, linearize, step, ...):");
     for (int i = 0; i + 1 < n_ev; ++i) { float ms; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); printf(" %.1f", ms * 1e3f); }

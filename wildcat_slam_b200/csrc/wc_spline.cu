@@ -341,16 +341,24 @@ extern "C" wc_status wc_update_surfel_poses(wc_ctx* c, const wc_imu_state* imu, 
 }
 
 // device-resident variant for the fused window pass (surfels already on the device)
-wc_status wc_update_surfel_poses_device(wc_ctx* c, const wc_imu_state* d_imu, size_t n_imu, wc_surfel* d_surf, size_t n) {
+// defer != 0: no host synchronisation here — the caller checks wc_pose_update_check() after its next one
+wc_status wc_update_surfel_poses_device(wc_ctx* c, const wc_imu_state* d_imu, size_t n_imu, wc_surfel* d_surf, size_t n, int defer) {
   wc_status s = spline_alloc(c, 0);
   if (s) return s;
   wc_spline_mem* m = (wc_spline_mem*)c->d_spline;
+  m->h_flags[2]    = 0;
   if (n == 0) return WC_OK;
   WC_CUDA(c, cudaMemsetAsync(m->flags, 0, 16, c->stream));
   { ++c->n_launches; update_surfel_poses<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_imu, (int)n_imu, d_surf, (int)n, m->flags + 2); }
   WC_CUDA(c, cudaMemcpyAsync(m->h_flags, m->flags, 16, cudaMemcpyDeviceToHost, c->stream));
+  if (defer) return WC_OK;
   WC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (m->h_flags[2]) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the IMU state span (lidar_odometry.cc:164)");
+  return WC_OK;
+}
+wc_status wc_pose_update_check(wc_ctx* c) {  // after a host synchronisation that followed a deferred pose update
+  wc_spline_mem* m = (wc_spline_mem*)c->d_spline;
+  if (m && m->h_flags[2]) WC_FAIL(c, WC_EOUT_OF_SPAN, "surfel timestamp outside the IMU state span (lidar_odometry.cc:164)");
   return WC_OK;
 }
 
