@@ -60,7 +60,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
+    def wait_first_sample(self, timeout=3.0):
+        """nvidia-smi needs 0.1 - 1 s for its first line (longer on an 8-GPU box): do not start the timed region before"""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def mark_begin(self):
+        self.wait_first_sample()
         self.t0 = time.perf_counter()
 
     def mark_end(self):
