@@ -21,18 +21,15 @@ def axis_cell(x, vsf):
     magic = F(12582912.0)
     y = (x * inv_v4).astype(F)
     gm = (y + magic).astype(F)
-    g = gm.view(np.int32) - np.int32(0x4B400000)
+    g0 = gm.view(np.int32) - np.int32(0x4B400000)
     gf = (gm - magic).astype(F)
     r0 = fma32(-gf, np.full_like(x, v4), x)
-    neg = r0 < 0
-    g = g - neg.astype(np.int32)
-    gf = np.where(neg, gf - F(1), gf).astype(F)
-    r = fma32(-gf, np.full_like(x, v4), x)
-    gl = g & 3
-    face = (r == 0) & (gl != 0)
+    dec = (r0 < 0) | ((r0 == 0) & ((g0 & 3) != 0))  # below the rounded cell, or on a face inside the voxel
+    g = g0 - dec.astype(np.int32)                    # leaf-cell index along the axis = 4 voxel + child
+    gf = np.where(dec, gf - F(1), gf).astype(F)
     q = g >> 2
-    f = gl - face.astype(np.int32)
-    gc = (np.where(face, gf - F(1), gf).astype(F) * F(2) + F(1)).astype(F)
+    f = g & 3
+    gc = (gf * F(2) + F(1)).astype(F)
     rel = np.rint(fma32(-gc, np.full_like(x, v8), x).astype(np.float64) * SCALE).astype(np.int64)
     return q, f, rel
 

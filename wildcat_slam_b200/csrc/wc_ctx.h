@@ -21,18 +21,24 @@
 #define WC_VOX_BIAS 16384 /* voxel coordinates relative to the first point's voxel, 15 bits per axis */
 #define WC_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 
-struct __align__(16) wc_slot {
-  unsigned long long key;     // [vx:15][vy:15][vz:15][leaf:6][bin:12]
-  long long          n;
-  long long          st;      // sum of (Q - bin<<31)
-  long long          s[3];    // sum rel
-  long long          ss[6];   // xx xy xz yy yz zz
-  unsigned long long tmin_inv;  // max of ~OrderedBits(t)  (zero-initialised)
-  unsigned long long tmax;      // max of  OrderedBits(t)
-  int                table_pos;
-  int                vid;
-};  // 128 bytes
-static_assert(sizeof(wc_slot) == 128, "slot layout");
+// Run / cell records ("slots") live in four planes, so that a warp whose lanes hold consecutive slots writes whole
+// 32-byte sectors side by side (a 128-byte array-of-structures record per lane costs one memory transaction per lane
+// and per 16 bytes: measured 38 of 80 us in K1) and so that the cell merge reads the keys as one dense array:
+//   key[s]                    [vx:15][vy:15][vz:15][leaf:6][bin:12]
+//   p0[s] = {n, imin, imax, 0 | st, s[0]}        n points; first / last point of the cell (indices into the sweep:
+//                                                timestamps are non-decreasing in the index, so these are its earliest /
+//                                                latest point; the emit stage reads their exact fp64 times);
+//                                                st = sum of (Q - bin<<31); s = sum rel
+//   p1[s] = {s[1], s[2] | ss[0], ss[1]}          ss = xx xy xz yy yz zz
+//   p2[s] = {ss[2], ss[3] | ss[4], ss[5]}
+// 104 bytes per slot.
+struct wc_slot_planes {
+  unsigned long long* key;
+  int4*               p0;  // two int4 per slot in each body plane
+  int4*               p1;
+  int4*               p2;
+};
+#define WC_SLOT_BYTES 104
 
 struct wc_extract_status {
   int      err_time_order;
@@ -81,14 +87,15 @@ struct wc_ctx {
   size_t              n_pts;
   void*               d_htab;     // cell hash: 16-byte {key, published slot id} entries
   size_t              hcap;
-  wc_slot*            d_slots;
+  void*               d_slots;      // slot planes (wc_slot_planes over one allocation)
   size_t              slot_cap;
   unsigned long long* d_vkeys;    // voxel hash
   int*                d_vslot;
   size_t              vcap;
   int*                d_vox_count;  // per voxel: number of slots
   int*                d_vox_off;
-  int*                d_vox_cursor;
+  int2*               d_rec_info;   // per run record: {voxel id or -1 (merged away), rank among the voxel's slots}
+  int*                d_rec_tpos;   // per run record: the cell-table entry it claimed, or -1
   unsigned long long* d_vox_key;
   int*                d_vox_hpos;   // voxel-table position of each voxel (for cleanup)
   int*                d_seg;        // slot ids grouped by voxel

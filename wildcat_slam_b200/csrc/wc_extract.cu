@@ -16,6 +16,7 @@
 // subtraction on the same two operands the reference performs, because those two points are consecutive in the
 // node's time-ordered list.
 #include <math.h>
+#include <stdlib.h>
 
 #include "wc_ctx.h"
 #include "wc_device_math.cuh"
@@ -37,34 +38,35 @@ struct ExtractParams {
   double t_first;
   float  v4, inv_v4, v8;  // leaf-cell width voxel/4 (exact in float32), its rounded reciprocal, half width voxel/8
   int    vox0[3];
+  int    goffm[3];        // 4 (WC_VOX_BIAS - vox0) - 0x4B400000: leaf-cell index bias of the tile keys, minus the magic exponent
   int    n;
+  int    dbg;
 };
 
 // axis_cell: x float32, v4 = voxel/4 (exact in float32).  y = RN(x * RN(1/v4)) is within 2^-6 of x / v4 (|x / v4| < 2^22),
 // so g0 = round-to-nearest(y) (magic-number add) is floor(x / v4) or floor + 1.  r0 = fma(-g0, v4, x) is the CORRECTLY
-// ROUNDED value of x - g0 v4: its sign is exact, hence g = g0 - [r0 < 0] is exactly floor(x / v4), and r = fma(-g, v4, x)
-// is zero iff x lies exactly on a cell face.  The reference (surfel_extraction.h:59-64, .cc:148-166,209-211) evaluates
+// ROUNDED value of x - g0 v4: its sign is exact (and it is zero iff x lies exactly on the cell face g0 v4), hence
+// g = g0 - [r0 < 0] is exactly floor(x / v4).  The reference (surfel_extraction.h:59-64, .cc:148-166,209-211) evaluates
 // floor(x / v), (0.5 + k) v, c +- v/4, c +- v/8 in double; all of these are exact there (products of a <= 22-bit integer
-// and the 24-bit v), so its cell decisions are the exact ones too: voxel = g >> 2, child index along the axis
-// f = g & 3 — except ON a face (r == 0), where the strict '>' sends the point to the lower cell unless that would leave
-// the voxel.  The fixed-point offset from the leaf centre (2 g' + 1) v8 is one more fused multiply-add: exact whenever
-// |x| >= 2^-4 m (the offset is then a multiple of 2^-27 below 2^-3), rounded by at most 0.75 * 2^-27 m closer to the axis.
-// tests/test_voxel_floor.py checks all of this against the reference's double-precision formulas.
-__device__ __forceinline__ bool axis_cell(float x, const ExtractParams& P, int& q, int& f, int& rel) {
+// and the 24-bit v), so its cell decisions are the exact ones too: voxel = g >> 2, child index along the axis g & 3 —
+// except ON a face (r0 == 0), where the strict '>' sends the point to the lower cell unless that would leave the voxel
+// (g0 & 3 == 0).  Both corrections are the same decrement, so the leaf-cell index along the axis is
+// g' = g0 - [r0 < 0 or (r0 == 0 and g0 & 3 != 0)] = 4 voxel + child.  The fixed-point offset from the leaf centre
+// (2 g' + 1) v8 is one more fused multiply-add: exact whenever |x| >= 2^-4 m (the offset is then a multiple of 2^-27
+// below 2^-3), rounded by at most 0.75 * 2^-27 m closer to the axis otherwise.  tests/test_voxel_floor.py checks all of
+// this against the reference's double-precision formulas.  Returns g' + bias in `a`.
+__device__ __forceinline__ bool axis_cell(float x, const ExtractParams& P, int goffm, int& a, int& rel) {
   const float MAGIC = 12582912.f;  // 1.5 * 2^23
   const float y     = __fmul_rn(x, P.inv_v4);
   const float gm    = __fadd_rn(y, MAGIC);
-  int         g     = __float_as_int(gm) - 0x4B400000;
   float       gf    = __fadd_rn(gm, -MAGIC);
   const float r0    = __fmaf_rn(-gf, P.v4, x);
-  if (r0 < 0.f) g -= 1, gf = __fadd_rn(gf, -1.f);
-  const float r    = __fmaf_rn(-gf, P.v4, x);
-  const int   gl   = g & 3;
-  const bool  face = (r == 0.f) && gl != 0;
-  q                = g >> 2;
-  f                = gl - (face ? 1 : 0);
-  const float gc   = __fmaf_rn(face ? __fadd_rn(gf, -1.f) : gf, 2.f, 1.f);  // 2 g' + 1: exact
-  rel              = __float2int_rn(__fmul_rn(__fmaf_rn(-gc, P.v8, x), (float)WC_COORD_SCALE));
+  const int   a0    = __float_as_int(gm) + goffm;  // g0 + bias (bias and exponent are multiples of 4: a0 & 3 == g0 & 3)
+  const bool  dec   = (r0 < 0.f) || (r0 == 0.f && (a0 & 3) != 0);
+  a                 = a0;
+  if (dec) a = a0 - 1, gf = __fadd_rn(gf, -1.f);
+  const float gc = __fmaf_rn(gf, 2.f, 1.f);  // 2 g' + 1: exact
+  rel            = __float2int_rn(__fmul_rn(__fmaf_rn(-gc, P.v8, x), (float)WC_COORD_SCALE));
   return fabsf(y) < 4.0e6f;  // also false for NaN / Inf
 }
 
@@ -88,179 +90,170 @@ struct __align__(16) HEnt {
   int                pad;
 };
 
-// Tile kernel: a CTA takes KT consecutive points, computes their cell keys, and groups equal keys with a shared-memory
-// hash table + counting sort (O(points), no comparison sort).  One thread per distinct key then sums that key's points in
-// exact 64-bit fixed point and writes ONE 128-byte run record with plain stores (the tile's records are contiguous: one
-// counter bump per tile reserves them).  No global atomics, fences or dependent probes here: a cell that straddles a
-// tile boundary simply yields two records, which voxel_index merges through the global cell table afterwards.  A
-// spinning lidar revisits a 0.2 m cell with a handful of adjacent rings x azimuth columns, all inside one tile, so the
-// record traffic per point drops by the run length (4-6x at C3).
-constexpr int KT = 2048, KNT = 512, KPT = KT / KNT, KTAB = 4096;
-constexpr int K1_SMEM = KTAB * 8 + KT * 16 + (KTAB / 2) * 4 + KTAB * 2 + KT * 2 + KT * 2;
+// Tile kernel: a CTA takes KT consecutive points.  Each point computes its cell key (leaf-cell index per axis + time
+// bin) and its exact fixed-point payload, finds the key's position in a shared-memory hash table (one 64-bit CAS for the
+// first point of a key) and pushes itself onto that position's list with ONE native 32-bit exchange; the payload, with
+// the link to the previous list head packed into its spare bits, goes to shared memory.  The first point of a key also
+// appends the position to the tile's compact run list.  After one barrier a thread per run walks its list, sums the
+// points in exact 64-bit integers (order-independent, so the records are bitwise reproducible whatever order the
+// exchanges happened in) and writes ONE 128-byte run record with plain stores (the tile's records are contiguous: one
+// counter bump per tile reserves them).  No counting sort, no scan, no global atomics, fences or dependent global probes
+// here: a cell that straddles a tile boundary simply yields two records, which voxel_index merges through the global
+// cell table afterwards.  A spinning lidar revisits a 0.2 m cell with a handful of adjacent rings x azimuth columns, all
+// inside one tile, so the record traffic per point drops by the run length (4-6x at C3).
+// 72 KB of shared memory and <= 40 registers: three CTAs (48 warps) per SM, so the key phase of one tile overlaps the
+// list walks of another.
+constexpr int KT = 2048, KNT = 512, KPT = KT / KNT, KTAB = 2816;
+constexpr unsigned K_END = 0xFFFFu;  // list terminator (links are point ids x 16 = byte offsets into pay[], < 2^15)
+constexpr int K1_OFF_HEAD = KTAB * 8, K1_OFF_PAY = KTAB * 12, K1_OFF_NXT = K1_OFF_PAY + KT * 16, K1_OFF_RUN = K1_OFF_NXT + KT * 2;
+constexpr int K1_SMEM = K1_OFF_RUN + KT * 2;
+static_assert(K1_OFF_PAY % 16 == 0, "table region is cleared with 16-byte stores");
 
-__global__ void __launch_bounds__(KNT, 2)
-voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ time, ExtractParams P, wc_slot* __restrict__ slots,
+__global__ void __launch_bounds__(KNT, 3)
+voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ time, ExtractParams P, wc_slot_planes slots,
                   int slot_cap, wc_extract_status* __restrict__ st, wc_point_assign* __restrict__ assign) {
   extern __shared__ __align__(16) unsigned char k1_smem[];
-  unsigned long long* skey = reinterpret_cast<unsigned long long*>(k1_smem);           // KTAB keys
-  int4*               pay  = reinterpret_cast<int4*>(k1_smem + KTAB * 8);               // KT payloads (xi, yi, zi, qrel)
-  unsigned*           cnt2 = reinterpret_cast<unsigned*>(k1_smem + KTAB * 8 + KT * 16);  // KTAB packed 16-bit counters
-  unsigned short*     off  = reinterpret_cast<unsigned short*>(cnt2 + KTAB / 2);        // KTAB exclusive offsets
-  unsigned short*     runh = off + KTAB;                                                // table position of each run
-  unsigned short*     perm = runh + KT;                                                 // point ids grouped by run
-  __shared__ int      wsum[KNT / 32];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(k1_smem);           // KTAB keys (all-ones = empty)
+  unsigned*           head = reinterpret_cast<unsigned*>(k1_smem + K1_OFF_HEAD);        // KTAB list heads (all-ones = none)
+  unsigned char*      payb = k1_smem + K1_OFF_PAY;                                      // KT payloads int4 (x, y, z, t)
+  unsigned char*      nxtb = k1_smem + K1_OFF_NXT;                                      // KT links, u16
+  unsigned short*     runh = reinterpret_cast<unsigned short*>(k1_smem + K1_OFF_RUN);   // table position of each run
   __shared__ int      s_nruns, s_base;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x;
   const int base = blockIdx.x * KT;
 
-  for (int k = t; k < KTAB; k += KNT) skey[k] = WC_KEY_EMPTY;
-  for (int k = t; k < KTAB / 2; k += KNT) cnt2[k] = 0u;
+  for (int k = t; k < K1_OFF_PAY / 16; k += KNT) reinterpret_cast<int4*>(k1_smem)[k] = make_int4(-1, -1, -1, -1);
+  if (t == 0) s_nruns = 0;
+  // the tile's points: all loads first, so that they are in flight together
+  float4 p[KPT];
+  double tt[KPT], tp[KPT];
+#pragma unroll
+  for (int u = 0; u < KPT; ++u) {
+    const int i = base + t + KNT * u;
+    if (i < P.n) {
+      p[u]  = xyz[i];
+      tt[u] = time[i];
+      tp[u] = i > 0 ? time[i - 1] : tt[u];
+    }
+  }
   __syncthreads();
+  if (P.dbg == 1) {
+    if (p[0].x + p[1].x + p[2].x + p[3].x + (float)(tt[0] + tt[1] + tt[2] + tt[3] + tp[0] + tp[1] + tp[2] + tp[3]) == 1.2345f) st->err_range = 1;
+    return;
+  }
 
-  // ---- keys and exact fixed-point payload: straight-line code over the thread's KPT points, so the loads and the
-  //      dependent fp64 chains of the points interleave (the shared-memory inserts, with their CAS loops, come after)
-  unsigned long long key[KPT];
 #pragma unroll
   for (int u = 0; u < KPT; ++u) {
     const int l = t + KNT * u, i = base + l;
-    key[u] = WC_KEY_EMPTY;
-    if (i < P.n) {
-      const float4 p  = xyz[i];
-      const double tt = time[i];
-      if (i > 0 && tt < time[i - 1]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
-      // VoxelLoc (surfel_extraction.h:59-64), the two child descents (.cc:148-166) and the exact fixed-point offset
-      // from the leaf-cell centre, in float32 / integer arithmetic (axis_cell)
-      int  vx, vy, vz, fx, fy, fz;
-      int4 q;
-      bool ok = axis_cell(p.x, P, vx, fx, q.x);
-      ok      = axis_cell(p.y, P, vy, fy, q.y) && ok;
-      ok      = axis_cell(p.z, P, vz, fz, q.z) && ok;
+    if (i >= P.n) continue;
+    if (tt[u] < tp[u]) st->err_time_order = 1;  // CHECK lidar_odometry.cc:491
+    // VoxelLoc (surfel_extraction.h:59-64), the two child descents (.cc:148-166) and the exact fixed-point offset
+    // from the leaf-cell centre, in float32 / integer arithmetic (axis_cell)
+    int  ax, ay, az;
+    int4 q;
+    bool ok = axis_cell(p[u].x, P, P.goffm[0], ax, q.x);
+    ok      = axis_cell(p[u].y, P, P.goffm[1], ay, q.y) && ok;
+    ok      = axis_cell(p[u].z, P, P.goffm[2], az, q.z) && ok;
+    if (assign) {
+      const int fx = ax & 3, fy = ay & 3, fz = az & 3;
       const int leaf = ((fx >> 1) << 5) | ((fy >> 1) << 4) | ((fz >> 1) << 3) | ((fx & 1) << 2) | ((fy & 1) << 1) | (fz & 1);
-      if (assign) assign[i] = wc_point_assign{vx, vy, vz, leaf};
-      const long long Q   = __double2ll_rn((tt - P.t_first) * WC_TIME_SCALE);
-      const long long bin = Q >> WC_BIN_SHIFT;
-      q.w                 = (int)(Q - (bin << WC_BIN_SHIFT));
-      pay[l]              = q;
-      const int rx = vx - P.vox0[0] + WC_VOX_BIAS, ry = vy - P.vox0[1] + WC_VOX_BIAS, rz = vz - P.vox0[2] + WC_VOX_BIAS;
-      if (!ok || (unsigned)rx >= 2u * WC_VOX_BIAS || (unsigned)ry >= 2u * WC_VOX_BIAS || (unsigned)rz >= 2u * WC_VOX_BIAS ||
-          Q < 0 || bin >= WC_MAX_BINS)
-        st->err_range = 1;
-      else
-        key[u] = ((unsigned long long)rx << 48) | ((unsigned long long)ry << 33) | ((unsigned long long)rz << 18) |
-                 ((unsigned long long)leaf << 12) | (unsigned long long)bin;
+      assign[i] = wc_point_assign{(ax >> 2) - WC_VOX_BIAS + P.vox0[0], (ay >> 2) - WC_VOX_BIAS + P.vox0[1],
+                                  (az >> 2) - WC_VOX_BIAS + P.vox0[2], leaf};
     }
-  }
-  // ---- shared-memory insert + rank of the point inside its key group
-  int hpos[KPT], rank[KPT];
-#pragma unroll
-  for (int u = 0; u < KPT; ++u) {
-    hpos[u] = -1, rank[u] = 0;
-    if (key[u] == WC_KEY_EMPTY) continue;
-    unsigned h = ((unsigned)key[u] * 0x9E3779B1u) ^ ((unsigned)(key[u] >> 32) * 0x85EBCA77u);  // tile-local table: a cheap mix
-    h          = ((h ^ (h >> 15)) * 0x2C1B3C6Du) >> 20 & (KTAB - 1);
-    for (;;) {  // at most KT distinct keys in KTAB = 2 KT positions: always terminates
+    // time: Q = rint((t - t_first) 2^36) read off the mantissa of (t - t_first) + 1.5 * 2^16 (ulp 2^-36, ties to even like
+    // rint); bin = Q >> 31, valid iff 0 <= Q < 2^43 (128 s)
+    const double dm  = __dadd_rn(__dadd_rn(tt[u], -P.t_first), 98304.0);
+    const int    qlo = __double2loint(dm), qhi = __double2hiint(dm) - 0x40F80000;
+    const int    bin = (qhi << 1) | (int)((unsigned)qlo >> 31);
+    q.w              = qlo & 0x7fffffff;
+    if (!ok || (((unsigned)ax | (unsigned)ay | (unsigned)az) >> 17) != 0u || (unsigned)qhi >= (unsigned)(WC_MAX_BINS >> 1)) {
+      st->err_range = 1;
+      continue;
+    }
+    const unsigned klo = ((unsigned)ay << 29) | ((unsigned)az << 12) | (unsigned)bin;
+    const unsigned khi = ((unsigned)ax << 14) | ((unsigned)ay >> 3);
+    const unsigned long long key = ((unsigned long long)khi << 32) | klo;
+    unsigned m = klo * 0x9E3779B1u + khi * 0x85EBCA77u;  // tile-local table: a cheap mix
+    m          = (m ^ (m >> 15)) * 0x2C1B3C6Du;
+    unsigned h = __umulhi(m, (unsigned)KTAB);
+    bool created = false;
+    for (;;) {  // at most KT distinct keys in KTAB positions: always terminates
       unsigned long long k = skey[h];
-      if (k == WC_KEY_EMPTY) k = atomicCAS(&skey[h], WC_KEY_EMPTY, key[u]);
-      if (k == WC_KEY_EMPTY || k == key[u]) break;
-      h = (h + 1) & (KTAB - 1);
-    }
-    hpos[u]           = (int)h;
-    const unsigned sh = (h & 1u) * 16u;
-    rank[u]           = (int)((atomicAdd(&cnt2[h >> 1], 1u << sh) >> sh) & 0xffffu);
-  }
-  __syncthreads();
-  // ---- exclusive scan of the per-position counts (8 positions per thread) -> offsets and the compact run list
-  {
-    unsigned c[8];
-    int      tot = 0, nz = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned w = cnt2[4 * t + k];
-      c[2 * k] = w & 0xffffu, c[2 * k + 1] = w >> 16;
-      tot += (int)(c[2 * k] + c[2 * k + 1]);
-      nz += (c[2 * k] != 0) + (c[2 * k + 1] != 0);
-    }
-    const int mine = (tot << 16) | nz;  // both prefix sums stay below 2^12
-    int       incl = mine;
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (t < 32) {
-      const int w  = t < KNT / 32 ? wsum[t] : 0;
-      int       wi = w;
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, wi, d);
-        if (t >= d) wi += o;
+      if (k == key) break;
+      if (k == WC_KEY_EMPTY) {
+        k = atomicCAS(&skey[h], WC_KEY_EMPTY, key);
+        if (k == WC_KEY_EMPTY) {
+          created = true;
+          break;
+        }
+        if (k == key) break;
       }
-      if (t < KNT / 32) wsum[t] = wi - w;
-      if (t == KNT / 32 - 1) {
-        s_nruns = wi & 0xffff;
-        s_base  = atomicAdd(&st->n_slots, wi & 0xffff);  // reserve one slot id per run of this tile
-      }
+      h = h + 1 == KTAB ? 0u : h + 1;
     }
-    __syncthreads();
-    const int ex = wsum[warp] + incl - mine;
-    int       o = ex >> 16, r = ex & 0xffff;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      off[8 * t + k] = (unsigned short)o;
-      if (c[k]) runh[r++] = (unsigned short)(8 * t + k);
-      o += (int)c[k];
+    const unsigned l16  = (unsigned)l << 4;
+    const unsigned prev = atomicExch(&head[h], l16);
+    *reinterpret_cast<int4*>(payb + l16)                = q;
+    *reinterpret_cast<unsigned short*>(nxtb + (l << 1)) = (unsigned short)prev;
+    if (created) {
+      // plain shared atomic (inline PTX: the compiler's warp-aggregated form costs ~25 instructions in divergent code)
+      unsigned rid;
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(rid) : "r"((unsigned)__cvta_generic_to_shared(&s_nruns)) : "memory");
+      runh[rid] = (unsigned short)h;
     }
   }
+  if (P.dbg == 2) return;
   __syncthreads();
-#pragma unroll
-  for (int u = 0; u < KPT; ++u)
-    if (hpos[u] >= 0) perm[off[hpos[u]] + rank[u]] = (unsigned short)(t + KNT * u);
-  __syncthreads();
-  // ---- one thread per run: sum it, then merge it into the global cell table
+  if (P.dbg == 3) return;
   const int nruns = s_nruns;
-  for (int r = t; r < nruns; r += KNT) {
-    const int                h   = runh[r];
-    const unsigned long long key = skey[h];
-    const int                p0  = off[h];
-    const int                np  = (int)((cnt2[h >> 1] >> ((h & 1) * 16)) & 0xffffu);
+  if (t == 0) s_base = atomicAdd(&st->n_slots, nruns);  // reserve one slot id per run of this tile (needed only after the walks)
+  // ---- one thread per run: walk its list and sum it
+  for (int r0 = 0; r0 < nruns; r0 += KNT) {
+    const int r = r0 + t;
     long long a_t = 0, a_x = 0, a_y = 0, a_z = 0, a_xx = 0, a_xy = 0, a_xz = 0, a_yy = 0, a_yz = 0, a_zz = 0;
-    int       lmin = KT, lmax = -1;
-    int j = 0;
-    for (; j + 1 < np; j += 2) {  // two points per step: the two dependent perm -> payload load chains overlap
-      const int  l0 = perm[p0 + j], l1 = perm[p0 + j + 1];
-      const int4 e = pay[l0], f = pay[l1];
-      lmin = min(lmin, min(l0, l1)), lmax = max(lmax, max(l0, l1));
-      a_t += e.w, a_x += e.x, a_y += e.y, a_z += e.z;
-      a_xx += (long long)e.x * e.x, a_xy += (long long)e.x * e.y, a_xz += (long long)e.x * e.z;
-      a_yy += (long long)e.y * e.y, a_yz += (long long)e.y * e.z, a_zz += (long long)e.z * e.z;
-      a_t += f.w, a_x += f.x, a_y += f.y, a_z += f.z;
-      a_xx += (long long)f.x * f.x, a_xy += (long long)f.x * f.y, a_xz += (long long)f.x * f.z;
-      a_yy += (long long)f.y * f.y, a_yz += (long long)f.y * f.z, a_zz += (long long)f.z * f.z;
+    unsigned  lmin = 0xffffffffu, lmax = 0u, np = 0;
+    unsigned long long key = 0;
+    if (r < nruns) {
+      const int h = runh[r];
+      key         = skey[h];
+      unsigned lo = head[h];
+      do {
+        const int4     e  = *reinterpret_cast<const int4*>(payb + lo);
+        const unsigned nl = *reinterpret_cast<const unsigned short*>(nxtb + (lo >> 3));
+        lmin = min(lmin, lo), lmax = max(lmax, lo);
+        ++np;
+        a_t += e.w, a_x += e.x, a_y += e.y, a_z += e.z;
+        a_xx += (long long)e.x * e.x, a_xy += (long long)e.x * e.y, a_xz += (long long)e.x * e.z;
+        a_yy += (long long)e.y * e.y, a_yz += (long long)e.y * e.z, a_zz += (long long)e.z * e.z;
+        lo = nl;
+      } while (lo != K_END);
     }
-    if (j < np) {
-      const int  l = perm[p0 + j];
-      const int4 e = pay[l];
-      lmin = min(lmin, l), lmax = max(lmax, l);
-      a_t += e.w, a_x += e.x, a_y += e.y, a_z += e.z;
-      a_xx += (long long)e.x * e.x, a_xy += (long long)e.x * e.y, a_xz += (long long)e.x * e.z;
-      a_yy += (long long)e.y * e.y, a_yz += (long long)e.y * e.z, a_zz += (long long)e.z * e.z;
+    if (r0 == 0) __syncthreads();  // s_base (the counter bump has long returned)
+    if (r >= nruns) continue;
+    if (P.dbg == 4) {
+      if (a_t + a_x + a_y + a_z + a_xx + a_xy + a_xz + a_yy + a_yz + a_zz == 12345) st->err_range = 1;
+      continue;
     }
-    // timestamps are non-decreasing in the point index (checked above), so the run's extrema sit at its end points
-    const unsigned long long tmin_inv = ~OrderedBits(time[base + lmin]), tmax = OrderedBits(time[base + lmax]);
-    const int                fresh    = s_base + r;
+    const int fresh = s_base + r;
     if (fresh >= slot_cap) {
       st->err_capacity = 1;
       continue;
     }
-    ulonglong2* d = reinterpret_cast<ulonglong2*>(slots + fresh);
-    d[0] = make_ulonglong2(key, (unsigned long long)np);
-    d[1] = make_ulonglong2((unsigned long long)a_t, (unsigned long long)a_x);
-    d[2] = make_ulonglong2((unsigned long long)a_y, (unsigned long long)a_z);
-    d[3] = make_ulonglong2((unsigned long long)a_xx, (unsigned long long)a_xy);
-    d[4] = make_ulonglong2((unsigned long long)a_xz, (unsigned long long)a_yy);
-    d[5] = make_ulonglong2((unsigned long long)a_yz, (unsigned long long)a_zz);
-    d[6] = make_ulonglong2(tmin_inv, tmax);
-    d[7] = make_ulonglong2(0ull, 0ull);  // table_pos / vid
+    // record key in the layout the later stages use: [vx:15][vy:15][vz:15][leaf:6][bin:12]
+    const unsigned ax = (unsigned)(key >> 46), ay = (unsigned)(key >> 29) & 0x1ffffu, az = (unsigned)(key >> 12) & 0x1ffffu;
+    const unsigned fx = ax & 3u, fy = ay & 3u, fz = az & 3u;
+    const unsigned leaf = ((fx >> 1) << 5) | ((fy >> 1) << 4) | ((fz >> 1) << 3) | ((fx & 1u) << 2) | ((fy & 1u) << 1) | (fz & 1u);
+    const unsigned long long rkey = ((unsigned long long)(ax >> 2) << 48) | ((unsigned long long)(ay >> 2) << 33) |
+                                    ((unsigned long long)(az >> 2) << 18) | ((unsigned long long)leaf << 12) | (key & 4095ull);
+    // timestamps are non-decreasing in the point index (checked above): the run's earliest / latest points are its
+    // lowest / highest indices
+    // consecutive lanes hold consecutive slots: every store below fills half of a 32-byte sector per lane, side by side
+    slots.key[fresh]        = rkey;
+    slots.p0[2 * fresh]     = make_int4((int)np, base + (int)(lmin >> 4), base + (int)(lmax >> 4), 0);
+    slots.p0[2 * fresh + 1] = make_int4((int)a_t, (int)(a_t >> 32), (int)a_x, (int)(a_x >> 32));
+    slots.p1[2 * fresh]     = make_int4((int)a_y, (int)(a_y >> 32), (int)a_z, (int)(a_z >> 32));
+    slots.p1[2 * fresh + 1] = make_int4((int)a_xx, (int)(a_xx >> 32), (int)a_xy, (int)(a_xy >> 32));
+    slots.p2[2 * fresh]     = make_int4((int)a_xz, (int)(a_xz >> 32), (int)a_yy, (int)(a_yy >> 32));
+    slots.p2[2 * fresh + 1] = make_int4((int)a_yz, (int)(a_yz >> 32), (int)a_zz, (int)(a_zz >> 32));
   }
 }
 
@@ -270,14 +263,14 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
 // native 64-bit RED atomics and retire (n = 0).  The records were completed by the previous kernel, so no fences are
 // needed — the only dependent chain is one CAS.  (2) Surviving slots register with their voxel (voxel table -> dense
 // voxel id, per-voxel slot count).
-__global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __restrict__ st, HEnt* __restrict__ tab,
+__global__ void voxel_index(wc_slot_planes slots, wc_extract_status* __restrict__ st, HEnt* __restrict__ tab,
                             unsigned long long capmask, unsigned long long* __restrict__ vkeys, int* __restrict__ vslot,
                             unsigned long long vmask, int* __restrict__ vox_count, unsigned long long* __restrict__ vox_key,
-                            int* __restrict__ vox_hpos, int vox_cap) {
+                            int* __restrict__ vox_hpos, int vox_cap, int2* __restrict__ rec_info, int* __restrict__ rec_tpos) {
   const int ns = min(st->n_slots, INT_MAX);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
-    const unsigned long long ckey = slots[s].key;
-    int                      owner = -2;
+    const unsigned long long ckey = slots.key[s];
+    int                      owner = -2, tpos = -1;
     {
       unsigned long long h = mix64(ckey) & capmask;
       for (unsigned long long probe = 0; probe <= capmask; ++probe, h = (h + 1) & capmask) {
@@ -285,6 +278,7 @@ __global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __re
         if (k == WC_KEY_EMPTY) {
           *((volatile int*)&tab[h].slot) = s;
           owner                          = s;
+          tpos                           = (int)h;
           break;
         }
         if (k == ckey) {
@@ -298,18 +292,22 @@ __global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __re
       if (owner < 0) {
         st->err_capacity = 1;
       } else {
-        wc_slot*       sl = slots + owner;
-        const wc_slot* me = slots + s;
-        atomicAdd((unsigned long long*)&sl->n, (unsigned long long)me->n);
-        atomicAdd((unsigned long long*)&sl->st, (unsigned long long)me->st);
+        const int4 a0 = slots.p0[2 * s];
+        atomicAdd(&slots.p0[2 * owner].x, a0.x);
+        atomicMin(&slots.p0[2 * owner].y, a0.y);
+        atomicMax(&slots.p0[2 * owner].z, a0.z);
+        const unsigned long long* m0 = reinterpret_cast<const unsigned long long*>(slots.p0 + 2 * s + 1);
+        const unsigned long long* m1 = reinterpret_cast<const unsigned long long*>(slots.p1 + 2 * s);
+        const unsigned long long* m2 = reinterpret_cast<const unsigned long long*>(slots.p2 + 2 * s);
+        unsigned long long*       o0 = reinterpret_cast<unsigned long long*>(slots.p0 + 2 * owner + 1);
+        unsigned long long*       o1 = reinterpret_cast<unsigned long long*>(slots.p1 + 2 * owner);
+        unsigned long long*       o2 = reinterpret_cast<unsigned long long*>(slots.p2 + 2 * owner);
+        atomicAdd(o0, m0[0]), atomicAdd(o0 + 1, m0[1]);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) atomicAdd((unsigned long long*)&sl->s[k], (unsigned long long)me->s[k]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) atomicAdd((unsigned long long*)&sl->ss[k], (unsigned long long)me->ss[k]);
-        atomicMax(&sl->tmin_inv, me->tmin_inv);
-        atomicMax(&sl->tmax, me->tmax);
+        for (int k = 0; k < 4; ++k) atomicAdd(o1 + k, m1[k]), atomicAdd(o2 + k, m2[k]);
       }
-      slots[s].vid = -1;  // retired: voxel_scatter skips it
+      rec_info[s] = make_int2(-1, 0);  // retired: voxel_scatter skips it
+      rec_tpos[s] = -1;
       continue;
     }
     const unsigned long long key = ckey >> 18;
@@ -338,8 +336,9 @@ __global__ void voxel_index(wc_slot* __restrict__ slots, wc_extract_status* __re
         break;
       }
     }
-    slots[s].vid = vid;
-    if (vid >= 0) atomicAdd(&vox_count[vid], 1);
+    // the record's rank among its voxel's slots: voxel_scatter places it without another atomic
+    rec_info[s] = make_int2(vid, vid >= 0 ? atomicAdd(&vox_count[vid], 1) : 0);
+    rec_tpos[s] = tpos;  // the cell-table entry this record claimed (extract_cleanup empties exactly those)
   }
 }
 
@@ -379,13 +378,13 @@ __global__ void __launch_bounds__(1024) voxel_scan(const int* __restrict__ cnt, 
   if (threadIdx.x == 0) off[nv] = carry;
 }
 
-__global__ void voxel_scatter(const wc_slot* __restrict__ slots, const wc_extract_status* __restrict__ st,
-                              const int* __restrict__ off, int* __restrict__ cursor, int* __restrict__ seg) {
-  const int ns = st->n_slots;
+__global__ void voxel_scatter(const int2* __restrict__ rec_info, const wc_extract_status* __restrict__ st, int slot_cap,
+                              const int* __restrict__ off, int* __restrict__ seg) {
+  const int ns = min(st->n_slots, slot_cap);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += gridDim.x * blockDim.x) {
-    const int vid = slots[s].vid;
-    if (vid < 0) continue;
-    seg[off[vid] + atomicAdd(&cursor[vid], 1)] = s;
+    const int2 vr = rec_info[s];
+    if (vr.x < 0) continue;
+    seg[off[vr.x] + vr.y] = s;
   }
 }
 
@@ -421,8 +420,23 @@ __device__ __forceinline__ void mom_zero(Mom& m) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) m.ss[k] = 0;
 }
+// one slot's values, gathered from the planes (six 16-byte loads)
+struct SlotVals {
+  long long n, st, s[3], ss[6];
+  int       imin, imax;
+};
+__device__ __forceinline__ long long ll_of(int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
+__device__ __forceinline__ SlotVals load_slot(const wc_slot_planes& S, int s) {
+  const int4 a = S.p0[2 * s], b = S.p0[2 * s + 1], c = S.p1[2 * s], d = S.p1[2 * s + 1], e = S.p2[2 * s], f = S.p2[2 * s + 1];
+  SlotVals   v;
+  v.n = a.x, v.imin = a.y, v.imax = a.z;
+  v.st = ll_of(b.x, b.y), v.s[0] = ll_of(b.z, b.w), v.s[1] = ll_of(c.x, c.y), v.s[2] = ll_of(c.z, c.w);
+  v.ss[0] = ll_of(d.x, d.y), v.ss[1] = ll_of(d.z, d.w), v.ss[2] = ll_of(e.x, e.y), v.ss[3] = ll_of(e.z, e.w);
+  v.ss[4] = ll_of(f.x, f.y), v.ss[5] = ll_of(f.z, f.w);
+  return v;
+}
 // add one slot's exact integer moments (about its leaf centre) shifted to the voxel centre
-__device__ __forceinline__ void mom_add_slot(Mom& m, const wc_slot* __restrict__ sl, int leaf, double q0, double q1) {
+__device__ __forceinline__ void mom_add_slot(Mom& m, const SlotVals* __restrict__ sl, int leaf, double q0, double q1) {
   const int    c1 = leaf >> 3, c2 = leaf & 7;
   const double dx = ((c1 & 4) ? q0 : -q0) + ((c2 & 4) ? q1 : -q1);
   const double dy = ((c1 & 2) ? q0 : -q0) + ((c2 & 2) ? q1 : -q1);
@@ -447,9 +461,11 @@ __device__ __forceinline__ void mom_add(Mom& a, const Mom& b) {
   for (int k = 0; k < 6; ++k) a.ss[k] += b.ss[k];
 }
 // per-entry record: moments about the voxel centre + exact time sums + time extrema, 14 doubles
-//   [0] n, [1..3] s, [4..9] ss, [10] n*bin, [11] sum(Q - bin<<31) (both exact integers < 2^53), [12] tmin_inv bits, [13] tmax bits
+//   [0] n, [1..3] s, [4..9] ss, [10] n*bin, [11] sum(Q - bin<<31) (both exact integers < 2^53), [12] index of the earliest point, [13] of the latest
 constexpr int REC = 14;
-__device__ __forceinline__ void rec_from_slot(const wc_slot* __restrict__ sl, unsigned lb, double q0, double q1, double* r) {
+__device__ __forceinline__ void rec_from_slot(const wc_slot_planes& S, int slot, unsigned lb, double q0, double q1, double* r) {
+  const SlotVals v = load_slot(S, slot);
+  const SlotVals* sl = &v;
   Mom m;
   mom_zero(m);
   mom_add_slot(m, sl, (int)(lb >> 12), q0, q1);
@@ -460,8 +476,8 @@ __device__ __forceinline__ void rec_from_slot(const wc_slot* __restrict__ sl, un
   for (int k = 0; k < 6; ++k) r[4 + k] = m.ss[k];
   r[10] = (double)(sl->n * (long long)(lb & 4095u));
   r[11] = (double)sl->st;
-  r[12] = __longlong_as_double((long long)sl->tmin_inv);
-  r[13] = __longlong_as_double((long long)sl->tmax);
+  r[12] = (double)sl->imin;
+  r[13] = (double)sl->imax;
 }
 __device__ __forceinline__ void mom_add_rec(Mom& m, const double* r) {
   m.n += r[0];
@@ -523,7 +539,7 @@ __device__ void bitonic_sort_smem(unsigned* keys, int npad) {
 #endif
 template <int ECAP, int NT, bool STAGE>
 __global__ void __launch_bounds__(NT, WC_EMIT_MINB(NT))
-cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg, const int* __restrict__ vox_off,
+cluster_eig_emit(const wc_slot_planes slots, const double* __restrict__ time, const int* __restrict__ seg, const int* __restrict__ vox_off,
                  const unsigned long long* __restrict__ vox_key, wc_extract_status* __restrict__ st, EmitParams P, int e_lo,
                  wc_surfel* __restrict__ out, unsigned long long* __restrict__ sort_hi,
                  unsigned long long* __restrict__ sort_lo, int* __restrict__ bcnt) {
@@ -537,7 +553,7 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
   // entry e -> its record (shared memory when staged, else built from the slot in L2)
   auto get_rec = [&](int e, double* tmp) -> const double* {
     if (STAGE) return rec + e * REC;
-    rec_from_slot(slots + sid[e], leafbin[e], P.q0, P.q1, tmp);
+    rec_from_slot(slots, sid[e], leafbin[e], P.q0, P.q1, tmp);
     return tmp;
   };
   __shared__ Mom           tot[73];   // 0 root, 1..8 layer 1, 9..72 layer 2
@@ -561,11 +577,11 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
     for (int e = threadIdx.x; e < npad; e += NT) {
       if (e < E) {
         const int                s   = seg[off + e];
-        const unsigned long long key = slots[s].key;
+        const unsigned long long key = slots.key[s];
         sid[e]                       = s;
         leafbin[e]                   = (unsigned)(key & 0x3ffffu);
         skey[e]                      = ((unsigned)(key & 0x3ffffu) << 14) | (unsigned)e;
-        if (STAGE) rec_from_slot(slots + s, (unsigned)(key & 0x3ffffu), P.q0, P.q1, rec + e * REC);
+        if (STAGE) rec_from_slot(slots, s, (unsigned)(key & 0x3ffffu), P.q0, P.q1, rec + e * REC);
       } else {
         skey[e] = 0xffffffffu;
       }
@@ -714,18 +730,18 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
         if (!emit[node_base + node_of(lk, level)]) continue;
         bool start = (f & 2) != 0;
         if (!start) {
-          unsigned long long gmin_inv = 0, pmax = 0;
+          int gmin = INT_MAX, pmax = -1;  // earliest point of this group, latest point of the previous one
           for (int j = i; j < E && (j == i || !(flag[j] & 1)); ++j) {
             const int e = skey[j] & 16383u;
-            gmin_inv = max(gmin_inv, STAGE ? (unsigned long long)__double_as_longlong(rec[e * REC + 12]) : slots[sid[e]].tmin_inv);
+            gmin        = min(gmin, STAGE ? (int)rec[e * REC + 12] : slots.p0[2 * sid[e]].y);
           }
           for (int j = i - 1; j >= 0; --j) {
             const int e = skey[j] & 16383u;
-            pmax = max(pmax, STAGE ? (unsigned long long)__double_as_longlong(rec[e * REC + 13]) : slots[sid[e]].tmax);
+            pmax        = max(pmax, STAGE ? (int)rec[e * REC + 13] : slots.p0[2 * sid[e]].z);
             if (flag[j] & 1) break;
           }
           // points[i].timestamp - cluster.back().timestamp > 0.05  (surfel_extraction.cc:24)
-          start = __dsub_rn(FromOrderedBits(~gmin_inv), FromOrderedBits(pmax)) > P.gap;
+          start = __dsub_rn(time[gmin], time[pmax]) > P.gap;
         }
         if (start) my_starts |= 1ull << trip;
       }
@@ -744,7 +760,7 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
         double n = 0.0;
         for (int j = i; j < E && (j == i || !(flag[j] & 6)); ++j) {
           const int e = skey[j] & 16383u;
-          n += STAGE ? rec[e * REC] : (double)slots[sid[e]].n;
+          n += STAGE ? rec[e * REC] : (double)slots.p0[2 * sid[e]].x;
         }
         if (n < (double)P.cmin) continue;
         jobs[atomicAdd(&s_njobs, 1)] = (unsigned short)i;
@@ -804,19 +820,22 @@ cluster_eig_emit(const wc_slot* __restrict__ slots, const int* __restrict__ seg,
   }
 }
 
-// leave the voxel table and counters clean for the next call (only the touched entries are reset; the cell table is
-// re-initialised by one memset per call and the slot records are fully rewritten by their creators)
-__global__ void extract_cleanup(const wc_extract_status* __restrict__ st, unsigned long long* __restrict__ vkeys,
-                                int* __restrict__ vslot, const int* __restrict__ vox_hpos, int* __restrict__ vox_count,
-                                int* __restrict__ vox_cursor) {
-  const int nv  = st->n_voxels;
+// leave the cell table, the voxel table and the counters clean for the next call: only the touched entries are reset
+// (the tables are initialised once, at allocation; the slot records are fully rewritten by their creators)
+__global__ void extract_cleanup(const wc_extract_status* __restrict__ st, int slot_cap, int vox_cap, HEnt* __restrict__ tab,
+                                const int* __restrict__ rec_tpos, unsigned long long* __restrict__ vkeys, int* __restrict__ vslot,
+                                const int* __restrict__ vox_hpos, int* __restrict__ vox_count) {
+  const int nv  = min(st->n_voxels, vox_cap), ns = min(st->n_slots, slot_cap);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int s = tid; s < ns; s += nth) {
+    const int h = rec_tpos[s];
+    if (h >= 0) *reinterpret_cast<int4*>(tab + h) = make_int4(-1, -1, -1, 0);  // {key = WC_KEY_EMPTY, slot = -1}
+  }
   for (int v = tid; v < nv; v += nth) {
-    const int h   = vox_hpos[v];
-    vkeys[h]      = WC_KEY_EMPTY;
-    vslot[h]      = -1;
-    vox_count[v]  = 0;
-    vox_cursor[v] = 0;
+    const int h  = vox_hpos[v];
+    vkeys[h]     = WC_KEY_EMPTY;
+    vslot[h]     = -1;
+    vox_count[v] = 0;
   }
 }
 
@@ -931,12 +950,14 @@ static wc_status extract_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMalloc(&c->d_xyz, np * sizeof(float4)));
   WC_CUDA(c, cudaMalloc(&c->d_time, np * sizeof(double)));
   WC_CUDA(c, cudaMalloc(&c->d_htab, c->hcap * sizeof(HEnt)));
-  WC_CUDA(c, cudaMalloc(&c->d_slots, c->slot_cap * sizeof(wc_slot)));
+  c->slot_cap     = (np + 3) & ~(size_t)3;  // keeps every plane 32-byte aligned
+  WC_CUDA(c, cudaMalloc(&c->d_slots, c->slot_cap * WC_SLOT_BYTES));
   WC_CUDA(c, cudaMalloc(&c->d_vkeys, c->vcap * 8));
   WC_CUDA(c, cudaMalloc(&c->d_vslot, c->vcap * 4));
   WC_CUDA(c, cudaMalloc(&c->d_vox_count, (np + 1) * 4));
   WC_CUDA(c, cudaMalloc(&c->d_vox_off, (np + 1) * 4));
-  WC_CUDA(c, cudaMalloc(&c->d_vox_cursor, (np + 1) * 4));
+  WC_CUDA(c, cudaMalloc(&c->d_rec_info, np * sizeof(int2)));
+  WC_CUDA(c, cudaMalloc(&c->d_rec_tpos, np * 4));
   WC_CUDA(c, cudaMalloc(&c->d_vox_key, (np + 1) * 8));
   WC_CUDA(c, cudaMalloc(&c->d_vox_hpos, (np + 1) * 4));
   WC_CUDA(c, cudaMalloc(&c->d_seg, np * 4));
@@ -957,7 +978,7 @@ static wc_status extract_alloc(wc_ctx* c) {
   WC_CUDA(c, cudaMemsetAsync(c->d_vkeys, 0xff, c->vcap * 8, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vslot, 0xff, c->vcap * 4, c->stream));
   WC_CUDA(c, cudaMemsetAsync(c->d_vox_count, 0, (np + 1) * 4, c->stream));
-  WC_CUDA(c, cudaMemsetAsync(c->d_vox_cursor, 0, (np + 1) * 4, c->stream));
+  WC_CUDA(c, cudaMemsetAsync(c->d_htab, 0xff, c->hcap * sizeof(HEnt), c->stream));
   WC_CUDA(c, cudaFuncSetAttribute(voxel_key_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
   WC_CUDA(c, cudaFuncSetAttribute((cluster_eig_emit<512, 128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * (16 + 8 * REC)));
   WC_CUDA(c, cudaFuncSetAttribute((cluster_eig_emit<8192, 256, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
@@ -966,11 +987,17 @@ static wc_status extract_alloc(wc_ctx* c) {
 
 void wc_extract_free(wc_ctx* c) {
   void* ptrs[] = {c->d_raw,     c->d_xyz,      c->d_time,    c->d_htab,   c->d_slots,    c->d_vkeys,
-                  c->d_vslot,   c->d_vox_count, c->d_vox_off, c->d_vox_cursor, c->d_vox_key, c->d_vox_hpos, c->d_seg,   c->d_xstat,
+                  c->d_vslot,   c->d_vox_count, c->d_vox_off, c->d_rec_info, c->d_rec_tpos, c->d_vox_key, c->d_vox_hpos, c->d_seg,   c->d_xstat,
                   c->d_surf_raw, c->d_surf,    c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, c->d_assign, c->d_sort_perm, c->d_bcnt, c->d_boff, c->d_bcur};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_xstat) cudaFreeHost(c->h_xstat);
+}
+
+static wc_slot_planes slot_planes(const wc_ctx* c) {
+  unsigned char* b = (unsigned char*)c->d_slots;
+  const size_t   n = c->slot_cap;
+  return wc_slot_planes{(unsigned long long*)b, (int4*)(b + 8 * n), (int4*)(b + 40 * n), (int4*)(b + 72 * n)};
 }
 
 extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n) {
@@ -1009,7 +1036,8 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   if (!(vsf > 0.f) || !isfinite(vsf) || (double)P.v8 * WC_COORD_SCALE >= 1073741824.0 || (double)P.v4 * 4 != (double)vsf)
     WC_FAIL(c, WC_EINVAL, "voxel_size out of range");
   P.t_first = c->t_first, P.n = n;
-  for (int k = 0; k < 3; ++k) P.vox0[k] = c->vox0[k];
+  P.dbg = getenv("WC_K1_DBG") ? atoi(getenv("WC_K1_DBG")) : 0;
+  for (int k = 0; k < 3; ++k) P.vox0[k] = c->vox0[k], P.goffm[k] = 4 * (WC_VOX_BIAS - c->vox0[k]) - 0x4B400000;
 
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
   WC_CUDA(c, cudaMemsetAsync(c->d_xstat, 0, sizeof(wc_extract_status), st));
@@ -1018,16 +1046,16 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   WC_CUDA(c, cudaMemsetAsync(c->d_bcnt, 0, SORT_NB * 4, st));
   // cell table sized to this sweep (worst case one cell per point still fits; typical load is ~0.2)
   const size_t hcap = wc_next_pow2(n < 1024 ? 1024 : (size_t)n);
-  WC_CUDA(c, cudaMemsetAsync(c->d_htab, 0xff, hcap * sizeof(HEnt), st));
   WC_CUDA(c, cudaEventRecord(c->ev[4], st));
   const int ntiles = (n + KT - 1) / KT;
-  { ++c->n_launches; voxel_key_moments<<<ntiles, KNT, K1_SMEM, st>>>(c->d_xyz, c->d_time, P, c->d_slots, (int)c->slot_cap, c->d_xstat,
+  const wc_slot_planes SP = slot_planes(c);
+  { ++c->n_launches; voxel_key_moments<<<ntiles, KNT, K1_SMEM, st>>>(c->d_xyz, c->d_time, P, SP, (int)c->slot_cap, c->d_xstat,
                                            c->want_assign ? c->d_assign : nullptr); }
   WC_CUDA(c, cudaEventRecord(c->ev[1], st));
-  { ++c->n_launches; voxel_index<<<c->num_sms * 8, 256, 0, st>>>(c->d_slots, c->d_xstat, (HEnt*)c->d_htab, hcap - 1, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
-                                              c->d_vox_key, c->d_vox_hpos, (int)c->prm.max_points); }
+  { ++c->n_launches; voxel_index<<<c->num_sms * 8, 256, 0, st>>>(SP, c->d_xstat, (HEnt*)c->d_htab, hcap - 1, c->d_vkeys, c->d_vslot, c->vcap - 1, c->d_vox_count,
+                                              c->d_vox_key, c->d_vox_hpos, (int)c->prm.max_points, c->d_rec_info, c->d_rec_tpos); }
   { ++c->n_launches; voxel_scan<<<1, 1024, 0, st>>>(c->d_vox_count, c->d_vox_off, c->d_xstat); }
-  { ++c->n_launches; voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_slots, c->d_xstat, c->d_vox_off, c->d_vox_cursor, c->d_seg); }
+  { ++c->n_launches; voxel_scatter<<<c->num_sms * 4, 256, 0, st>>>(c->d_rec_info, c->d_xstat, (int)c->slot_cap, c->d_vox_off, c->d_seg); }
   EmitParams E;
   E.voxel = (double)vsf, E.q0 = (double)P.v4, E.q1 = (double)P.v8, E.t_first = P.t_first;
   E.thr = (double)c->prm.planer_threshold, E.min_like = c->prm.min_plane_likeness, E.gap = c->prm.cluster_time_gap;
@@ -1041,21 +1069,21 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   WC_CUDA(c, cudaEventRecord(c->ev_fork, st));
   for (int i = 0; i < 3; ++i) WC_CUDA(c, cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
   c->n_launches += 1;
-  cluster_eig_emit<512, 128, true><<<c->num_sms * 3, 128, 512 * (16 + 8 * REC), st>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat,
+  cluster_eig_emit<512, 128, true><<<c->num_sms * 3, 128, 512 * (16 + 8 * REC), st>>>(SP, c->d_time, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat,
                                                                                         E, 256, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
-  cluster_eig_emit<256, 128, true><<<c->num_sms * 6, 128, 256 * (16 + 8 * REC), c->side[2]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key,
+  cluster_eig_emit<256, 128, true><<<c->num_sms * 6, 128, 256 * (16 + 8 * REC), c->side[2]>>>(SP, c->d_time, c->d_seg, c->d_vox_off, c->d_vox_key,
                                                                                                 c->d_xstat, E, 128, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
-  cluster_eig_emit<128, 64, true><<<c->num_sms * 12, 64, 128 * (16 + 8 * REC), c->side[0]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key,
+  cluster_eig_emit<128, 64, true><<<c->num_sms * 12, 64, 128 * (16 + 8 * REC), c->side[0]>>>(SP, c->d_time, c->d_seg, c->d_vox_off, c->d_vox_key,
                                                                                                c->d_xstat, E, 0, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
-  cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, c->side[1]>>>(c->d_slots, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
+  cluster_eig_emit<8192, 256, false><<<c->num_sms, 256, 8192 * 16, c->side[1]>>>(SP, c->d_time, c->d_seg, c->d_vox_off, c->d_vox_key, c->d_xstat, E,
                                                                                  512, c->d_surf_raw, c->d_sort_hi, c->d_sort_lo, c->d_bcnt);
   for (int i = 0; i < 3; ++i) {
     WC_CUDA(c, cudaEventRecord(c->ev_join[i], c->side[i]));
     WC_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[i], 0));
   }
   WC_CUDA(c, cudaMemcpyAsync(c->h_xstat, c->d_xstat, sizeof(wc_extract_status), cudaMemcpyDeviceToHost, st));
-  { ++c->n_launches; extract_cleanup<<<c->num_sms, 256, 0, st>>>(c->d_xstat, c->d_vkeys, c->d_vslot, c->d_vox_hpos, c->d_vox_count,
-                                              c->d_vox_cursor); }
+  { ++c->n_launches; extract_cleanup<<<c->num_sms * 4, 256, 0, st>>>(c->d_xstat, (int)c->slot_cap, (int)c->prm.max_points, (HEnt*)c->d_htab, c->d_rec_tpos,
+                                                  c->d_vkeys, c->d_vslot, c->d_vox_hpos, c->d_vox_count); }
   WC_CUDA(c, cudaEventRecord(c->ev[2], st));
   // final order by timestamp: enqueued without waiting for the surfel count (the kernels read it on the device), so the
   // whole extraction has ONE host synchronisation
