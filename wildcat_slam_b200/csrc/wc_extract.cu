@@ -40,7 +40,6 @@ struct ExtractParams {
   int    vox0[3];
   int    goffm[3];        // 4 (WC_VOX_BIAS - vox0) - 0x4B400000: leaf-cell index bias of the tile keys, minus the magic exponent
   int    n;
-  int    dbg;
 };
 
 // axis_cell: x float32, v4 = voxel/4 (exact in float32).  y = RN(x * RN(1/v4)) is within 2^-6 of x / v4 (|x / v4| < 2^22),
@@ -123,7 +122,7 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
   const int base = blockIdx.x * KT;
 
   for (int k = t; k < K1_OFF_PAY / 16; k += KNT) reinterpret_cast<int4*>(k1_smem)[k] = make_int4(-1, -1, -1, -1);
-  if (t == 0) s_nruns = 0;
+  if (t == 0) s_nruns = 0, s_base = -1;
   // the tile's points: all loads first, so that they are in flight together
   float4 p[KPT];
   double tt[KPT], tp[KPT];
@@ -137,10 +136,6 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
     }
   }
   __syncthreads();
-  if (P.dbg == 1) {
-    if (p[0].x + p[1].x + p[2].x + p[3].x + (float)(tt[0] + tt[1] + tt[2] + tt[3] + tp[0] + tp[1] + tp[2] + tp[3]) == 1.2345f) st->err_range = 1;
-    return;
-  }
 
 #pragma unroll
   for (int u = 0; u < KPT; ++u) {
@@ -201,11 +196,12 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
       runh[rid] = (unsigned short)h;
     }
   }
-  if (P.dbg == 2) return;
   __syncthreads();
-  if (P.dbg == 3) return;
   const int nruns = s_nruns;
-  if (t == 0) s_base = atomicAdd(&st->n_slots, nruns);  // reserve one slot id per run of this tile (needed only after the walks)
+  // reserve one slot id per run of this tile: thread 0 publishes the base through shared memory; it is needed only after
+  // the walks, by which time the counter bump has long returned (no second barrier: a warp writes its records as soon
+  // as its own lists are summed)
+  if (t == 0) *(volatile int*)&s_base = atomicAdd(&st->n_slots, nruns);
   // ---- one thread per run: walk its list and sum it
   for (int r0 = 0; r0 < nruns; r0 += KNT) {
     const int r = r0 + t;
@@ -227,13 +223,11 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
         lo = nl;
       } while (lo != K_END);
     }
-    if (r0 == 0) __syncthreads();  // s_base (the counter bump has long returned)
     if (r >= nruns) continue;
-    if (P.dbg == 4) {
-      if (a_t + a_x + a_y + a_z + a_xx + a_xy + a_xz + a_yy + a_yz + a_zz == 12345) st->err_range = 1;
-      continue;
+    int sb;
+    while ((sb = *(volatile int*)&s_base) < 0) {
     }
-    const int fresh = s_base + r;
+    const int fresh = sb + r;
     if (fresh >= slot_cap) {
       st->err_capacity = 1;
       continue;
@@ -1036,7 +1030,6 @@ extern "C" wc_status wc_build_surfels_resident(wc_ctx* c, size_t* n_out, double*
   if (!(vsf > 0.f) || !isfinite(vsf) || (double)P.v8 * WC_COORD_SCALE >= 1073741824.0 || (double)P.v4 * 4 != (double)vsf)
     WC_FAIL(c, WC_EINVAL, "voxel_size out of range");
   P.t_first = c->t_first, P.n = n;
-  P.dbg = getenv("WC_K1_DBG") ? atoi(getenv("WC_K1_DBG")) : 0;
   for (int k = 0; k < 3; ++k) P.vox0[k] = c->vox0[k], P.goffm[k] = 4 * (WC_VOX_BIAS - c->vox0[k]) - 0x4B400000;
 
   WC_CUDA(c, cudaEventRecord(c->ev[0], st));
