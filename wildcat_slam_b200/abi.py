@@ -9,7 +9,7 @@ import re
 from . import types as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libwildcat_b200.so")
+SO_PATH = os.environ.get("WC_LIB_OVERRIDE") or os.path.join(_HERE, "libwildcat_b200.so")  # override: A/B experiments of tools/
 HEADER = os.path.join(_HERE, "..", "include", "wildcat_b200.h")
 _lib = None
 

@@ -1177,6 +1177,12 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   __shared__ __align__(16) LMState sst;
   static_assert(sizeof(LMState) % 8 == 0, "LMState is copied as 8-byte words");
   const int t  = threadIdx.x;
+  // mbarrier of the bulk copies that bring the normal equations into shared memory (every thread arrives once)
+  __shared__ __align__(8) uint64_t build_bar;
+  if (A_IN_SMEM && t == 0) {
+    wctma::mbar_init(&build_bar, LMT);
+    wctma::mbar_fence_init();
+  }
   pdl_trigger();
   pdl_wait();
 #ifdef WC_LM_TIMING
@@ -1227,6 +1233,71 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   double*       A    = A_IN_SMEM ? sA : B.A;            // (Dp + 4) x LD; compile-time choice: shared accesses are LDS/STS
   double*       rinv = A + (size_t)(Dp + 4) * LD;       // reciprocal pivots
   const double  radius = st->radius;
+  // A = S H S + diag / radius, lower triangle only; padding rows are identity, row Dp is the right-hand side g_s = S g,
+  // rows Dp+1..Dp+3 are zero.
+  double* sscale = rinv + Dp;    // A_IN_SMEM: jacobian scaling and LM diagonal of this step, staged next to the pivots
+  double* sdiag  = sscale + Dp;
+  if constexpr (A_IN_SMEM) {
+    // The raw lower-triangle rows of H (and g) come in by the copy engine: one 1-D bulk copy per row, all completing on
+    // one mbarrier — every row is in flight at once, where register-staged loads paid ~5 dependent L2 round trips
+    // (19 k -> ~4 k cycles at 141 unknowns).  Row r lands at the start of A's row r in H's own column numbering; the
+    // scaling pass below compacts it in place (the three fixed position columns drop out).
+    const double spre = t < D ? B.scale[t] : 1.0;
+    const double dpre = (t < D && st->reuse_diagonal) ? B.diag[t] : 0.0;
+    if (t < D) {
+      const int      ir    = amb_of(t, ff);
+      const unsigned bytes = (unsigned)(((ir + 1) * 8 + 15) & ~15);  // never past the row: N is even
+      wctma::mbar_expect_tx(&build_bar, bytes);
+      wctma::bulk_g2s(A + (size_t)t * LD, H + (size_t)ir * N, bytes, &build_bar);
+    } else if (t == D) {
+      wctma::mbar_expect_tx(&build_bar, (unsigned)(N * 8));
+      wctma::bulk_g2s(A + (size_t)Dp * LD, g, (unsigned)(N * 8), &build_bar);
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wctma::smem_addr(&build_bar)) : "memory");
+    }
+    wctma::mbar_wait(&build_bar, 0);
+    if (t < D) {
+      double d = dpre;
+      if (!st->reuse_diagonal) {
+        d         = fmin(fmax(A[(size_t)t * LD + amb_of(t, ff)] * spre * spre, o.min_lm_diagonal), o.max_lm_diagonal);
+        B.diag[t] = d;
+      }
+      sscale[t] = spre, sdiag[t] = d;
+    }
+    __syncthreads();
+    const int lane = t & 31, nw = LMT / 32;
+    for (int r = t >> 5; r < Dp + 4; r += nw) {
+      double*      Ar = A + (size_t)r * LD;
+      const double sr = r < D ? sscale[r] : 1.0;
+      const int    nq = (Dp + 31) >> 5;  // column chunks (<= BS_SLOTS: the system fits shared memory)
+      double       v[BS_SLOTS];
+#pragma unroll
+      for (int q = 0; q < BS_SLOTS; ++q) {
+        const int c = lane + 32 * q;
+        v[q]        = 0.0;
+        if (q < nq && c < D && (r == Dp || (r < D && c <= r))) v[q] = Ar[amb_of(c, ff)];
+      }
+      __syncwarp();  // the row is compacted in place: every raw value is read before any lane writes
+#pragma unroll
+      for (int q = 0; q < BS_SLOTS; ++q) {
+        const int c = lane + 32 * q;
+        if (q >= nq || c >= Dp || (r < Dp && c > r)) continue;
+        double x = v[q];
+        if (r < D) {
+          x *= sr * sscale[c];
+          if (r == c) {
+            const double sq = sqrt(sdiag[r] / radius);
+            x += sq * sq;
+          }
+        } else if (r < Dp) {
+          x = c == r ? 1.0 : 0.0;
+        } else if (r == Dp && c < D) {
+          x *= sscale[c];
+        }
+        Ar[c] = x;
+      }
+    }
+  } else {
   if (!st->reuse_diagonal)
     for (int c = t; c < D; c += LMT) {
       const int    i = amb_of(c, ff);
@@ -1294,6 +1365,7 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
       }
     }
   }
+  }  // !A_IN_SMEM
   __syncthreads();
 #ifdef WC_LM_TIMING
   tk[2] = clock64();
@@ -2134,7 +2206,7 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
   SolveBufs     B  = make_bufs(c, o.fix_first_position ? 1 : 0);
   const int     D  = o.fix_first_position ? N - 3 : N;
   const int     Dp          = (D + CB - 1) / CB * CB, LD = ((Dp >> 1) & 1) ? Dp : Dp + 2;
-  const size_t  a_bytes     = ((size_t)(Dp + 4) * LD + Dp) * 8;
+  const size_t  a_bytes     = ((size_t)(Dp + 4) * LD + 3 * (size_t)Dp) * 8;  // A, reciprocal pivots, scaling, LM diagonal
   const int     a_in_smem   = a_bytes <= 200 * 1024;
   const size_t  smem        = a_in_smem ? a_bytes : 0;
   static const int no_wide  = getenv("WC_LM_NO_WIDE") != nullptr;  // test hook: the single-CTA global-memory step
