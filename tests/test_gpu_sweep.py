@@ -168,3 +168,30 @@ def test_predict_states_matches_oracle(od, ctx, oracle):
     with pytest.raises(WildcatError) as e:
         od.PredictStates(imu, ba, bg, S.GRAV, float(imu["timestamp"][-1]), sdt, 1, ctx=ctx)
     assert e.value.status == T.WC_EOUT_OF_SPAN
+
+
+def test_prefetched_sweep_equals_plain_upload(od, ctx):
+    """wc_points_prefetch: a sweep copied in ahead of time on the copy stream gives bitwise the same surfels as the plain
+    upload; an unclaimed prefetch (another buffer is uploaded instead) is ignored; a second prefetch replaces the first."""
+    w = S.make_window("C2")
+    plain = od.ResidentSweep(w.points, ctx=ctx)
+    plain.extract()
+    ref = plain.fetch()
+    a = ctx.pinned(len(w.points), T.POINT48)
+    a[:] = w.points
+    b = ctx.pinned(len(w.points) // 2, T.POINT48)
+    b[:] = w.points[: len(b)]
+    ctx.prefetch(b)           # replaced below
+    ctx.prefetch(a)
+    rs = od.ResidentSweep(a, ctx=ctx)   # claims the prefetched copy
+    rs.extract()
+    got = rs.fetch()
+    assert got.tobytes() == ref.tobytes()
+    ctx.prefetch(b)           # never claimed: the next upload is of another buffer
+    rs2 = od.ResidentSweep(w.points, ctx=ctx)
+    rs2.extract()
+    assert rs2.fetch().tobytes() == ref.tobytes()
+    half = od.ResidentSweep(b, ctx=ctx)  # the pending prefetch of b is still valid and is claimed here
+    n_half, _ = half.extract()
+    plain_half = od.ResidentSweep(np.array(b), ctx=ctx)
+    assert plain_half.extract()[0] == n_half and half.fetch().tobytes() == plain_half.fetch().tobytes()

@@ -82,6 +82,11 @@ struct wc_ctx {
 
   // ---- extraction
   void*               d_raw;      // wc_point48 staging (raw upload)
+  void*               d_raw_next; // second staging buffer: the NEXT sweep, copied in by wc_points_prefetch while a pass runs
+  cudaStream_t        copy_stream;
+  cudaEvent_t         ev_prefetch;
+  const void*         prefetch_src;  // host buffer of the prefetched sweep (nullptr: none pending)
+  size_t              prefetch_n;
   float4*             d_xyz;      // resident points
   double*             d_time;
   size_t              n_pts;

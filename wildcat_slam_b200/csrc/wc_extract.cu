@@ -980,18 +980,46 @@ static wc_status extract_alloc(wc_ctx* c) {
 }
 
 void wc_extract_free(wc_ctx* c) {
-  void* ptrs[] = {c->d_raw,     c->d_xyz,      c->d_time,    c->d_htab,   c->d_slots,    c->d_vkeys,
+  void* ptrs[] = {c->d_raw,  c->d_raw_next,   c->d_xyz,      c->d_time,    c->d_htab,   c->d_slots,    c->d_vkeys,
                   c->d_vslot,   c->d_vox_count, c->d_vox_off, c->d_rec_info, c->d_rec_tpos, c->d_vox_key, c->d_vox_hpos, c->d_seg,   c->d_xstat,
                   c->d_surf_raw, c->d_surf,    c->d_sort_hi, c->d_sort_lo, c->d_sort_idx, c->d_assign, c->d_sort_perm, c->d_bcnt, c->d_boff, c->d_bcur};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_xstat) cudaFreeHost(c->h_xstat);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream), cudaStreamDestroy(c->copy_stream);
+  if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
 }
 
 static wc_slot_planes slot_planes(const wc_ctx* c) {
   unsigned char* b = (unsigned char*)c->d_slots;
   const size_t   n = c->slot_cap;
   return wc_slot_planes{(unsigned long long*)b, (int4*)(b + 8 * n), (int4*)(b + 40 * n), (int4*)(b + 72 * n)};
+}
+
+// Streaming ingestion: start copying the NEXT sweep into a second staging buffer on a dedicated copy stream and return at
+// once.  The caller runs the current window pass meanwhile; the wc_points_upload of that same buffer then finds the data
+// already on the device (it only waits for the copy's event).  pts must stay valid and unchanged until that upload, and
+// should be pinned memory (wc_host_alloc) for the copy to be truly asynchronous.  A prefetch that is never claimed is
+// simply overwritten by the next one.
+extern "C" wc_status wc_points_prefetch(wc_ctx* c, const wc_point48* pts, size_t n) {
+  if (!c || (!pts && n)) return WC_EINVAL;
+  if (n > (size_t)c->prm.max_points) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_points=%lld", n, (long long)c->prm.max_points);
+  wc_status s = extract_alloc(c);
+  if (s) return s;
+  c->prefetch_src = nullptr;
+  if (n == 0) return WC_OK;
+  if (!c->d_raw_next) {
+    WC_CUDA(c, cudaMalloc(&c->d_raw_next, (size_t)c->prm.max_points * sizeof(wc_point48)));
+    WC_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    WC_CUDA(c, cudaEventCreateWithFlags(&c->ev_prefetch, cudaEventDisableTiming));
+  }
+  // the buffer may still be the source of the previous upload's repack on the main stream
+  WC_CUDA(c, cudaEventRecord(c->ev_prefetch, c->stream));
+  WC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_prefetch, 0));
+  WC_CUDA(c, cudaMemcpyAsync(c->d_raw_next, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+  WC_CUDA(c, cudaEventRecord(c->ev_prefetch, c->copy_stream));
+  c->prefetch_src = pts, c->prefetch_n = n;
+  return WC_OK;
 }
 
 extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n) {
@@ -1001,7 +1029,14 @@ extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n
   if (s) return s;
   c->n_pts = n;
   if (n == 0) return WC_OK;
-  WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
+  if (c->prefetch_src == pts && c->prefetch_n == n) {
+    // this sweep was prefetched: swap the staging buffers and wait (on the device) for the copy
+    void* tmp = c->d_raw; c->d_raw = c->d_raw_next; c->d_raw_next = tmp;
+    c->prefetch_src = nullptr;
+    WC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
+  } else {
+    WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
+  }
   { ++c->n_launches; repack_points<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const wc_point48*)c->d_raw, (int)n, c->d_xyz, c->d_time); }
   WC_CUDA(c, cudaGetLastError());
   // voxel of the first point / first timestamp anchor the relative keys (host copy of element 0 is at hand)

@@ -1177,12 +1177,6 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   __shared__ __align__(16) LMState sst;
   static_assert(sizeof(LMState) % 8 == 0, "LMState is copied as 8-byte words");
   const int t  = threadIdx.x;
-  // mbarrier of the bulk copies that bring the normal equations into shared memory (every thread arrives once)
-  __shared__ __align__(8) uint64_t build_bar;
-  if (A_IN_SMEM && t == 0) {
-    wctma::mbar_init(&build_bar, LMT);
-    wctma::mbar_fence_init();
-  }
   pdl_trigger();
   pdl_wait();
 #ifdef WC_LM_TIMING
@@ -1238,24 +1232,26 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
   double* sscale = rinv + Dp;    // A_IN_SMEM: jacobian scaling and LM diagonal of this step, staged next to the pivots
   double* sdiag  = sscale + Dp;
   if constexpr (A_IN_SMEM) {
-    // The raw lower-triangle rows of H (and g) come in by the copy engine: one 1-D bulk copy per row, all completing on
-    // one mbarrier — every row is in flight at once, where register-staged loads paid ~5 dependent L2 round trips
-    // (19 k -> ~4 k cycles at 141 unknowns).  Row r lands at the start of A's row r in H's own column numbering; the
-    // scaling pass below compacts it in place (the three fixed position columns drop out).
+    // The raw lower-triangle rows of H (and g) come in by asynchronous 16-byte copies (cp.async: global -> shared without
+    // a register stage), ~10 per thread and all in flight at once, where register-staged loads paid ~5 dependent L2 round
+    // trips.  (One bulk copy per row through the TMA unit was measured too: 142 small copies serialise in the copy engine
+    // and take as long as the loads did.)  Row r lands at the start of A's row r in H's own column numbering; the scaling
+    // pass below compacts it in place (the three fixed position columns drop out).
     const double spre = t < D ? B.scale[t] : 1.0;
     const double dpre = (t < D && st->reuse_diagonal) ? B.diag[t] : 0.0;
-    if (t < D) {
-      const int      ir    = amb_of(t, ff);
-      const unsigned bytes = (unsigned)(((ir + 1) * 8 + 15) & ~15);  // never past the row: N is even
-      wctma::mbar_expect_tx(&build_bar, bytes);
-      wctma::bulk_g2s(A + (size_t)t * LD, H + (size_t)ir * N, bytes, &build_bar);
-    } else if (t == D) {
-      wctma::mbar_expect_tx(&build_bar, (unsigned)(N * 8));
-      wctma::bulk_g2s(A + (size_t)Dp * LD, g, (unsigned)(N * 8), &build_bar);
-    } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wctma::smem_addr(&build_bar)) : "memory");
+    {
+      const int lane = t & 31, nw = LMT / 32;
+      for (int r = t >> 5; r <= D; r += nw) {
+        const double* src = r < D ? H + (size_t)amb_of(r, ff) * N : g;            // 16-byte aligned rows (N is even)
+        double*       dst = A + (size_t)(r < D ? r : Dp) * LD;
+        const int     nch = r < D ? (amb_of(r, ff) >> 1) + 1 : N / 2;              // 16-byte chunks: columns 0 .. amb(r) (+1)
+        for (int j = lane; j < nch; j += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wctma::smem_addr(dst + 2 * j)), "l"(src + 2 * j) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    wctma::mbar_wait(&build_bar, 0);
+    __syncthreads();
     if (t < D) {
       double d = dpre;
       if (!st->reuse_diagonal) {
@@ -1265,24 +1261,22 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
       sscale[t] = spre, sdiag[t] = d;
     }
     __syncthreads();
+    // (rolled loops on purpose: this code runs once per launch, from a cold instruction cache — an unrolled version is
+    //  fetch bound)
     const int lane = t & 31, nw = LMT / 32;
+#pragma unroll 1
     for (int r = t >> 5; r < Dp + 4; r += nw) {
       double*      Ar = A + (size_t)r * LD;
       const double sr = r < D ? sscale[r] : 1.0;
-      const int    nq = (Dp + 31) >> 5;  // column chunks (<= BS_SLOTS: the system fits shared memory)
-      double       v[BS_SLOTS];
-#pragma unroll
-      for (int q = 0; q < BS_SLOTS; ++q) {
-        const int c = lane + 32 * q;
-        v[q]        = 0.0;
-        if (q < nq && c < D && (r == Dp || (r < D && c <= r))) v[q] = Ar[amb_of(c, ff)];
-      }
-      __syncwarp();  // the row is compacted in place: every raw value is read before any lane writes
-#pragma unroll
-      for (int q = 0; q < BS_SLOTS; ++q) {
-        const int c = lane + 32 * q;
-        if (q >= nq || c >= Dp || (r < Dp && c > r)) continue;
-        double x = v[q];
+      const int    c1 = r < Dp ? r : Dp - 1;  // last column of this row
+#pragma unroll 1
+      for (int c = lane; c - lane <= c1; c += 32) {
+        // the row is compacted in place, 32 columns at a time in ascending order: a chunk reads columns up to c + 3 and
+        // writes columns <= c, so later chunks still find their raw values
+        double x = 0.0;
+        if (c < D && (r == Dp || (r < D && c <= r))) x = Ar[amb_of(c, ff)];
+        __syncwarp();
+        if (c > c1) continue;
         if (r < D) {
           x *= sr * sscale[c];
           if (r == c) {
@@ -1291,8 +1285,10 @@ __global__ void __launch_bounds__(LMT) lm_step(SolveBufs B, wc_solve_opts o, int
           }
         } else if (r < Dp) {
           x = c == r ? 1.0 : 0.0;
-        } else if (r == Dp && c < D) {
-          x *= sscale[c];
+        } else if (r == Dp) {
+          x = c < D ? x * sscale[c] : 0.0;
+        } else {
+          x = 0.0;
         }
         Ar[c] = x;
       }
