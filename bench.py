@@ -493,12 +493,14 @@ def main():
             t0 = time.perf_counter()
             cur, nxt = bufs[turn[0] & 1], bufs[(turn[0] + 1) & 1]
             turn[0] += 1
-            rp2 = od.ResidentPass(cur, w.imu, w.samples, fix_p, ctx=ctx2)   # claims the prefetched copy of `cur` (first step: plain upload)
+            # claims the prefetched copy of `cur` (first step: plain upload); the fixed window is uploaded once and then stays
+            # on the device, as it does in the reference between two ShrinkToFit calls
+            rp2 = od.ResidentPass(cur, w.imu, w.samples, fix_p, ctx=ctx2, keep_fix=turn[0] > 1)
             ctx2.prefetch(nxt)                                              # H2D of the next sweep, overlapped with this pass
             x2, sg2, st2 = rp2.run()                                        # D2H: corrections + summary
             torch.cuda.synchronize()                                        # (includes the copy stream)
             dt = time.perf_counter() - t0
-            h2d = N * 48 + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + len(fix) * 208
+            h2d = N * 48 + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + (0 if turn[0] > 1 else len(fix) * 208)
             d2h = K * 96 + 2400
             return dt, sg2.num_iterations, h2d, d2h
 
@@ -507,7 +509,7 @@ def main():
         e2e = measure(e2e_stream_step)
         e2e["api"] = ("wc_points_upload + wc_pass_upload + wc_points_prefetch(next sweep) + wc_window_pass_resident: host buffers in, "
                       "corrections out; the copy of sweep k+1 overlaps the pass of sweep k (one 96 MB upload and one result "
-                      "read-back per step, all inside the timed region)")
+                      "read-back per step, all inside the timed region); the fixed window stays resident after the first step")
         e2e["serial"] = serial
         if world == 1:
             e2e["per_call_api"] = measure(e2e_step)

@@ -357,7 +357,9 @@ class ResidentPass:
     """Device-resident window pass (steps 7-13 of AddLidarScan in one call): upload sweep + IMU/sample states + fixed
     window once, then run extract -> poses -> match x2 -> assemble -> solve repeatedly without host round trips."""
 
-    def __init__(self, cloud, imu, samples, fix_body, ctx=None):
+    def __init__(self, cloud, imu, samples, fix_body, ctx=None, keep_fix=False):
+        """keep_fix: the fixed window uploaded by an earlier pass on this context stays where it is (it only changes at
+        ShrinkToFit, lidar_odometry.cc:228-250); fix_body is ignored."""
         self.ctx = ctx or default_context()
         self.cloud = np.ascontiguousarray(cloud, dtype=T.POINT48)
         self.imu = np.ascontiguousarray(imu, dtype=T.IMU)
@@ -365,8 +367,12 @@ class ResidentPass:
         self.fix = np.ascontiguousarray(fix_body if fix_body is not None else np.zeros(0, T.SURFEL), dtype=T.SURFEL)
         lib, h = self.ctx.lib, self.ctx.handle
         self.ctx.check(lib.wc_points_upload(h, T.ptr(self.cloud), len(self.cloud)), "wc_points_upload")
-        self.ctx.check(lib.wc_pass_upload(h, T.ptr(self.imu), len(self.imu), T.ptr(self.samples), len(self.samples),
-                                          T.ptr(self.fix), len(self.fix)), "wc_pass_upload")
+        if keep_fix:
+            st = lib.wc_pass_upload_windows(h, T.ptr(self.imu), len(self.imu), T.ptr(self.samples), len(self.samples), None, 0, None, 0, 2)
+            self.ctx.check(st, "wc_pass_upload_windows")
+        else:
+            self.ctx.check(lib.wc_pass_upload(h, T.ptr(self.imu), len(self.imu), T.ptr(self.samples), len(self.samples),
+                                              T.ptr(self.fix), len(self.fix)), "wc_pass_upload")
 
     def run(self, opts=None):
         o = opts or T.default_solve_opts()
