@@ -201,7 +201,7 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
   // reserve one slot id per run of this tile: thread 0 publishes the base through shared memory; it is needed only after
   // the walks, by which time the counter bump has long returned (no second barrier: a warp writes its records as soon
   // as its own lists are summed)
-  if (t == 0) *(volatile int*)&s_base = atomicAdd(&st->n_slots, nruns);
+  if (t == 0) atomicExch(&s_base, atomicAdd(&st->n_slots, nruns));  // (shared-memory atomics on both sides of the hand-over)
   // ---- one thread per run: walk its list and sum it
   for (int r0 = 0; r0 < nruns; r0 += KNT) {
     const int r = r0 + t;
@@ -225,7 +225,7 @@ voxel_key_moments(const float4* __restrict__ xyz, const double* __restrict__ tim
     }
     if (r >= nruns) continue;
     int sb;
-    while ((sb = *(volatile int*)&s_base) < 0) {
+    while ((sb = atomicAdd(&s_base, 0)) < 0) {
     }
     const int fresh = sb + r;
     if (fresh >= slot_cap) {
