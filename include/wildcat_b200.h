@@ -218,9 +218,9 @@ wc_status wc_build_surfels(wc_ctx* ctx, const wc_point48* pts, size_t n, wc_surf
 wc_status wc_points_upload(wc_ctx* ctx, const wc_point48* pts, size_t n);
 /* Streaming ingestion (no reference counterpart: the reference processes one rosbag message at a time,
  * wildcat_slam_node.cc:83-99): starts the host-to-device copy of the NEXT sweep on a copy stream and returns at once, so
- * that it overlaps the window pass of the current sweep; the later wc_points_upload of the same (pts, n) then finds
- * the points on the device.  pts must stay valid and unchanged until that call; pinned memory (wc_host_alloc) makes
- * the copy asynchronous. */
+ * that it overlaps the window pass of the current sweep; the NEXT wc_points_upload, if it names the same (pts, n), finds
+ * the points on the device (any other upload drops the prefetch).  pts must stay valid and unchanged until that call;
+ * pinned memory (wc_host_alloc) makes the copy asynchronous. */
 wc_status wc_points_prefetch(wc_ctx* ctx, const wc_point48* pts, size_t n);
 wc_status wc_build_surfels_resident(wc_ctx* ctx, size_t* n_out, double* gpu_ms_keys,
                                     double* gpu_ms_emit, double* gpu_ms_total);

@@ -187,11 +187,12 @@ def test_prefetched_sweep_equals_plain_upload(od, ctx):
     rs.extract()
     got = rs.fetch()
     assert got.tobytes() == ref.tobytes()
-    ctx.prefetch(b)           # never claimed: the next upload is of another buffer
+    ctx.prefetch(b)           # never claimed: the next upload is of another buffer, which drops the prefetch
     rs2 = od.ResidentSweep(w.points, ctx=ctx)
     rs2.extract()
     assert rs2.fetch().tobytes() == ref.tobytes()
-    half = od.ResidentSweep(b, ctx=ctx)  # the pending prefetch of b is still valid and is claimed here
+    b[:] = w.points[len(b): 2 * len(b)]  # the buffer changes after its prefetch was dropped: the upload must see the new content
+    half = od.ResidentSweep(b, ctx=ctx)
     n_half, _ = half.extract()
     plain_half = od.ResidentSweep(np.array(b), ctx=ctx)
     assert plain_half.extract()[0] == n_half and half.fetch().tobytes() == plain_half.fetch().tobytes()

@@ -999,8 +999,8 @@ static wc_slot_planes slot_planes(const wc_ctx* c) {
 // Streaming ingestion: start copying the NEXT sweep into a second staging buffer on a dedicated copy stream and return at
 // once.  The caller runs the current window pass meanwhile; the wc_points_upload of that same buffer then finds the data
 // already on the device (it only waits for the copy's event).  pts must stay valid and unchanged until that upload, and
-// should be pinned memory (wc_host_alloc) for the copy to be truly asynchronous.  A prefetch that is never claimed is
-// simply overwritten by the next one.
+// should be pinned memory (wc_host_alloc) for the copy to be truly asynchronous.  Only the NEXT wc_points_upload can claim
+// a prefetch; one that is not claimed is dropped.
 extern "C" wc_status wc_points_prefetch(wc_ctx* c, const wc_point48* pts, size_t n) {
   if (!c || (!pts && n)) return WC_EINVAL;
   if (n > (size_t)c->prm.max_points) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_points=%lld", n, (long long)c->prm.max_points);
@@ -1029,10 +1029,13 @@ extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n
   if (s) return s;
   c->n_pts = n;
   if (n == 0) return WC_OK;
-  if (c->prefetch_src == pts && c->prefetch_n == n) {
+  // a prefetch can only be claimed by the upload that directly follows it (same buffer, same size): any other upload
+  // drops it, so a stale copy can never be mistaken for a later buffer that happens to live at the same address
+  const bool claimed = c->prefetch_src == pts && c->prefetch_n == n;
+  c->prefetch_src    = nullptr;
+  if (claimed) {
     // this sweep was prefetched: swap the staging buffers and wait (on the device) for the copy
     void* tmp = c->d_raw; c->d_raw = c->d_raw_next; c->d_raw_next = tmp;
-    c->prefetch_src = nullptr;
     WC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
   } else {
     WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
