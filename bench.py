@@ -220,8 +220,8 @@ def run_c5(args, rank, world, local_rank):
     sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
-    barrier()
-    sampler.mark_begin()
+    sampler.mark_begin()  # waits for the sampler's first reading: a different time on every rank
+    barrier()             # ... so the ranks line up AFTER it (a late rank's delay would otherwise be timed as device time on its peers, which wait for it inside their first collective)
     l0 = ctx.lib.wc_launch_count(ctx.handle)
     dev_ms, lin_ms, iters, nlin, summ, x = 0.0, 0.0, 0, 0, None, None
     t_wall = time.perf_counter()
@@ -381,8 +381,8 @@ def main():
     sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
-    barrier()
-    sampler.mark_begin()
+    sampler.mark_begin()  # waits for the sampler's first reading: a different time on every rank
+    barrier()             # ... so the ranks line up AFTER it (a late rank's delay would otherwise be timed as device time on its peers, which wait for it inside their first collective)
     l0 = ctx.lib.wc_launch_count(ctx.handle)
     dev_ms, iters, stats, summ = 0.0, 0, [], None
     t_wall = time.perf_counter()
