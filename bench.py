@@ -361,6 +361,7 @@ def main():
         from wildcat_slam_b200 import sharding
 
         ctx.comm_connect(rank, world, sharding.exchange_handles(ctx.comm_export(), dist, device="cuda"))
+        ctx.comm_shard_upload(True)  # sweep uploads: each rank copies its 1/world slab over PCIe, the rest comes over NVLink
     # fixed window = surfels of the preceding (already optimised) sweep, body frame; built once by the GPU path
     fix = od.UpdateSurfelPoses(w.fix_imu, od.BuildSurfels(w.fix_points, ctx=ctx), ctx=ctx) if len(w.fix_points) else None
     rp = od.ResidentPass(w.points, w.imu, w.samples, fix, ctx=ctx)
@@ -458,7 +459,7 @@ def main():
             x2, sg2, st2 = rp2.run()                                        # D2H: corrections + summary
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            h2d = N * 48 + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + len(fix) * 208
+            h2d = N * 48 // world + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + len(fix) * 208  # per rank: its slab of the sweep
             d2h = K * 96 + 2400
             return dt, sg2.num_iterations, h2d, d2h
 
@@ -500,7 +501,7 @@ def main():
             x2, sg2, st2 = rp2.run()                                        # D2H: corrections + summary
             torch.cuda.synchronize()                                        # (includes the copy stream)
             dt = time.perf_counter() - t0
-            h2d = N * 48 + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + (0 if turn[0] > 1 else len(fix) * 208)
+            h2d = N * 48 // world + len(w.imu) * T.IMU.itemsize + K * T.SAMPLE.itemsize + (0 if turn[0] > 1 else len(fix) * 208)
             d2h = K * 96 + 2400
             return dt, sg2.num_iterations, h2d, d2h
 

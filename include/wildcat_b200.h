@@ -431,6 +431,11 @@ wc_status wc_apply_corrections(wc_ctx* ctx, wc_sample_state* samples, size_t K, 
 #define WC_IPC_HANDLE_BYTES 64
 wc_status wc_comm_export(wc_ctx* ctx, uint8_t handle[WC_IPC_HANDLE_BYTES]);
 wc_status wc_comm_connect(wc_ctx* ctx, int rank, int world, const uint8_t* all_handles /* world*64 */);
+/* Sharded sweep upload (upload half).  After wc_comm_shard_upload(ctx, 1) the calls wc_points_upload and
+ * wc_points_prefetch are COLLECTIVE: every rank passes the same (pts, n); each copies only its 1/world slab of the raw
+ * sweep over its own PCIe link into its exported raw area, and every rank repacks each point from its owner's area over
+ * NVLink.  Off by default (a rank may then upload on its own). */
+wc_status wc_comm_shard_upload(wc_ctx* ctx, int on);
 wc_status wc_comm_disconnect(wc_ctx* ctx);
 
 #ifdef __cplusplus

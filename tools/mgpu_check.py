@@ -27,6 +27,21 @@ ctx.comm_connect(rank, world, handles)
 m = od.KnnSurfelMatcher(ctx); m.BuildIndex(sld); cs2, _ = m.Match(sld)
 m2 = od.KnnSurfelMatcher(ctx); m2.BuildIndex(fix); cf2, _ = m2.Match(sld)
 assert cs2.tobytes() == cs.tobytes() and cf2.tobytes() == cf.tobytes(), "sharded matcher differs from the single-GPU matcher"
+# sharded sweep upload: each rank copies its slab over PCIe, the repack reads every point from its owner over NVLink ->
+# bitwise the same surfels as the plain upload, with and without the prefetch
+from wildcat_slam_b200 import types as T  # noqa: E402
+rs0 = od.ResidentSweep(w.points, ctx=ctx); rs0.extract(); g0 = rs0.fetch()
+ctx.comm_shard_upload(True)
+rs1 = od.ResidentSweep(w.points, ctx=ctx); rs1.extract(); g1 = rs1.fetch()
+pin = ctx.pinned(len(w.points), T.POINT48); pin[:] = w.points
+ctx.prefetch(pin)
+rs2 = od.ResidentSweep(pin, ctx=ctx); rs2.extract(); g2 = rs2.fetch()
+rs3 = od.ResidentSweep(w.points[: len(w.points) // 3], ctx=ctx); n3, _ = rs3.extract()   # another size, other parity
+ctx.comm_shard_upload(False)
+rs4 = od.ResidentSweep(w.points[: len(w.points) // 3], ctx=ctx); n4, _ = rs4.extract()
+assert g1.tobytes() == g0.tobytes() and g2.tobytes() == g0.tobytes() and n3 == n4 and rs3.fetch().tobytes() == rs4.fetch().tobytes(), \
+    "sharded sweep upload differs from the plain upload"
+print(f"[rank {rank}] sharded upload identical: {len(g1)} surfels", flush=True)
 rw = od.ResidentWindow(sld, fix, cs, cf, w.imu, w.samples, ctx)                  # sharded: this rank packs its block only
 for rep in range(3):
     xs, ss = rw.solve()

@@ -157,6 +157,30 @@ __global__ void __launch_bounds__(256) comm_allgather_rows(GatherArgs a) {
   }
 }
 
+// flag round of the sharded sweep upload: "my slab of this epoch is in my raw area" -> every peer; wait for all peers
+struct ReadyArgs {
+  unsigned long long* my_flags;
+  unsigned long long* peer_flags[8];
+  int*                err;
+  unsigned long long  epoch;
+  int                 rank, world;
+  long long           timeout_cycles;
+};
+__global__ void comm_raw_ready(ReadyArgs a) {
+  if (threadIdx.x < a.world) {
+    __threadfence_system();
+    *((volatile unsigned long long*)&a.peer_flags[threadIdx.x][a.rank]) = a.epoch;
+    const long long t0 = clock64();
+    while (*((volatile unsigned long long*)&a.my_flags[threadIdx.x]) < a.epoch) {
+      if (clock64() - t0 > a.timeout_cycles) {
+        *a.err = WC_ECOMM;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
 }  // namespace
 
 static size_t part_doubles(const wc_ctx* c) {
@@ -167,10 +191,14 @@ static size_t part_doubles(const wc_ctx* c) {
 static size_t gather_ints(const wc_ctx* c) { return (size_t)c->prm.max_surfels * 16; }
 static size_t gather_off(const wc_ctx* c) { return 256 + 2 * part_doubles(c) * 8; }  // byte offset of the gather flags
 
+static size_t raw_off(const wc_ctx* c) { return (gather_off(c) + 256 + 2 * gather_ints(c) * 4 + 255) & ~(size_t)255; }  // byte offset of the raw flags
+static size_t raw_area_bytes(const wc_ctx* c) { return (size_t)c->prm.max_points * 48; }
+
 static wc_status comm_alloc(wc_ctx* c) {
   if (c->d_xchg) return WC_OK;
   // [256 B reduce flags][2 x partial normal equations][256 B gather flags][2 x gather region of max_surfels x 16 ints]
-  c->xchg_bytes = 256 + 2 * part_doubles(c) * 8 + 256 + 2 * gather_ints(c) * 4;
+  // [256 B raw flags][2 x raw sweep area of max_points x 48 B]
+  c->xchg_bytes = raw_off(c) + 256 + 2 * raw_area_bytes(c);
   WC_CUDA(c, cudaMalloc(&c->d_xchg, c->xchg_bytes));
   WC_CUDA(c, cudaMemset(c->d_xchg, 0, c->xchg_bytes));
   WC_CUDA(c, cudaMalloc(&c->d_comm_err, 4));
@@ -185,7 +213,7 @@ void wc_comm_free(wc_ctx* c) {
   }
   if (c->d_xchg) cudaFree(c->d_xchg);
   if (c->d_comm_err) cudaFree(c->d_comm_err);
-  c->d_xchg = nullptr, c->d_comm_err = nullptr, c->comm_ready = 0, c->world = 1, c->rank = 0;
+  c->d_xchg = nullptr, c->d_comm_err = nullptr, c->comm_ready = 0, c->world = 1, c->rank = 0, c->shard_upload = 0;
 }
 
 extern "C" wc_status wc_comm_export(wc_ctx* c, uint8_t handle[WC_IPC_HANDLE_BYTES]) {
@@ -215,7 +243,18 @@ extern "C" wc_status wc_comm_connect(wc_ctx* c, int rank, int world, const uint8
     if (e != cudaSuccess) WC_FAIL(c, WC_ECOMM, "cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
     c->peer_xchg[r] = (double*)p;
   }
-  c->rank = rank, c->world = world, c->comm_ready = 1, c->comm_epoch = 0, c->gather_epoch = 0;
+  c->rank = rank, c->world = world, c->comm_ready = 1, c->comm_epoch = 0, c->gather_epoch = 0, c->raw_epoch = 0;
+  return WC_OK;
+}
+
+// Sweep uploads (wc_points_upload / wc_points_prefetch) become collective calls: every rank passes the same sweep, copies
+// only its 1 / world slab over its own PCIe link, and reads the other slabs from its peers over NVLink.
+extern "C" wc_status wc_comm_shard_upload(wc_ctx* c, int on) {
+  if (!c) return WC_EINVAL;
+  if (on && (!c->comm_ready || c->world < 2)) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
+  cudaStreamSynchronize(c->stream);
+  c->prefetch_src = nullptr;  // a pending prefetch belongs to the other mode
+  c->shard_upload = on ? 1 : 0;
   return WC_OK;
 }
 
@@ -301,6 +340,31 @@ wc_status wc_comm_allgather_rows(wc_ctx* c, int* dst, const int* row0, int width
   a.dst = dst, a.err = c->d_comm_err, a.epoch = c->gather_epoch, a.rank = c->rank, a.world = c->world, a.width = width;
   a.timeout_cycles = 4000000000ll;
   { ++c->n_launches; comm_allgather_rows<<<c->num_sms, 256, 0, c->stream>>>(a); }
+  WC_CUDA(c, cudaGetLastError());
+  return WC_OK;
+}
+
+// ---- sharded sweep upload (upload half): every rank copies only ITS slab of the raw sweep over PCIe into
+// its exported raw area; after one flag round the repack kernel of every rank reads each point from its owner's area
+// over NVLink (wc_extract.cu).  Areas are double-buffered by epoch parity like the reduction partials: a rank can write
+// its area of parity p again only after every peer signalled the epoch in between, i.e. finished reading it.
+// this rank's raw area of the given epoch's parity (device pointer, record 0 of the sweep at offset 0)
+void* wc_comm_raw_area(wc_ctx* c, unsigned long long epoch) {
+  return (char*)c->d_xchg + raw_off(c) + 256 + (size_t)(epoch & 1) * raw_area_bytes(c);
+}
+void wc_comm_raw_areas(wc_ctx* c, unsigned long long epoch, const void* areas[8]) {
+  for (int r = 0; r < 8; ++r)
+    areas[r] = r < c->world ? (const void*)((char*)c->peer_xchg[r] + raw_off(c) + 256 + (size_t)(epoch & 1) * raw_area_bytes(c)) : nullptr;
+}
+wc_status wc_comm_raw_ready(wc_ctx* c, unsigned long long epoch) {
+  if (!c->comm_ready) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
+  ReadyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.my_flags = (unsigned long long*)((char*)c->d_xchg + raw_off(c));
+  for (int r = 0; r < c->world; ++r) a.peer_flags[r] = (unsigned long long*)((char*)c->peer_xchg[r] + raw_off(c));
+  a.err = c->d_comm_err, a.epoch = epoch, a.rank = c->rank, a.world = c->world;
+  a.timeout_cycles = 4000000000ll;
+  { ++c->n_launches; comm_raw_ready<<<1, 32, 0, c->stream>>>(a); }
   WC_CUDA(c, cudaGetLastError());
   return WC_OK;
 }

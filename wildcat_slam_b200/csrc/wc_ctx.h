@@ -181,6 +181,9 @@ struct wc_ctx {
   int     comm_ready;
   unsigned long long comm_epoch;
   unsigned long long gather_epoch;
+  int                shard_upload;     // wc_comm_shard_upload: sweep uploads are collective, each rank copies its slab only
+  unsigned long long raw_epoch;        // sharded sweep upload: one epoch per upload / prefetch (parity selects the raw area)
+  unsigned long long prefetch_epoch;   // epoch taken by the pending prefetch
   int*    d_comm_err;
 };
 

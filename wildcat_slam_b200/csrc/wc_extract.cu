@@ -81,6 +81,25 @@ __global__ void repack_points(const wc_point48* __restrict__ raw, int n, float4*
   t[i]            = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z));
 }
 
+// sharded upload: point i sits in the raw area of the rank that copied its slab; read it there (NVLink peer load,
+// cache-volatile: a peer's memory may change between sweeps) and repack into this rank's resident layout
+struct RawAreas {
+  const wc_point48* area[8];
+  int               row0[9];  // slab of rank r: points [row0[r], row0[r + 1])
+  int               world;
+};
+__global__ void repack_points_sharded(RawAreas A, int n, float4* __restrict__ xyz, double* __restrict__ t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = (int)(((long long)i * A.world) / n);
+  while (r > 0 && i < A.row0[r]) --r;
+  while (r + 1 < A.world && i >= A.row0[r + 1]) ++r;
+  const uint4* q = reinterpret_cast<const uint4*>(A.area[r] + i);
+  const uint4  a = __ldcv(q), b = __ldcv(q + 1);  // b: intensity, pad, time (as two words)
+  xyz[i]         = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+  t[i]           = __hiloint2double((int)b.w, (int)b.z);
+}
+
 // ---------------------------------------------------------------------------------------------- K1
 // Cell table entry: key and published slot id share one 16-byte word, so a probe touches one sector.
 struct __align__(16) HEnt {
@@ -990,6 +1009,17 @@ void wc_extract_free(wc_ctx* c) {
   if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
 }
 
+void*     wc_comm_raw_area(wc_ctx* c, unsigned long long epoch);  // wc_comm.cu
+void      wc_comm_raw_areas(wc_ctx* c, unsigned long long epoch, const void* areas[8]);
+wc_status wc_comm_raw_ready(wc_ctx* c, unsigned long long epoch);
+wc_status wc_comm_check(wc_ctx* c);
+
+// sharded sweep upload: world > 1 and switched on by wc_comm_shard_upload (the uploads are then collective calls)
+static bool shard_upload(const wc_ctx* c) { return c->shard_upload && c->world > 1 && c->comm_ready; }
+static void slab_of(const wc_ctx* c, size_t n, int r, size_t* lo, size_t* hi) {
+  *lo = n * (size_t)r / (size_t)c->world, *hi = n * (size_t)(r + 1) / (size_t)c->world;
+}
+
 static wc_slot_planes slot_planes(const wc_ctx* c) {
   unsigned char* b = (unsigned char*)c->d_slots;
   const size_t   n = c->slot_cap;
@@ -1008,15 +1038,25 @@ extern "C" wc_status wc_points_prefetch(wc_ctx* c, const wc_point48* pts, size_t
   if (s) return s;
   c->prefetch_src = nullptr;
   if (n == 0) return WC_OK;
-  if (!c->d_raw_next) {
-    WC_CUDA(c, cudaMalloc(&c->d_raw_next, (size_t)c->prm.max_points * sizeof(wc_point48)));
+  if (!c->copy_stream) {
     WC_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     WC_CUDA(c, cudaEventCreateWithFlags(&c->ev_prefetch, cudaEventDisableTiming));
   }
+  if (!shard_upload(c) && !c->d_raw_next) WC_CUDA(c, cudaMalloc(&c->d_raw_next, (size_t)c->prm.max_points * sizeof(wc_point48)));
   // the buffer may still be the source of the previous upload's repack on the main stream
   WC_CUDA(c, cudaEventRecord(c->ev_prefetch, c->stream));
   WC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_prefetch, 0));
-  WC_CUDA(c, cudaMemcpyAsync(c->d_raw_next, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+  if (shard_upload(c)) {
+    // only this rank's slab crosses PCIe, into this rank's exported raw area of the next epoch (every peer has finished
+    // reading that area: it signalled the epoch in between after its repack)
+    size_t lo, hi;
+    slab_of(c, n, c->rank, &lo, &hi);
+    c->prefetch_epoch = ++c->raw_epoch;
+    wc_point48* area  = (wc_point48*)wc_comm_raw_area(c, c->prefetch_epoch);
+    if (hi > lo) WC_CUDA(c, cudaMemcpyAsync(area + lo, pts + lo, (hi - lo) * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+  } else {
+    WC_CUDA(c, cudaMemcpyAsync(c->d_raw_next, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+  }
   WC_CUDA(c, cudaEventRecord(c->ev_prefetch, c->copy_stream));
   c->prefetch_src = pts, c->prefetch_n = n;
   return WC_OK;
@@ -1033,20 +1073,47 @@ extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n
   // drops it, so a stale copy can never be mistaken for a later buffer that happens to live at the same address
   const bool claimed = c->prefetch_src == pts && c->prefetch_n == n;
   c->prefetch_src    = nullptr;
-  if (claimed) {
-    // this sweep was prefetched: swap the staging buffers and wait (on the device) for the copy
-    void* tmp = c->d_raw; c->d_raw = c->d_raw_next; c->d_raw_next = tmp;
-    WC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
+  if (shard_upload(c)) {
+    // Collective over the ranks (every rank uploads the same sweep): this rank copies its slab into its exported raw area
+    // (or finds it there, prefetched), one flag round, then every point is repacked straight from its owner's area.
+    unsigned long long epoch;
+    if (claimed) {
+      epoch = c->prefetch_epoch;
+      WC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
+    } else {
+      epoch = ++c->raw_epoch;
+      size_t lo, hi;
+      slab_of(c, n, c->rank, &lo, &hi);
+      wc_point48* area = (wc_point48*)wc_comm_raw_area(c, epoch);
+      if (hi > lo) WC_CUDA(c, cudaMemcpyAsync(area + lo, pts + lo, (hi - lo) * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((s = wc_comm_raw_ready(c, epoch))) return s;
+    RawAreas A;
+    memset(&A, 0, sizeof(A));
+    const void* areas[8];
+    wc_comm_raw_areas(c, epoch, areas);
+    for (int r = 0; r < 8; ++r) A.area[r] = (const wc_point48*)areas[r];
+    for (int r = 0; r <= c->world; ++r) A.row0[r] = (int)(n * (size_t)r / (size_t)c->world);
+    A.world = c->world;
+    { ++c->n_launches; repack_points_sharded<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(A, (int)n, c->d_xyz, c->d_time); }
+    WC_CUDA(c, cudaGetLastError());
   } else {
-    WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
+    if (claimed) {
+      // this sweep was prefetched: swap the staging buffers and wait (on the device) for the copy
+      void* tmp = c->d_raw; c->d_raw = c->d_raw_next; c->d_raw_next = tmp;
+      WC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
+    } else {
+      WC_CUDA(c, cudaMemcpyAsync(c->d_raw, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->stream));
+    }
+    { ++c->n_launches; repack_points<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const wc_point48*)c->d_raw, (int)n, c->d_xyz, c->d_time); }
+    WC_CUDA(c, cudaGetLastError());
   }
-  { ++c->n_launches; repack_points<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const wc_point48*)c->d_raw, (int)n, c->d_xyz, c->d_time); }
-  WC_CUDA(c, cudaGetLastError());
   // voxel of the first point / first timestamp anchor the relative keys (host copy of element 0 is at hand)
   const double vs = (double)c->prm.voxel_size;
   c->vox0[0] = (int)floor((double)pts[0].x / vs), c->vox0[1] = (int)floor((double)pts[0].y / vs), c->vox0[2] = (int)floor((double)pts[0].z / vs);
   c->t_first = pts[0].time, c->t_last = pts[n - 1].time;
   WC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (shard_upload(c)) return wc_comm_check(c);
   return WC_OK;
 }
 

@@ -101,6 +101,10 @@ class Context:
         all_handles = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world * 64)
         self.check(self.lib.wc_comm_connect(self._h, rank, world, T.ptr(all_handles)), "wc_comm_connect")
 
+    def comm_shard_upload(self, on=True):
+        """sweep uploads become collective: each rank copies its 1/world slab over PCIe, the rest comes from the peers"""
+        self.check(self.lib.wc_comm_shard_upload(self._h, 1 if on else 0), "wc_comm_shard_upload")
+
     def comm_disconnect(self):
         self.check(self.lib.wc_comm_disconnect(self._h), "wc_comm_disconnect")
 
