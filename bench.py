@@ -497,7 +497,7 @@ def main():
             # claims the prefetched copy of `cur` (first step: plain upload); the fixed window is uploaded once and then stays
             # on the device, as it does in the reference between two ShrinkToFit calls
             rp2 = od.ResidentPass(cur, w.imu, w.samples, fix_p, ctx=ctx2, keep_fix=turn[0] > 1)
-            ctx2.prefetch(nxt)                                              # H2D of the next sweep, overlapped with this pass
+            ctx2.prefetch(nxt, at_solve=True)                               # H2D of the next sweep, beside the solve stage of this pass
             x2, sg2, st2 = rp2.run()                                        # D2H: corrections + summary
             torch.cuda.synchronize()                                        # (includes the copy stream)
             dt = time.perf_counter() - t0
@@ -509,7 +509,7 @@ def main():
         serial["api"] = "wc_points_upload + wc_pass_upload + wc_window_pass_resident (host buffers in, corrections out)"
         e2e = measure(e2e_stream_step)
         e2e["api"] = ("wc_points_upload + wc_pass_upload + wc_points_prefetch(next sweep) + wc_window_pass_resident: host buffers in, "
-                      "corrections out; the copy of sweep k+1 overlaps the pass of sweep k (one 96 MB upload and one result "
+                      "corrections out; the copy of sweep k+1 runs beside the solve stage of sweep k's pass (one 96 MB upload and one result "
                       "read-back per step, all inside the timed region); the fixed window stays resident after the first step")
         e2e["serial"] = serial
         if world == 1:

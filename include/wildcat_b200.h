@@ -217,11 +217,15 @@ wc_status wc_build_surfels(wc_ctx* ctx, const wc_point48* pts, size_t n, wc_surf
  * extraction repeatedly without host traffic.  Results stay on the device until fetched. */
 wc_status wc_points_upload(wc_ctx* ctx, const wc_point48* pts, size_t n);
 /* Streaming ingestion (no reference counterpart: the reference processes one rosbag message at a time,
- * wildcat_slam_node.cc:83-99): starts the host-to-device copy of the NEXT sweep on a copy stream and returns at once, so
- * that it overlaps the window pass of the current sweep; the NEXT wc_points_upload, if it names the same (pts, n), finds
- * the points on the device (any other upload drops the prefetch).  pts must stay valid and unchanged until that call;
- * pinned memory (wc_host_alloc) makes the copy asynchronous. */
-wc_status wc_points_prefetch(wc_ctx* ctx, const wc_point48* pts, size_t n);
+ * wildcat_slam_node.cc:83-99): copies the NEXT sweep to the device on a copy stream while the window pass of the current
+ * sweep runs; the NEXT wc_points_upload, if it names the same (pts, n), finds the points on the device (any other upload
+ * drops the prefetch).  pts must stay valid and unchanged until that call; pinned memory (wc_host_alloc) makes the copy
+ * asynchronous.  when: WC_PREFETCH_NOW starts the copy at once; WC_PREFETCH_AT_SOLVE starts it when the next
+ * wc_window_pass_resident reaches its solve stage (the memory-bound extraction and matching stages are slowed by a
+ * transfer running beside them, the solve is not); if no pass runs before the upload, the upload copies normally. */
+#define WC_PREFETCH_NOW 0
+#define WC_PREFETCH_AT_SOLVE 1
+wc_status wc_points_prefetch(wc_ctx* ctx, const wc_point48* pts, size_t n, int when);
 wc_status wc_build_surfels_resident(wc_ctx* ctx, size_t* n_out, double* gpu_ms_keys,
                                     double* gpu_ms_emit, double* gpu_ms_total);
 wc_status wc_surfels_fetch(wc_ctx* ctx, wc_surfel* out, size_t cap, size_t* n_out);

@@ -196,3 +196,26 @@ def test_prefetched_sweep_equals_plain_upload(od, ctx):
     n_half, _ = half.extract()
     plain_half = od.ResidentSweep(np.array(b), ctx=ctx)
     assert plain_half.extract()[0] == n_half and half.fetch().tobytes() == plain_half.fetch().tobytes()
+
+
+def test_prefetch_at_solve_is_issued_by_the_pass(od, ctx):
+    """WC_PREFETCH_AT_SOLVE: the copy of the next sweep starts when the window pass reaches its solve stage; the next
+    pass claims it and gives the same result; without a pass in between the upload copies the sweep itself."""
+    w = S.make_window("C2")
+    fix = od.UpdateSurfelPoses(w.fix_imu, od.BuildSurfels(w.fix_points, ctx=ctx), ctx=ctx)
+    a = ctx.pinned(len(w.points), T.POINT48)
+    a[:] = w.points
+    b = ctx.pinned(len(w.points), T.POINT48)
+    b[:] = w.points
+    rp = od.ResidentPass(a, w.imu, w.samples, fix, ctx=ctx)
+    ctx.prefetch(b, at_solve=True)
+    x1, s1, st1 = rp.run()                      # issues the copy of b beside its solve
+    rp2 = od.ResidentPass(b, w.imu, w.samples, None, ctx=ctx, keep_fix=True)   # finds b on the device
+    x2, s2, st2 = rp2.run()
+    assert st2.n_surfels == st1.n_surfels and st2.n_sld_corr == st1.n_sld_corr and st2.n_fix_corr == st1.n_fix_corr
+    assert s2.num_iterations == s1.num_iterations
+    np.testing.assert_allclose(x2, x1, rtol=0, atol=1e-9)
+    ctx.prefetch(a, at_solve=True)              # no pass follows: the upload below copies the sweep itself
+    rs = od.ResidentSweep(a, ctx=ctx)
+    n, _ = rs.extract()
+    assert n == st1.n_surfels

@@ -53,7 +53,7 @@ def load():
     lib.wc_stream.restype = vp
     lib.wc_build_surfels.argtypes = [vp, vp, sz, vp, sz, P(sz), vp, P(dbl)]
     lib.wc_points_upload.argtypes = [vp, vp, sz]
-    lib.wc_points_prefetch.argtypes = [vp, vp, sz]
+    lib.wc_points_prefetch.argtypes = [vp, vp, sz, i32]
     lib.wc_comm_shard_upload.argtypes = [vp, i32]
     lib.wc_build_surfels_resident.argtypes = [vp, P(sz), P(dbl), P(dbl), P(dbl)]
     lib.wc_surfels_fetch.argtypes = [vp, vp, sz, P(sz)]

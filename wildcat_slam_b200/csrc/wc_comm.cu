@@ -253,7 +253,7 @@ extern "C" wc_status wc_comm_shard_upload(wc_ctx* c, int on) {
   if (!c) return WC_EINVAL;
   if (on && (!c->comm_ready || c->world < 2)) WC_FAIL(c, WC_ECOMM, "wc_comm_connect has not been called");
   cudaStreamSynchronize(c->stream);
-  c->prefetch_src = nullptr;  // a pending prefetch belongs to the other mode
+  c->prefetch_src = nullptr, c->defer_src = nullptr;  // a pending prefetch belongs to the other mode
   c->shard_upload = on ? 1 : 0;
   return WC_OK;
 }

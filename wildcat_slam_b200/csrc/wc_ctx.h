@@ -87,6 +87,8 @@ struct wc_ctx {
   cudaEvent_t         ev_prefetch;
   const void*         prefetch_src;  // host buffer of the prefetched sweep (nullptr: none pending)
   size_t              prefetch_n;
+  const void*         defer_src;     // prefetch requested for the solve stage of the next window pass, not issued yet
+  size_t              defer_n;
   float4*             d_xyz;      // resident points
   double*             d_time;
   size_t              n_pts;

@@ -1026,26 +1026,35 @@ static wc_slot_planes slot_planes(const wc_ctx* c) {
   return wc_slot_planes{(unsigned long long*)b, (int4*)(b + 8 * n), (int4*)(b + 40 * n), (int4*)(b + 72 * n)};
 }
 
-// Streaming ingestion: start copying the NEXT sweep into a second staging buffer on a dedicated copy stream and return at
-// once.  The caller runs the current window pass meanwhile; the wc_points_upload of that same buffer then finds the data
-// already on the device (it only waits for the copy's event).  pts must stay valid and unchanged until that upload, and
-// should be pinned memory (wc_host_alloc) for the copy to be truly asynchronous.  Only the NEXT wc_points_upload can claim
-// a prefetch; one that is not claimed is dropped.
-extern "C" wc_status wc_points_prefetch(wc_ctx* c, const wc_point48* pts, size_t n) {
-  if (!c || (!pts && n)) return WC_EINVAL;
-  if (n > (size_t)c->prm.max_points) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_points=%lld", n, (long long)c->prm.max_points);
-  wc_status s = extract_alloc(c);
-  if (s) return s;
-  c->prefetch_src = nullptr;
-  if (n == 0) return WC_OK;
+// The background copy goes out in pieces: the pass that runs meanwhile reads a few small results back between its stages,
+// and a copy engine works through its queue in order — behind one 96 MB transfer such a read-back would wait up to 2 ms.
+static wc_status copy_chunked(wc_ctx* c, wc_point48* dst, const wc_point48* src, size_t n) {
+  static const long long chunk_mb = getenv("WC_PREFETCH_CHUNK_MB") ? atoll(getenv("WC_PREFETCH_CHUNK_MB")) : 1;
+  const size_t per = chunk_mb > 0 ? (size_t)chunk_mb * (1u << 20) / sizeof(wc_point48) : n;
+  for (size_t i = 0; i < n; i += per) {
+    const size_t m = n - i < per ? n - i : per;
+    WC_CUDA(c, cudaMemcpyAsync(dst + i, src + i, m * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  return WC_OK;
+}
+
+// Streaming ingestion: copy the NEXT sweep into a second staging buffer on a dedicated copy stream while the current window
+// pass runs; the wc_points_upload of that same buffer then finds the data already on the device (it only waits for the
+// copy's event).  pts must stay valid and unchanged until that upload, and should be pinned memory (wc_host_alloc) for the
+// copy to be truly asynchronous.  Only the NEXT wc_points_upload can claim a prefetch; one that is not claimed is dropped.
+// when = WC_PREFETCH_NOW: the copy starts at once.  when = WC_PREFETCH_AT_SOLVE: it starts when the next
+// wc_window_pass_resident reaches its solve stage — extraction and matching are memory bound and lose 0.45 ms at C3 to a
+// transfer running beside them, the latency-bound solve (2.2 ms >= the 1.9 ms copy) loses nothing; without a pass before
+// the upload, the upload simply copies the sweep itself.
+static wc_status prefetch_issue(wc_ctx* c, const wc_point48* pts, size_t n) {
+  wc_status s = WC_OK;
   if (!c->copy_stream) {
     WC_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     WC_CUDA(c, cudaEventCreateWithFlags(&c->ev_prefetch, cudaEventDisableTiming));
   }
   if (!shard_upload(c) && !c->d_raw_next) WC_CUDA(c, cudaMalloc(&c->d_raw_next, (size_t)c->prm.max_points * sizeof(wc_point48)));
-  // the buffer may still be the source of the previous upload's repack on the main stream
-  WC_CUDA(c, cudaEventRecord(c->ev_prefetch, c->stream));
-  WC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_prefetch, 0));
+  // (no dependency on the main stream: the staging buffer written here was last read by the repack of an upload that
+  //  synchronised the stream before it returned; the exported raw areas are protected by the flag protocol)
   if (shard_upload(c)) {
     // only this rank's slab crosses PCIe, into this rank's exported raw area of the next epoch (every peer has finished
     // reading that area: it signalled the epoch in between after its repack)
@@ -1053,13 +1062,35 @@ extern "C" wc_status wc_points_prefetch(wc_ctx* c, const wc_point48* pts, size_t
     slab_of(c, n, c->rank, &lo, &hi);
     c->prefetch_epoch = ++c->raw_epoch;
     wc_point48* area  = (wc_point48*)wc_comm_raw_area(c, c->prefetch_epoch);
-    if (hi > lo) WC_CUDA(c, cudaMemcpyAsync(area + lo, pts + lo, (hi - lo) * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+    if ((s = copy_chunked(c, area + lo, pts + lo, hi - lo))) return s;
   } else {
-    WC_CUDA(c, cudaMemcpyAsync(c->d_raw_next, pts, n * sizeof(wc_point48), cudaMemcpyHostToDevice, c->copy_stream));
+    if ((s = copy_chunked(c, (wc_point48*)c->d_raw_next, pts, n))) return s;
   }
   WC_CUDA(c, cudaEventRecord(c->ev_prefetch, c->copy_stream));
   c->prefetch_src = pts, c->prefetch_n = n;
   return WC_OK;
+}
+
+extern "C" wc_status wc_points_prefetch(wc_ctx* c, const wc_point48* pts, size_t n, int when) {
+  if (!c || (!pts && n) || (when != WC_PREFETCH_NOW && when != WC_PREFETCH_AT_SOLVE)) return WC_EINVAL;
+  if (n > (size_t)c->prm.max_points) WC_FAIL(c, WC_ECAPACITY, "n=%zu exceeds max_points=%lld", n, (long long)c->prm.max_points);
+  wc_status s = extract_alloc(c);
+  if (s) return s;
+  c->prefetch_src = nullptr, c->defer_src = nullptr;
+  if (n == 0) return WC_OK;
+  if (when == WC_PREFETCH_AT_SOLVE) {
+    c->defer_src = pts, c->defer_n = n;
+    return WC_OK;
+  }
+  return prefetch_issue(c, pts, n);
+}
+
+// called by the window pass when its solve stage is about to be enqueued
+wc_status wc_points_prefetch_deferred(wc_ctx* c) {
+  if (!c->defer_src) return WC_OK;
+  const wc_point48* pts = (const wc_point48*)c->defer_src;
+  c->defer_src          = nullptr;
+  return prefetch_issue(c, pts, c->defer_n);
 }
 
 extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n) {
@@ -1073,6 +1104,7 @@ extern "C" wc_status wc_points_upload(wc_ctx* c, const wc_point48* pts, size_t n
   // drops it, so a stale copy can never be mistaken for a later buffer that happens to live at the same address
   const bool claimed = c->prefetch_src == pts && c->prefetch_n == n;
   c->prefetch_src    = nullptr;
+  c->defer_src       = nullptr;  // a prefetch still waiting for a pass's solve stage: this upload copies the sweep itself
   if (shard_upload(c)) {
     // Collective over the ranks (every rank uploads the same sweep): this rank copies its slab into its exported raw area
     // (or finds it there, prefetched), one flag round, then every point is repacked straight from its owner's area.

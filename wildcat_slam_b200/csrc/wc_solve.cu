@@ -2191,6 +2191,8 @@ static void fill_summary(const wc_ctx* c, const LMState* s, wc_solve_summary* su
     sum->iter_cost[i] = s->iter_cost[i], sum->iter_radius[i] = s->iter_radius[i], sum->iter_accepted[i] = s->iter_accepted[i];
 }
 
+wc_status wc_points_prefetch_deferred(wc_ctx* c);  // wc_extract.cu
+
 extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* opts, wc_solve_summary* summary,
                                               double* data_cor_out) {
   if (!c || !c->d_lm || c->K < 2) return WC_EINVAL;
@@ -2284,6 +2286,9 @@ extern "C" wc_status wc_window_solve_resident(wc_ctx* c, const wc_solve_opts* op
       else if ((s = enqueue_batch())) return s;
     }
     ahead = 1;
+    // the LM iterations are enqueued and the host is about to wait for them: the sweep announced by
+    // wc_points_prefetch(..., WC_PREFETCH_AT_SOLVE) starts crossing PCIe now, beside the solve (no-op when none is pending)
+    if ((s = wc_points_prefetch_deferred(c))) return s;
     WC_CUDA(c, cudaMemcpyAsync(m->h_st, m->st, sizeof(LMState), cudaMemcpyDeviceToHost, st));
     WC_CUDA(c, cudaStreamSynchronize(st));
     if ((s = pack_error(c, m->h_perr[0]))) return s;

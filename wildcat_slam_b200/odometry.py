@@ -81,15 +81,16 @@ class Context:
     def stream(self):
         return self.lib.wc_stream(self._h)
 
-    def prefetch(self, cloud):
-        """wc_points_prefetch: start the host-to-device copy of the NEXT sweep (it overlaps whatever runs meanwhile); the
-        upload of the same array (ResidentSweep / ResidentPass / WindowOdometry) then finds it on the device.  `cloud`
-        must be a contiguous POINT48 array — pinned (Context.pinned) for a truly asynchronous copy — left untouched until
-        that upload."""
+    def prefetch(self, cloud, at_solve=False):
+        """wc_points_prefetch: host-to-device copy of the NEXT sweep beside whatever runs meanwhile; the upload of the same
+        array (ResidentSweep / ResidentPass / ResidentWindows) then finds it on the device.  at_solve: the copy starts when
+        the next window pass reaches its solve stage (it would slow the memory-bound extraction and matching stages).
+        `cloud` must be a contiguous POINT48 array — pinned (Context.pinned) for a truly asynchronous copy — left untouched
+        until that upload."""
         if cloud.dtype != T.POINT48 or not cloud.flags["C_CONTIGUOUS"]:
             raise ValueError("prefetch needs a contiguous POINT48 array (the upload must see the same buffer)")
         self._prefetched = cloud  # keeps the buffer alive
-        self.check(self.lib.wc_points_prefetch(self._h, T.ptr(cloud), len(cloud)), "wc_points_prefetch")
+        self.check(self.lib.wc_points_prefetch(self._h, T.ptr(cloud), len(cloud), 1 if at_solve else 0), "wc_points_prefetch")
 
     # ---- multi-GPU residual sharding -------------------------------------------------------------------------
     def comm_export(self):
