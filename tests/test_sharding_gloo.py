@@ -69,3 +69,21 @@ def test_two_rank_sharded_normal_equations(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_sweep_slab_owner_matches_the_block_partition():
+    """the owner lookup of the sharded sweep upload (one guess + one correction step, as in repack_points_sharded) agrees
+    with the block partition shard_range for every point, also when slabs are empty (n < world) or uneven"""
+    from wildcat_slam_b200 import sharding
+
+    rng = np.random.default_rng(5)
+    cases = [(1, 2), (3, 8), (7, 8), (8, 8), (9, 8), (100_003, 3), (2_000_000, 8), (393_216, 7)]
+    cases += [(int(rng.integers(1, 50_000)), int(rng.integers(2, 9))) for _ in range(40)]
+    for n, world in cases:
+        i = np.arange(n) if n <= 200_000 else rng.integers(0, n, 200_000)
+        owner = sharding.slab_owner(i, n, world)
+        lo = np.array([sharding.shard_range(n, r, world)[0] for r in range(world)] + [n])
+        want = np.searchsorted(lo, i, side="right") - 1
+        # empty slabs share a boundary: the partition's owner is the LAST rank starting at or before i
+        assert np.array_equal(lo[owner] <= i, np.ones_like(i, bool)) and np.array_equal(i < lo[owner + 1], np.ones_like(i, bool)), (n, world)
+        assert np.array_equal(owner, want), (n, world)

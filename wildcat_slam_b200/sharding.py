@@ -15,6 +15,20 @@ def split_corrs(sld_corr, fix_corr, rank, world):
     return sld_corr[min(c0, ns):min(c1, ns)], fix_corr[max(c0 - ns, 0):max(c1 - ns, 0)]
 
 
+def slab_owner(i, n, world):
+    """rank whose slab of a sharded sweep upload holds point i (wc_comm_shard_upload: rank r copies points
+    [n r // world, n (r + 1) // world); repack_points_sharded, wc_extract.cu, finds the owner the same way: first guess
+    i world // n, then steps down / up until the slab brackets i — more than one step only when slabs are empty)."""
+    i = np.asarray(i, dtype=np.int64)
+    r = (i * world) // n
+    lo = lambda q: (n * q) // world  # noqa: E731
+    for _ in range(world):
+        r = np.where((r > 0) & (i < lo(r)), r - 1, r)
+    for _ in range(world):
+        r = np.where((r + 1 < world) & (i >= lo(np.minimum(r + 1, world))), r + 1, r)
+    return r
+
+
 def exchange_handles(handle, dist, device=None):
     """all-gather of the 64-byte exchange-buffer handles; returns a (world, 64) uint8 array identical on every rank."""
     import torch
