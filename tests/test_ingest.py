@@ -92,3 +92,44 @@ def test_device_unpack_matches_host_mapping():
         assert len(od.FilterPoints(g, flt, ctx=ctx)) <= len(g)
     finally:
         ctx.close()
+
+
+def test_imu_resampler_known_answer_of_the_reference():
+    """src/sensor/imu_resampler_test.cc:7-31 — 10 Hz re-sampling of two samples one second apart: timestamps 0, 0.1, 0.2
+    (compared with EXPECT_EQ upstream, i.e. exactly) and the 0.8 / 0.2 interpolation weights of the third sample"""
+    ir = I.ImuResampler(10)
+    acc1, gyr1 = np.array([1.0, 2.0, 3.0]), np.array([435.0, 342.0, 434.0])      # ImuData{t, linear_acceleration, angular_velocity}
+    acc2, gyr2 = np.array([11.0, 234.0, 453.0]), np.array([234.0, 46.0, 32.0])
+    ir.add(0, acc1, gyr1)
+    assert ir.advance() is None                                               # one sample only: nothing yet (:24)
+    ir.add(1, acc2, gyr2)
+    t, a, g = ir.advance()
+    assert t == 0 and np.array_equal(a, acc1) and np.array_equal(g, gyr1)
+    t, a, g = ir.advance()
+    assert t == 0.1
+    t, a, g = ir.advance()
+    assert t == 0.2
+    np.testing.assert_allclose(g, 0.8 * gyr1 + 0.2 * gyr2, rtol=1e-12)         # isApprox upstream
+    np.testing.assert_allclose(a, 0.8 * acc1 + 0.2 * acc2, rtol=1e-12)
+
+
+def test_imu_resampler_stream_follows_the_node():
+    """one add + one advance per message (wildcat_slam_node.cc:30-44): a 400 Hz recording re-sampled to 200 Hz gives a
+    uniform 5 ms grid that the state prediction's spacing check accepts; a bracket that does not contain the next instant
+    yields nothing, and the queue never holds more than two samples"""
+    rng = np.random.default_rng(2)
+    n = 2000
+    t = 100.0 + np.cumsum(rng.uniform(0.0023, 0.0027, n))                      # ~400 Hz with jitter
+    acc, gyr = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    ts, a, g = I.resample_imu(t, acc, gyr, 200)
+    assert ts[0] == t[0] and len(ts) > 0.45 * n
+    np.testing.assert_allclose(np.diff(ts), 0.005, rtol=0, atol=1e-9)
+    k = 7                                                                        # every sample is a lerp of its bracket
+    j = np.searchsorted(t, ts[k], side="right") - 1
+    f = (ts[k] - t[j]) / (t[j + 1] - t[j])
+    np.testing.assert_allclose(a[k], (1 - f) * acc[j] + f * acc[j + 1], rtol=1e-9, atol=1e-12)
+    slow = I.ImuResampler(200)                                                   # raw data slower than the grid: stalls like upstream
+    slow.add(0.0, acc[0], gyr[0]); slow.add(1.0, acc[1], gyr[1])
+    assert slow.advance()[0] == 0.0 and slow.advance()[0] == 0.005
+    slow.add(1.5, acc[2], gyr[2])                                                # bracket [1, 1.5] does not contain 0.01
+    assert slow.advance() is None and len(slow.pair) == 2

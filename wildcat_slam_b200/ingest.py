@@ -11,7 +11,11 @@ sensor_msgs/PointCloud2 and sensor_msgs/Imu (wildcat_slam_node.cc:30-52,83-99), 
                                     rosbag::View on an unfiltered bag).  The writer exists for tests and for exporting
                                     synthetic sweeps.
 
-The numeric path of the payload (field extraction) runs on the GPU; everything here is header parsing.
+  * ImuResampler                    the fixed-rate IMU re-sampling between the bag and LidarOdometry::AddImuData
+                                    (src/sensor/imu_resampler.h:12-53, HandleImuMessage wildcat_slam_node.cc:30-44)
+
+The numeric path of the payload (field extraction) runs on the GPU; everything here is header parsing and O(200 Hz) host
+logic.
 """
 import bz2
 import struct
@@ -326,3 +330,51 @@ class BagWriter:
         self.flush()
         self._write_bag_header()
         self.f.close()
+
+
+# ---- fixed-rate IMU re-sampling ---------------------------------------------------------------------------------------
+class ImuResampler:
+    """src/sensor/imu_resampler.h:12-53.  Keeps the two most recent raw samples; every call of advance() yields at most one
+    sample of the fixed-rate sequence: the first raw sample itself, then t_prev + 1 / freq whenever that instant lies
+    inside the bracket of the two raw samples (both ends inclusive), linearly interpolated.  A bracket that does not
+    contain the next instant yields nothing (the caller feeds the next raw sample and asks again, as HandleImuMessage does,
+    wildcat_slam_node.cc:30-44) — so with raw data slower than 2 x freq the sequence stalls, exactly like upstream."""
+
+    def __init__(self, freq):
+        self.period = 1.0 / freq  # the reference divides 1.0 by the int rate on every call: the same double
+        self.pair = []            # [(t, acc[3], gyr[3])], at most two
+        self.t_prev = None
+
+    def add(self, t, acc, gyr):
+        """AddImuData (:16-21)"""
+        self.pair.append((float(t), np.asarray(acc, dtype=np.float64), np.asarray(gyr, dtype=np.float64)))
+        del self.pair[:-2]
+
+    def advance(self):
+        """AdvanceGetResampledImuData (:23-46): (t, acc, gyr) or None"""
+        if len(self.pair) < 2:
+            return None
+        (t0, a0, g0), (t1, a1, g1) = self.pair
+        if self.t_prev is None:
+            self.t_prev = t0
+            return t0, a0.copy(), g0.copy()
+        t = self.t_prev + self.period
+        if not (t0 <= t <= t1):
+            return None
+        f = (t - t0) / (t1 - t0)
+        self.t_prev = t
+        return t, (1 - f) * a0 + f * a1, (1 - f) * g0 + f * g1
+
+
+def resample_imu(stamps, acc, gyr, freq):
+    """HandleImuMessage over a whole recording (wildcat_slam_node.cc:30-44): one add + ONE advance per raw message, as the
+    node does.  Returns (t[M], acc[M, 3], gyr[M, 3]) of what LidarOdometry::AddImuData would have received."""
+    r, out = ImuResampler(freq), []
+    for t, a, g in zip(stamps, acc, gyr):
+        r.add(t, a, g)
+        s = r.advance()
+        if s is not None:
+            out.append(s)
+    if not out:
+        return np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3))
+    return np.array([o[0] for o in out]), np.stack([o[1] for o in out]), np.stack([o[2] for o in out])
