@@ -272,4 +272,57 @@ inline void ApplyCorrections(std::deque<SampleState::Ptr>& sample_states, std::d
   for (size_t i = 0; i < imu.size(); ++i) std::memcpy(static_cast<void*>(&imu_states[i]), &imu[i], sizeof(wc_imu_state));
 }
 
+// ---- streaming ingestion (no reference counterpart: wildcat_slam_node.cc:83-99 hands the bag over message by message) ------
+// Announce the NEXT sweep before the window pass of the current one: its host-to-device copy then runs beside that pass's
+// solve stage (at_solve) or starts at once, and the next BuildSurfels / wc_points_upload of the same vector finds the points
+// on the device.  The vector must stay untouched until then.
+inline void PrefetchSweep(const std::vector<Point>& next_sweep, bool at_solve = true, Context& ctx = Context::Default()) {
+  ctx.Check(wc_points_prefetch(ctx.get(), next_sweep.data(), next_sweep.size(), at_solve ? WC_PREFETCH_AT_SOLVE : WC_PREFETCH_NOW),
+            "PrefetchSweep");
+}
+
+// ---- ImuResampler, src/sensor/imu_resampler.h:12-53 (host logic at the IMU rate; same interface) ---------------------------
+struct ImuData {  // common.h:31-35
+  double   timestamp;
+  Vector3d linear_acceleration;
+  Vector3d angular_velocity;
+};
+
+class ImuResampler {
+ public:
+  explicit ImuResampler(int freq) : period_(1.0 / freq) {}
+
+  void AddImuData(const ImuData& d) {  // the bracket: the two most recent raw samples
+    if (have_ == 2) raw_[0] = raw_[1], have_ = 1;
+    raw_[have_++] = d;
+  }
+
+  // one sample of the fixed-rate sequence, or nullptr: the first raw sample itself, afterwards t_prev + 1 / freq whenever
+  // that instant lies inside the bracket (ends included), linearly interpolated
+  std::shared_ptr<ImuData> AdvanceGetResampledImuData() {
+    if (have_ < 2) return nullptr;
+    if (!started_) {
+      started_ = true, t_prev_ = raw_[0].timestamp;
+      return std::make_shared<ImuData>(raw_[0]);
+    }
+    const double t = t_prev_ + period_;
+    if (t < raw_[0].timestamp || t > raw_[1].timestamp) return nullptr;
+    const double f = (t - raw_[0].timestamp) / (raw_[1].timestamp - raw_[0].timestamp);
+    auto         out = std::make_shared<ImuData>();
+    out->timestamp   = t;
+    for (int k = 0; k < 3; ++k) {
+      out->linear_acceleration[k] = (1 - f) * raw_[0].linear_acceleration[k] + f * raw_[1].linear_acceleration[k];
+      out->angular_velocity[k]    = (1 - f) * raw_[0].angular_velocity[k] + f * raw_[1].angular_velocity[k];
+    }
+    t_prev_ = t;
+    return out;
+  }
+
+ private:
+  ImuData raw_[2];
+  int     have_    = 0;
+  bool    started_ = false;
+  double  period_, t_prev_ = 0.0;
+};
+
 }  // namespace wildcat_b200

@@ -36,6 +36,21 @@ def test_mirror_compiles_and_links(tmp_path):
     assert r.returncode == 1 and "cannot open" in r.stderr  # fails on its inputs, before any device call
 
 
+def test_cpp_imu_resampler_known_answer_of_the_reference(tmp_path):
+    """tests/cpp/resampler_test.cc replays src/sensor/imu_resampler_test.cc:7-31 on the C++ mirror's ImuResampler (host only)"""
+    exe = str(tmp_path / "resampler_test")
+    libdir = os.path.dirname(abi.SO_PATH)
+    if not os.path.exists(abi.SO_PATH):
+        from wildcat_slam_b200 import build
+
+        build.build()
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "resampler_test.cc"), "-o", exe, "-L", libdir, "-l:libwildcat_b200.so",
+                           f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "resampler_test ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_mirror_pipeline_equals_python_mirror(tmp_path):
     from wildcat_slam_b200 import odometry as od
